@@ -1,0 +1,75 @@
+"""ctypes binding of the in-tree C-ABI library (include/m3l_b200.h).
+
+There is no CPU fallback: if the shared object is missing, or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libm3l_b200.so"
+_lib = None
+
+
+class M3LError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p),
+        ("lda", C.c_int32), ("ldb", C.c_int32),
+        ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("splits", C.c_int32), ("bn", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int32), ("out_mode", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int32),
+        ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p),
+        ("ld_aux", C.c_int32), ("alpha", C.c_float),
+    ]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads libm3l_b200.so (building it first if M3L_B200_AUTOBUILD=1 and it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        if os.environ.get("M3L_B200_AUTOBUILD", "0") == "1":
+            from . import build as _build
+
+            _build.build(verbose=False)
+        else:
+            raise M3LError(
+                f"{_LIB_PATH} not found: the CUDA extension is not built. Run "
+                "`python -m m3l_b200.build` (or __graft_entry__.build()); there is no CPU fallback."
+            )
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.m3l_last_error.restype = C.c_char_p
+    lib.m3l_last_error.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().m3l_last_error().decode("utf-8", "replace")
+        raise M3LError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t) -> C.c_void_p:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def current_stream() -> C.c_void_p:
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,369 @@
+// m3l_b200 — persistent warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )
+//
+// This one kernel serves every dense contraction of the VTMAE step that the reference hands to
+// cuBLAS through nn.Linear (vit_pytorch Attention.to_qkv / to_out / FeedForward.net, the patch
+// embedding Linear and the to_pixels / to_tactiles heads: /root/reference/models/
+// pretrain_models.py:113-116,766-779,784) and their autograd dgrad / wgrad products:
+//   * forward and dgrad: both operands K-major (activations [M,K]; weights [N,K], or the bf16
+//     transposed shadow copy of the weight for dgrad);
+//   * wgrad dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major (the contraction runs over
+//     the token rows), split-K over the token dimension, fp32 vector red.add into the grad arena.
+//
+// Structure (one CTA per SM, persistent over a static round-robin tile schedule):
+//   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier tx)
+//   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BN x 16), fp32 accum in TMEM,
+//                              tcgen05.commit frees smem stages / publishes the accumulator
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> regs -> swizzled smem transpose -> coalesced
+//                              16-byte global accesses; bias / GELU / GELU' / residual fused
+// TMEM holds two accumulators (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1 (K is only 256 for most of these GEMMs: SURVEY.md §7.3 hard part 2).
+#include "common.cuh"
+#include "m3l_internal.h"
+
+namespace m3l {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
+constexpr int kStagingBytesPerWarp = 32 * 128;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes =
+      1024 /*align slack*/ + kStages * kStageBytes + kNumEpiWarps * kStagingBytesPerWarp + 256;
+};
+
+struct alignas(8) GemmBarriers {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+M3L_DEVINL void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  GemmBarriers* bars =
+      reinterpret_cast<GemmBarriers*>(staging + kNumEpiWarps * kStagingBytesPerWarp);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const int num_items = tiles_m * tiles_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer ---------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int t = item / p.splits;
+        const int n0 = (t % tiles_n) * BN;
+        const int m0 = (t / tiles_n) * BM;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &map_a, &bars->full[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &map_a, &bars->full[stage], m0 + 64 * j, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &map_b, &bars->full[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &map_b, &bars->full[stage], n0 + 64 * j, kb * BK);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -----------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int split = item % p.splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kb_total);
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[buf], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -------------------------------------------
+    const int ew = warp - 2;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int col_half = ew >> 2;              // which half of the BN columns
+    constexpr int kChunks = BN / 64;           // 32-column chunks per warp
+    uint8_t* stg = staging + ew * kStagingBytesPerWarp;
+    const uint32_t stg_u32 = smem_u32(stg);
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int t = item / p.splits;
+      const int n0 = (t % tiles_n) * BN;
+      const int m0 = (t / tiles_n) * BM;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&bars->tmem_full[buf], acc_phase);
+      tc_fence_after_sync();
+      const int row_base = m0 + quad * 32;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int col0 = (col_half * kChunks + c) * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + col0, v);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // all TMEM reads of this warp for this accumulator are done -> hand it back early
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]),
+                       "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        const int cc = lane & 7;
+        const int gcol = n0 + col0 + cc * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (lane >> 3) + 4 * i;
+          const int grow = row_base + r;
+          float4 a;
+          const uint32_t addr = stg_u32 + r * 128 + ((cc ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                       : "r"(addr)
+                       : "memory");
+          if (grow < p.M && gcol < p.N) {
+            a.x *= p.alpha; a.y *= p.alpha; a.z *= p.alpha; a.w *= p.alpha;
+            if (p.bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + gcol);
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (p.act == 1) {
+              if (p.aux_out != nullptr) {
+                uint2 pk = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+                *reinterpret_cast<uint2*>(p.aux_out + (size_t)grow * p.ld_aux + gcol) = pk;
+              }
+              a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+            } else if (p.act == 2) {
+              const uint2 pk =
+                  *reinterpret_cast<const uint2*>(p.aux_in + (size_t)grow * p.ld_aux + gcol);
+              const float2 p0 = unpack_bf16x2(pk.x), p1 = unpack_bf16x2(pk.y);
+              a.x *= gelu_erf_grad(p0.x); a.y *= gelu_erf_grad(p0.y);
+              a.z *= gelu_erf_grad(p1.x); a.w *= gelu_erf_grad(p1.y);
+            }
+            if (p.residual != nullptr) {
+              const uint2 pk =
+                  *reinterpret_cast<const uint2*>(p.residual + (size_t)grow * p.ldr + gcol);
+              const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
+              a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+            }
+            if (p.out_mode == 0) {
+              uint2 pk = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo +
+                                        gcol) = pk;
+            } else if (p.out_mode == 1) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo +
+                                         gcol) = a;
+            } else {
+              red_add_v4(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol, a);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& p, int grid,
+                   cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    M3L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+}  // namespace
+
+int gemm_pick_bn(int M, int N) {
+  const int sms = device_sm_count();
+  const int tiles_m = (M + BM - 1) / BM;
+  if (N % 256 == 0 && tiles_m * (N / 256) >= sms) return 256;
+  if (N >= 128 && tiles_m * ((N + 127) / 128) >= sms / 2) return 128;
+  if (N % 128 == 0 && N >= 512) return 128;
+  return N >= 128 && (N % 128 == 0) ? 128 : 64;
+}
+
+int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
+  GemmArgs p = args;
+  M3L_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
+  M3L_REQUIRE(p.N % 8 == 0, "gemm: N=%d must be a multiple of 8", p.N);
+  M3L_REQUIRE(p.a_mn_major == p.b_mn_major,
+              "gemm: mixed operand majors are not instantiated (a=%d b=%d)", p.a_mn_major,
+              p.b_mn_major);
+  M3L_REQUIRE(p.out != nullptr && p.a != nullptr && p.b != nullptr, "gemm: null pointer");
+  if (p.splits < 1) p.splits = 1;
+  const int kb_total = (p.K + BK - 1) / BK;
+  if (p.splits > kb_total) p.splits = kb_total;
+  // every split must own at least one k-block
+  while (p.splits > 1 && ((kb_total + p.splits - 1) / p.splits) * (p.splits - 1) >= kb_total)
+    --p.splits;
+  M3L_REQUIRE(p.splits == 1 || p.out_mode == 2, "gemm: split-K requires the atomic output mode");
+  if (bn == 0) bn = gemm_pick_bn(p.M, p.N);
+  M3L_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
+  plan->bn = bn;
+  plan->args = p;
+  if (!p.a_mn_major) {
+    int s = make_tmap_2d_bf16(&plan->map_a, p.a, p.M, p.K, p.lda, BM);
+    if (s) return s;
+    s = make_tmap_2d_bf16(&plan->map_b, p.b, p.N, p.K, p.ldb, bn);
+    if (s) return s;
+  } else {
+    // operands stored [K rows, M or N columns]
+    int s = make_tmap_2d_bf16(&plan->map_a, p.a, p.K, p.M, p.lda, BK);
+    if (s) return s;
+    s = make_tmap_2d_bf16(&plan->map_b, p.b, p.K, p.N, p.ldb, BK);
+    if (s) return s;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.splits;
+  plan->grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  return M3L_OK;
+}
+
+int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
+  const bool mn = plan.args.a_mn_major != 0;
+  switch (plan.bn) {
+    case 64:
+      return mn ? launch_variant<64, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
+                : launch_variant<64, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
+    case 128:
+      return mn ? launch_variant<128, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
+                : launch_variant<128, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
+    case 256:
+      return mn ? launch_variant<256, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
+                : launch_variant<256, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
+  }
+  set_last_error("gemm: BN=%d unsupported", plan.bn);
+  return M3L_ERR_INVALID;
+}
+
+}  // namespace m3l
+
+// ---------------------------------------------------------------------------------------
+// C-ABI (include/m3l_b200.h)
+// ---------------------------------------------------------------------------------------
+extern "C" int m3l_gemm_bf16(const m3l_gemm_args* a, void* stream) {
+  if (a == nullptr) return m3l::M3L_ERR_INVALID;
+  m3l::GemmArgs g;
+  g.a = a->a; g.b = a->b; g.lda = a->lda; g.ldb = a->ldb;
+  g.a_mn_major = a->a_mn_major; g.b_mn_major = a->b_mn_major;
+  g.M = a->m; g.N = a->n; g.K = a->k; g.splits = a->splits;
+  g.out = a->out; g.ldo = a->ldo; g.out_mode = a->out_mode;
+  g.bias = a->bias; g.residual = (const m3l::bf16*)a->residual; g.ldr = a->ldr;
+  g.act = a->act; g.aux_out = (m3l::bf16*)a->aux_out; g.aux_in = (const m3l::bf16*)a->aux_in;
+  g.ld_aux = a->ld_aux; g.alpha = a->alpha;
+  m3l::GemmPlan plan;
+  int s = m3l::gemm_make_plan(&plan, g, a->bn);
+  if (s) return s;
+  return m3l::gemm_run(plan, (cudaStream_t)stream);
+}

@@ -1,0 +1,41 @@
+// m3l_b200 — internal (C++) declarations shared by the kernels and the step engine.
+#pragma once
+
+#include "../../include/m3l_b200.h"
+#include "common.cuh"
+
+namespace m3l {
+
+// ----------------------------------------------------------------------------- GEMM (gemm.cu)
+struct GemmArgs {
+  const void* a = nullptr;  // bf16; K-major: [M, K] (lda); MN-major: [K, M] (lda)
+  const void* b = nullptr;  // bf16; K-major: [N, K] (ldb); MN-major: [K, N] (ldb)
+  int lda = 0, ldb = 0;
+  int a_mn_major = 0, b_mn_major = 0;
+  int M = 0, N = 0, K = 0;
+  int splits = 1;           // split-K (requires out_mode 2)
+  void* out = nullptr;      // [M, ldo]
+  int ldo = 0;
+  int out_mode = 0;         // 0 bf16 store, 1 fp32 store, 2 fp32 red.add
+  const float* bias = nullptr;      // [N] fp32
+  const bf16* residual = nullptr;   // [M, ldr] bf16, added after activation
+  int ldr = 0;
+  int act = 0;              // 0 none; 1 GELU (aux_out <- pre-activation); 2 multiply by GELU'(aux_in)
+  bf16* aux_out = nullptr;
+  const bf16* aux_in = nullptr;
+  int ld_aux = 0;
+  float alpha = 1.0f;
+};
+
+struct GemmPlan {
+  CUtensorMap map_a, map_b;
+  GemmArgs args;
+  int bn = 0;
+  int grid = 0;
+};
+
+int gemm_pick_bn(int M, int N);
+int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn /*0 = auto*/);
+int gemm_run(const GemmPlan& plan, cudaStream_t stream);
+
+}  // namespace m3l
