@@ -1,0 +1,70 @@
+"""CPU: the oracle restatement reproduces the golden vectors frozen from the unmodified reference."""
+import pytest
+import torch
+
+from oracle import vtmae_oracle as O
+from tests._golden import CASES, Golden
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    g = Golden(name)
+    cfg, sd, x, noise = g.cfg, g.weights(), g.inputs(), g.noise()
+    st = O.AdamWState()
+    inter = {}
+    keys = O.param_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    loss = O.vtmae_forward(sd, cfg, x, noise, intermediates=inter)
+    # integer results: bit-exact
+    assert torch.equal(inter["masked_indices"], g.t("masked_indices"))
+    assert torch.equal(inter["unmasked_indices"], g.t("unmasked_indices"))
+    # fp32 CPU vs fp32 CPU of the same op sequence: tight tolerance (summation order of in-place adds)
+    assert torch.allclose(loss.detach(), g.t("loss"), rtol=1e-6, atol=0)
+    for k in ("enc_in", "encoded", "decoded"):
+        assert torch.allclose(inter[k].detach(), g.t(k), rtol=1e-5, atol=1e-5), k
+    loss.backward()
+    present = g.grad_present()
+    for k, gn in g.grad_norms().items():
+        if not present[k]:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+        else:
+            assert abs(float(sd[k].grad.double().norm()) - gn) <= 1e-4 * max(gn, 1e-6), k
+    for k, gr in g.full_grads().items():
+        assert torch.allclose(sd[k].grad, gr, rtol=1e-4, atol=1e-7), k
+    # one clip + AdamW step
+    grads = {k: (sd[k].grad if present.get(k, True) else None) for k in keys}
+    total = O.clip_and_adamw(sd, grads, st)
+    assert torch.allclose(total, g.t("grad_total_norm"), rtol=1e-5)
+    for k, w in g.after().items():
+        assert torch.allclose(sd[k].detach(), w, rtol=1e-6, atol=1e-7), k
+    with torch.no_grad():
+        loss2 = O.vtmae_forward(sd, cfg, x, noise)
+    assert torch.allclose(loss2, g.t("loss_after_step"), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_embeddings_golden(name):
+    g = Golden(name)
+    with torch.no_grad():
+        emb = O.vtmae_embeddings(g.weights(), g.cfg, g.inputs())
+        assert torch.allclose(emb[:1], g.t("embeddings"), rtol=1e-5, atol=1e-5)
+        if g.has("embeddings_vision_only"):
+            emb = O.vtmae_embeddings(g.weights(), g.cfg, g.inputs(), use_tactile=False)
+            assert torch.allclose(emb[:1], g.t("embeddings_vision_only"), rtol=1e-5, atol=1e-5)
+
+
+def test_mask_counts_python_float_truncation():
+    # pretrain_models.py:223-227 on the canonical and the DINO-tac geometry
+    assert O.mask_counts(0.95, 64, 128, 2) == (60, 61)
+    assert O.mask_counts(0.95, 64, 0, 0) == (60, 0)
+    assert O.mask_counts(0.8, 0, 50, 2) == (0, 20)
+    assert O.mask_counts(0.75, 16, 32, 2) == (12, 12)
+
+
+def test_tie_free_noise_has_no_ties():
+    g = torch.Generator().manual_seed(0)
+    n = O.tie_free_noise(512, 192, g, [64, 64, 64])
+    for off in (0, 64, 128):
+        s = n[:, off:off + 64].sort(dim=-1).values
+        assert not (s[:, 1:] == s[:, :-1]).any()

@@ -1,0 +1,86 @@
+"""CPU, build container only: the oracle against the UNMODIFIED reference module imported through
+oracle/stubs (skipped where /root/reference does not exist, e.g. on the GPU box)."""
+import pytest
+import torch
+
+from oracle import reference_adapter as R
+from oracle import vtmae_oracle as O
+
+pytestmark = pytest.mark.skipif(not R.reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("ecm,nt,sincos", [(False, 2, True), (False, 0, True), (True, 2, True), (False, 2, False)])
+def test_forward_backward_and_embeddings_match_reference(ecm, nt, sincos):
+    cfg = O.VTMAEConfig(early_conv_masking=ecm, num_tactiles=nt, use_sincosmod_encodings=sincos,
+                        depth=2, decoder_depth=1)
+    mae = R.build_reference_model(cfg, seed=3)
+    sd_ref = mae.state_dict()
+    mine = O.expand_aliases(O.init_state_dict(cfg))
+    assert set(mine) == set(sd_ref)
+    assert all(mine[k].shape == sd_ref[k].shape for k in mine)
+    sd = O.canonical({k: v.clone() for k, v in sd_ref.items()})
+    for k, v in O.position_buffers(cfg).items():
+        assert torch.equal(v, sd_ref[k]), k
+    g = torch.Generator().manual_seed(7)
+    B = 3
+    x = {"image": torch.rand(B, 12, 64, 64, generator=g)}
+    for i in range(nt):
+        x[f"tactile{i + 1}"] = torch.rand(B, 12, 32, 32, generator=g)
+    noise = O.tie_free_noise(B, cfg.n_img + nt * cfg.n_tac, g, [64] * (1 + nt))
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    loss = O.vtmae_forward(sd, cfg, x, noise)
+    loss.backward()
+    with R.injected_noise(R.split_noise(noise, cfg, True, nt > 0)):
+        lref = mae(x)
+    lref.backward()
+    assert torch.equal(loss.detach(), lref.detach())
+    for k, p in mae.named_parameters():
+        if k not in sd:
+            continue
+        if p.grad is None:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+        else:
+            assert torch.allclose(sd[k].grad, p.grad, rtol=1e-5, atol=1e-7), k
+    with torch.no_grad():
+        assert torch.equal(O.vtmae_embeddings(sd, cfg, x), mae.get_embeddings(x, eval=False))
+        if nt:
+            assert torch.equal(O.vtmae_embeddings(sd, cfg, x, use_tactile=False),
+                               mae.get_embeddings(x, eval=False, use_tactile=False))
+
+
+def test_vt_load_matches_reference():
+    ref = R.load_reference_module()
+    import numpy as np
+    rng = np.random.default_rng(0)
+    obs = {"image": rng.random((2, 64, 64, 12), dtype=np.float32),
+           "tactile": (rng.random((2, 24, 32, 32), dtype=np.float32) * 2 - 1)}
+    a = O.vt_load({k: v.copy() for k, v in obs.items()}, frame_stack=4)
+    b = ref.vt_load({k: v.copy() for k, v in obs.items()}, frame_stack=4)
+    assert set(a) == set(b) == {"image", "tactile1", "tactile2"}
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_train_step_matches_reference_optimizer():
+    cfg = O.VTMAEConfig(depth=1, decoder_depth=1)
+    mae = R.build_reference_model(cfg, seed=5)
+    sd = O.canonical({k: v.clone() for k, v in mae.state_dict().items()})
+    g = torch.Generator().manual_seed(11)
+    x = {"image": torch.rand(2, 12, 64, 64, generator=g), "tactile1": torch.rand(2, 12, 32, 32, generator=g),
+         "tactile2": torch.rand(2, 12, 32, 32, generator=g)}
+    noise = O.tie_free_noise(2, 192, g, [64, 64, 64])
+    opt = torch.optim.AdamW(mae.parameters(), lr=1e-4)
+    st = O.AdamWState()
+    for _ in range(2):
+        opt.zero_grad()
+        with R.injected_noise(R.split_noise(noise, cfg)):
+            l = mae(x)
+        l.backward()
+        torch.nn.utils.clip_grad_norm_(mae.parameters(), 0.5)
+        opt.step()
+        lo, _, _ = O.train_step(sd, cfg, x, noise, st)
+        assert torch.allclose(lo, l.detach(), rtol=1e-6)
+    ref_sd = mae.state_dict()
+    for k in O.param_keys(sd):
+        assert torch.allclose(sd[k].detach(), ref_sd[k], rtol=1e-6, atol=1e-8), k
