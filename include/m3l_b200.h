@@ -56,6 +56,135 @@ typedef struct m3l_gemm_args {
 
 int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Mask sampling: per sample and per token segment (image, tactile1, tactile2, ...) the ascending
+ * argsort of the supplied uniform noise; the first n_masked[s] positions of each segment's
+ * permutation are "masked", the rest "unmasked"; lists are concatenated segment by segment.
+ * Replaces torch.rand(...).argsort(-1) + slicing + cat, pretrain_models.py:223-248 (the noise is an
+ * input so results can be compared bit-exactly with the reference).  Ties resolve stably.
+ *   noise            fp32 [batch, n_total]
+ *   masked           int64 [batch, sum n_masked]        (global token indices)
+ *   unmasked         int64 [batch, n_total - sum n_masked]
+ *   slot_of_token    int32 [batch, n_total] or NULL: >= 0 -> position in `unmasked`,
+ *                    < 0 -> -(1 + position in `masked`)
+ * ---------------------------------------------------------------------------------------- */
+#define M3L_MAX_SEGMENTS 8
+typedef struct m3l_mask_segments {
+  int32_t count;
+  int32_t offset[M3L_MAX_SEGMENTS];   /* first token of the segment */
+  int32_t length[M3L_MAX_SEGMENTS];   /* tokens in the segment */
+  int32_t n_masked[M3L_MAX_SEGMENTS]; /* how many of them are masked */
+} m3l_mask_segments;
+
+int m3l_mask_indices(const float* noise, int batch, int n_total, const m3l_mask_segments* segs,
+                     int64_t* masked, int64_t* unmasked, int32_t* slot_of_token, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch sources: up to 4 fp32 NCHW maps of one modality (the image, or tactile1..tactile{nt}),
+ * patchified on the fly as einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
+ * (pretrain_models.py:768,775); token_base = global index of the modality's first token.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct m3l_patch_source {
+  const float* src[4];
+  int32_t channels, height, width, patch_h, patch_w;
+  int32_t token_base;
+} m3l_patch_source;
+
+/* Fused patchify + row gather + LayerNorm(patch_dim) -> bf16 rows [batch*ncols, P]
+ * (pretrain_models.py:157,166 + the first LayerNorm of *_patch_to_emb, :769,776).
+ * Row (b, jj) reads token tok_idx[b, col0 + jj] (tok_idx NULL: token_base + jj, i.e. all tokens).
+ * xhat (optional) receives the normalised values before the affine, for the backward pass. */
+int m3l_patch_layernorm(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld,
+                        int col0, int ncols, const float* gamma, const float* beta, float eps,
+                        void* out_bf16, void* xhat_bf16, void* stream);
+
+/* LayerNorm forward over rows (nn.LayerNorm, eps 1e-5): y = LN(x) * gamma + beta
+ *   (+ add0[add0_row[r]] + add1[add1_row[r]], fp32 rows: modality / position embeddings,
+ *   pretrain_models.py:202-219).  x is bf16, or fp32 if x_fp32.  stats (optional) <- (mean, rstd)
+ *   per row.  dst_row (optional): output row remap, negative = row not written. */
+int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, const float* gamma,
+                      const float* beta, float eps, void* y_bf16, float* stats,
+                      const int32_t* dst_row, const float* add0, const int32_t* add0_row,
+                      const float* add1, const int32_t* add1_row, void* stream);
+
+/* LayerNorm backward: dx = dLN(dy) (+ skip), dgamma/dbeta += column sums (fp32 atomics).
+ * src_row (optional): dy row gather, negative = zero gradient row. */
+int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, const void* x, int x_fp32,
+                      const float* stats, int rows, int dim, const float* gamma,
+                      const void* skip_bf16, void* dx, int dx_fp32, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* Decoder input assembly (pretrain_models.py:270-307): z[b,t] = (visible ? d[b, slot] : mask_token)
+ * + add0[tok_class[t]] + add1[t].  Backward scatters / reduces the gradient accordingly. */
+int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const float* mask_token,
+                             const int32_t* slot_of_token, int batch, int n_tokens, int dim,
+                             const float* add0, const int32_t* tok_class, const float* add1,
+                             void* z_bf16, void* stream);
+int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot_of_token, int batch,
+                             int n_tokens, int dim, int n_visible, void* dd_bf16,
+                             float* dmask_token, float* dadd0, const int32_t* tok_class,
+                             float* dadd1, void* stream);
+
+/* Gradient of the broadcast embedding adds on the encoder side: dclass[slot_class[j]] += sum_b dx[b,j],
+ * dpos[row_pos[b,j]] += dx[b,j] (either may be NULL). */
+int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, int dim,
+                     const int32_t* slot_class, float* dclass, const int32_t* row_pos, float* dpos,
+                     void* stream);
+
+/* Masked-patch MSE (pretrain_models.py:327-340): target rows are gathered from the raw maps;
+ * *loss_acc += weight * sum((pred - target)^2); dpred = 2 * weight * (pred - target) (bf16). */
+int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
+                 int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
+                 void* stream);
+
+/* out[n] += sum_m x[m, n] (bias gradients). */
+int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);
+
+/* dgamma[p] += sum_r da[r,p] * xhat[r,p]; dbeta[p] += sum_r da[r,p] (patch LayerNorm parameters). */
+int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int dim, float* dgamma,
+                      float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head attention, sequence length n <= 256, dim_head == 64 (tcgen05 / TMEM / TMA).
+ * Replaces vit_pytorch Attention's softmax(q k^T * scale) v and its backward
+ * (pretrain_models.py:113,784 through vit-pytorch 1.6.4).
+ *   qkv   bf16 [batch*n, 3*heads*64]: columns [q | k | v], head h at h*64 inside each third
+ *   out   bf16 [batch*n, heads*64]   ('b h n d -> b n (h d)')
+ *   lse   fp32 [batch, heads, n]     log-sum-exp of the scaled scores (saved for backward)
+ *   dqkv  bf16 [batch*n, 3*heads*64]
+ * ---------------------------------------------------------------------------------------- */
+int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int heads, int dim_head, float scale,
+                      void* out_bf16, float* lse, void* stream);
+int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
+                      const float* lse, int batch, int n, int heads, int dim_head, float scale,
+                      void* dqkv_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer over flat fp32 arenas: clip_grad_norm_(params, max_norm) + AdamW.step()
+ * (pretrain_models.py:670-676,707-711; torch.optim.AdamW defaults).  `state` is 3 doubles on the
+ * device: [0] step counter, [1] sum of squares of all gradients (zero it, then call
+ * m3l_grad_sumsq once per live range), [2] total gradient norm (written by step_begin).
+ * Sequence per step: sumsq(ranges...) -> step_begin -> clip_adamw(ranges...).  Parameters whose
+ * gradient is None in the reference are simply left out of the ranges.
+ * ---------------------------------------------------------------------------------------- */
+int m3l_grad_sumsq(const float* grads, size_t count, double* state, void* stream);
+int m3l_optimizer_step_begin(double* state, void* stream);
+int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t count,
+                   const double* state, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float max_norm, int write_clipped_grad, void* stream);
+
+/* bf16 shadow copies of the fp32 master weights consumed by the GEMMs: a flat cast, and transposed
+ * copies (dst[c, r] = src[r, c]) of a table of matrices for the dgrad products. */
+typedef struct m3l_matrix_desc {
+  int64_t src_offset; /* elements from src_base */
+  int64_t dst_offset; /* elements from dst_base */
+  int32_t rows, cols; /* of the source, row-major */
+} m3l_matrix_desc;
+int m3l_cast_bf16(const float* src, void* dst_bf16, size_t count, void* stream);
+int m3l_transpose_cast_bf16(const float* src_base, void* dst_base_bf16, const m3l_matrix_desc* descs_dev,
+                            int count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,29 @@ def current_stream() -> C.c_void_p:
     import torch
 
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class MaskSegments(C.Structure):
+    _fields_ = [("count", C.c_int32), ("offset", C.c_int32 * 8), ("length", C.c_int32 * 8),
+                ("n_masked", C.c_int32 * 8)]
+
+
+class PatchSource(C.Structure):
+    _fields_ = [("src", C.c_void_p * 4), ("channels", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("patch_h", C.c_int32), ("patch_w", C.c_int32),
+                ("token_base", C.c_int32)]
+
+
+class MatrixDesc(C.Structure):
+    _fields_ = [("src_offset", C.c_int64), ("dst_offset", C.c_int64), ("rows", C.c_int32),
+                ("cols", C.c_int32)]
+
+
+# every symbol include/m3l_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "m3l_last_error", "m3l_gemm_bf16", "m3l_mask_indices", "m3l_patch_layernorm", "m3l_layernorm_fwd",
+    "m3l_layernorm_bwd", "m3l_decoder_assemble_fwd", "m3l_decoder_assemble_bwd", "m3l_rowclass_sum",
+    "m3l_mse_loss", "m3l_colsum", "m3l_ln_param_grad", "m3l_attention_fwd", "m3l_attention_bwd",
+    "m3l_grad_sumsq", "m3l_optimizer_step_begin", "m3l_clip_adamw", "m3l_cast_bf16",
+    "m3l_transpose_cast_bf16",
+)

@@ -1,0 +1,658 @@
+// m3l_b200 — HBM-bound kernels of the VTMAE step: mask sampling, fused patchify + LayerNorm
+// gather, token-embedding finish, LayerNorm forward/backward, decoder-sequence assembly and its
+// backward, masked-patch MSE (+ its gradient), column sums.
+//
+// Reference semantics (paths relative to /root/reference):
+//   mask sampling             models/pretrain_models.py:223-248
+//   patchify + LN(P)          models/pretrain_models.py:768-769,775-776 (Rearrange + LayerNorm)
+//   LN(D) + modality + pos    models/pretrain_models.py:771,778,202-219
+//   decoder assembly          models/pretrain_models.py:270-307
+//   masked MSE                models/pretrain_models.py:327-340 (and :311-322 for early_conv_masking)
+#include "common.cuh"
+#include "m3l_internal.h"
+
+namespace m3l {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// 1. mask sampling: per (sample, segment) rank sort of the noise keys (stable, ascending)
+// ------------------------------------------------------------------------------------------
+__global__ void mask_indices_kernel(const float* __restrict__ noise, int n_total, m3l_mask_segments segs,
+                                    int64_t* __restrict__ masked, int n_masked_total,
+                                    int64_t* __restrict__ unmasked, int n_unmasked_total,
+                                    int32_t* __restrict__ slot_of_token) {
+  extern __shared__ float keys[];
+  const int b = blockIdx.x;
+  const int s = blockIdx.y;
+  const int off = segs.offset[s], len = segs.length[s], nmask = segs.n_masked[s];
+  int moff = 0, uoff = 0;
+  for (int i = 0; i < s; ++i) {
+    moff += segs.n_masked[i];
+    uoff += segs.length[i] - segs.n_masked[i];
+  }
+  const float* row = noise + (size_t)b * n_total + off;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) keys[i] = row[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const float ki = keys[i];
+    int rank = 0;
+    for (int j = 0; j < len; ++j) {
+      const float kj = keys[j];
+      rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    const int64_t tok = off + i;
+    if (rank < nmask) {
+      masked[(size_t)b * n_masked_total + moff + rank] = tok;
+      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = -(1 + moff + rank);
+    } else {
+      unmasked[(size_t)b * n_unmasked_total + uoff + rank - nmask] = tok;
+      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = uoff + rank - nmask;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// patch addressing shared by the gather kernels
+// ------------------------------------------------------------------------------------------
+struct PatchSrc {
+  const float* src[4];   // per sensor [B, C, H, W] fp32 (image: one entry)
+  int C, H, W, ph, pw;   // channels, height, width, patch height / width
+  int gw;                // patches per row (W / pw)
+  int n_per_src;         // patches per source (gh * gw)
+  int tok_base;          // global token index of this modality's first token
+  int P;                 // ph * pw * C
+};
+
+M3L_DEVINL const float* patch_origin(const PatchSrc& ps, int b, int tok, int* sensor) {
+  const int t = tok - ps.tok_base;
+  const int s = t / ps.n_per_src;
+  const int tl = t - s * ps.n_per_src;
+  const int hh = tl / ps.gw, ww = tl - hh * ps.gw;
+  *sensor = s;
+  return ps.src[s] + ((size_t)b * ps.C * ps.H + (size_t)hh * ps.ph) * ps.W + (size_t)ww * ps.pw;
+}
+
+// element e of the flattened patch, order (p1, p2, c) with c fastest
+M3L_DEVINL float patch_elem(const PatchSrc& ps, const float* origin, int e) {
+  const int c = e % ps.C;
+  const int pp = e / ps.C;
+  const int p1 = pp / ps.pw, p2 = pp - p1 * ps.pw;
+  return origin[((size_t)c * ps.H + p1) * ps.W + p2];
+}
+
+M3L_DEVINL float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. fused patchify + gather + LayerNorm(P): one block per output row
+//    row r = b * ncols + jj ; token = tok_idx ? tok_idx[b, col0 + jj] : tok_base + jj
+// ------------------------------------------------------------------------------------------
+__global__ void patch_ln_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0,
+                                int ncols, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                bf16* __restrict__ out, bf16* __restrict__ xhat_out, float eps) {
+  extern __shared__ float patch[];   // P floats
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int b = r / ncols, jj = r - b * ncols;
+  const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+  int sensor;
+  const float* origin = patch_origin(ps, b, tok, &sensor);
+  // read in source order (c, p1, p2): p2 runs along W, contiguous in memory
+  const int P = ps.P, ppw = ps.ph * ps.pw;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int c = i / ppw;
+    const int pp = i - c * ppw;
+    const int p1 = pp / ps.pw, p2 = pp - p1 * ps.pw;
+    patch[pp * ps.C + c] = origin[((size_t)c * ps.H + p1) * ps.W + p2];
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s += patch[i];
+  const float mean = block_sum(s, red) / P;
+  float v = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float d = patch[i] - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(v, red) / P + eps);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float xh = (patch[i] - mean) * rstd;
+    out[(size_t)r * P + i] = __float2bfloat16(xh * gamma[i] + beta[i]);
+    if (xhat_out) xhat_out[(size_t)r * P + i] = __float2bfloat16(xh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic warp-per-row LayerNorm helpers (D multiple of 8, D <= 1024); lane owns 8-element chunks
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 4;  // D <= 32 * 8 * 4 = 1024
+
+template <typename T>
+M3L_DEVINL void load8(const T* p, float (&v)[8]);
+template <>
+M3L_DEVINL void load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <>
+M3L_DEVINL void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+M3L_DEVINL void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+M3L_DEVINL void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// 3./4. LayerNorm forward.  x: TIn [M, D]; y: bf16.  Optional additive terms (token embedding
+// finish / nothing for plain LN): add0[row_class[r]] and add1[row_pos[r]] fp32 rows of D.
+// Optional output row remap (dst_row[r] < 0 -> row skipped).
+template <typename TIn>
+__global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+                                     float* __restrict__ stats, const int32_t* __restrict__ dst_row,
+                                     const float* __restrict__ add0, const int32_t* __restrict__ add0_row,
+                                     const float* __restrict__ add1, const int32_t* __restrict__ add1_row) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
+    float v[kMaxChunks][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        load8<TIn>(x + (size_t)r * D + ch * 8, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      }
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[c][i] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    if (stats && lane == 0) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = rstd;
+    }
+    const int dr = dst_row ? dst_row[r] : r;
+    if (dr < 0) continue;
+    const float* a0 = add0 ? add0 + (size_t)(add0_row ? add0_row[r] : 0) * D : nullptr;
+    const float* a1 = add1 ? add1 + (size_t)(add1_row ? add1_row[r] : 0) * D : nullptr;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float g[8], bt[8], o[8];
+        load8<float>(gamma + ch * 8, g);
+        load8<float>(beta + ch * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mean) * rstd * g[i] + bt[i];
+        if (a0) {
+          float t[8];
+          load8<float>(a0 + ch * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        if (a1) {
+          float t[8];
+          load8<float>(a1 + ch * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        store8(y + (size_t)dr * D + ch * 8, o);
+      }
+    }
+  }
+}
+
+// LayerNorm backward.  dy: bf16 rows (optionally gathered: src_row[r] < 0 -> dy row is zero),
+// x: TIn LN input, stats (mean, rstd).  dx = LN'(dy) (+ skip[r]) written as TOut;
+// dgamma / dbeta accumulated with atomics (fp32).
+template <typename TIn, typename TOut>
+__global__ void layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_row,
+                                     const TIn* __restrict__ x, const float* __restrict__ stats, int M, int D,
+                                     const float* __restrict__ gamma, const bf16* __restrict__ skip,
+                                     TOut* __restrict__ dx, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  extern __shared__ float sacc[];  // [2][D] block accumulators
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float ag[kMaxChunks][8], ab[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = 0.f;
+
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
+    const int sr = src_row ? src_row[r] : r;
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float xh[kMaxChunks][8], g[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float xv[8], dv[8], gm[8];
+        load8<TIn>(x + (size_t)r * D + ch * 8, xv);
+        if (sr >= 0) {
+          load8<bf16>(dy + (size_t)sr * D + ch * 8, dv);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = 0.f;
+        }
+        load8<float>(gamma + ch * 8, gm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (xv[i] - mean) * rstd;
+          g[c][i] = dv[i] * gm[i];
+          s1 += g[c][i];
+          s2 += g[c][i] * xh[c][i];
+          ag[c][i] += dv[i] * xh[c][i];
+          ab[c][i] += dv[i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        if (skip) {
+          float t[8];
+          load8<bf16>(skip + (size_t)r * D + ch * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        store8(dx + (size_t)r * D + ch * 8, o);
+      }
+    }
+  }
+  if (dgamma) {
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(&sacc[ch * 8 + i], ag[c][i]);
+          atomicAdd(&sacc[D + ch * 8 + i], ab[c][i]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(&dgamma[i], sacc[i]);
+      atomicAdd(&dbeta[i], sacc[D + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 5. decoder sequence assembly: z[b, t] = (slot >= 0 ? d[b*nv + slot] : mask_token) + add0[cls] + add1[t]
+// ------------------------------------------------------------------------------------------
+__global__ void assemble_fwd_kernel(const bf16* __restrict__ d, int nv, const float* __restrict__ mask_token,
+                                    const int32_t* __restrict__ slot_of_token, int B, int n, int D,
+                                    const float* __restrict__ add0, const int32_t* __restrict__ tok_class,
+                                    const float* __restrict__ add1, bf16* __restrict__ z) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const int M = B * n;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
+    const int b = r / n, t = r - b * n;
+    const int slot = slot_of_token[r];
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      float v[8];
+      if (slot >= 0) load8<bf16>(d + ((size_t)b * nv + slot) * D + ch * 8, v);
+      else load8<float>(mask_token + ch * 8, v);
+      if (add0) {
+        float a[8];
+        load8<float>(add0 + (size_t)tok_class[t] * D + ch * 8, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+      }
+      if (add1) {
+        float a[8];
+        load8<float>(add1 + (size_t)t * D + ch * 8, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+      }
+      store8(z + (size_t)r * D + ch * 8, v);
+    }
+  }
+}
+
+// backward: dd[b*nv+slot] = dz[b,t] (visible); d mask_token += sum(masked rows);
+// d add0[class] += sum rows of the class; d add1[t] += sum over b (only if dadd1 != null).
+// One block per token position t: loops over the batch so every sum is block-local.
+__global__ void assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slot_of_token,
+                                    int B, int n, int D, int nv, bf16* __restrict__ dd,
+                                    float* __restrict__ dmask_token, float* __restrict__ dadd0,
+                                    const int32_t* __restrict__ tok_class, float* __restrict__ dadd1) {
+  const int t = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sum_all = 0.f, sum_masked = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const size_t r = (size_t)b * n + t;
+      const int slot = slot_of_token[r];
+      const bf16 g = dz[r * D + c];
+      const float gf = __bfloat162float(g);
+      sum_all += gf;
+      if (slot >= 0) dd[((size_t)b * nv + slot) * D + c] = g;
+      else sum_masked += gf;
+    }
+    if (dmask_token) atomicAdd(&dmask_token[c], sum_masked);
+    if (dadd0) atomicAdd(&dadd0[(size_t)tok_class[t] * D + c], sum_all);
+    if (dadd1) atomicAdd(&dadd1[(size_t)t * D + c], sum_all);
+  }
+}
+
+// token-embedding finish backward: class / position sums of dx0 rows (rows ordered [b, nv]).
+__global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, int D,
+                                    const int32_t* __restrict__ row_class, float* __restrict__ dclass,
+                                    const int32_t* __restrict__ row_pos, float* __restrict__ dpos) {
+  // one block per visible slot j (class is a function of j only; position varies per sample)
+  const int j = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const size_t r = (size_t)b * nv + j;
+      const float g = __bfloat162float(dx[r * D + c]);
+      s += g;
+      if (dpos) atomicAdd(&dpos[(size_t)row_pos[r] * D + c], g);
+    }
+    if (dclass) atomicAdd(&dclass[(size_t)row_class[j] * D + c], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 6. masked-patch MSE: pred fp32 [rows, P]; target gathered from the raw maps.
+//    loss_acc[slot] += weight * sum((pred - tgt)^2) ; dpred = 2 * weight * (pred - tgt)  (bf16)
+// ------------------------------------------------------------------------------------------
+__global__ void mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0,
+                                int ncols, const float* __restrict__ pred, float weight,
+                                bf16* __restrict__ dpred, float* __restrict__ loss_acc) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int b = r / ncols, jj = r - b * ncols;
+  const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+  int sensor;
+  const float* origin = patch_origin(ps, b, tok, &sensor);
+  const int P = ps.P;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < P; e += blockDim.x) {
+    const float diff = pred[(size_t)r * P + e] - patch_elem(ps, origin, e);
+    acc += diff * diff;
+    dpred[(size_t)r * P + e] = __float2bfloat16(2.f * weight * diff);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_acc, weight * tot);
+}
+
+// ------------------------------------------------------------------------------------------
+// 7. column sums of a bf16 matrix: out[n] += sum_m x[m, n]   (bias gradients)
+// ------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
+  // block: 32 x 8 threads; each thread owns 8 consecutive columns
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  __shared__ float part[8][32][8];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < N) {
+    const int rows_per_block = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, M);
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v[8];
+      load8<bf16>(x + (size_t)r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += part[y][threadIdx.x][i];
+      atomicAdd(&out[col + i], s);
+    }
+  }
+}
+
+// LayerNorm(P) parameter gradients of the patch embedding: dgamma[p] += sum_r dA[r,p]*xhat[r,p]; dbeta[p] += sum_r dA[r,p]
+__global__ void ln_param_grad_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ xhat, int M, int P,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, M);
+  float g = 0.f, bsum = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float d = __bfloat162float(dA[(size_t)r * P + p]);
+    g += d * __bfloat162float(xhat[(size_t)r * P + p]);
+    bsum += d;
+  }
+  atomicAdd(&dgamma[p], g);
+  atomicAdd(&dbeta[p], bsum);
+}
+
+PatchSrc make_patch_src(const m3l_patch_source* s) {
+  PatchSrc ps;
+  for (int i = 0; i < 4; ++i) ps.src[i] = s->src[i];
+  ps.C = s->channels; ps.H = s->height; ps.W = s->width; ps.ph = s->patch_h; ps.pw = s->patch_w;
+  ps.gw = s->width / s->patch_w;
+  ps.n_per_src = (s->height / s->patch_h) * ps.gw;
+  ps.tok_base = s->token_base;
+  ps.P = s->patch_h * s->patch_w * s->channels;
+  return ps;
+}
+
+int ln_grid(int M, int warps_per_block) {
+  const int blocks = (M + warps_per_block - 1) / warps_per_block;
+  const int cap = device_sm_count() * 8;
+  return blocks < cap ? blocks : cap;
+}
+
+}  // namespace
+}  // namespace m3l
+
+using namespace m3l;
+
+extern "C" int m3l_mask_indices(const float* noise, int batch, int n_total, const m3l_mask_segments* segs,
+                                int64_t* masked, int64_t* unmasked, int32_t* slot_of_token, void* stream) {
+  M3L_REQUIRE(noise && segs && masked && unmasked, "mask_indices: null pointer");
+  M3L_REQUIRE(segs->count >= 1 && segs->count <= M3L_MAX_SEGMENTS, "mask_indices: bad segment count %d", segs->count);
+  if (batch == 0) return M3L_OK;
+  int nm = 0, nu = 0, maxlen = 0;
+  for (int i = 0; i < segs->count; ++i) {
+    M3L_REQUIRE(segs->n_masked[i] >= 0 && segs->n_masked[i] <= segs->length[i] &&
+                    segs->offset[i] >= 0 && segs->offset[i] + segs->length[i] <= n_total,
+                "mask_indices: bad segment %d", i);
+    nm += segs->n_masked[i];
+    nu += segs->length[i] - segs->n_masked[i];
+    maxlen = segs->length[i] > maxlen ? segs->length[i] : maxlen;
+  }
+  M3L_REQUIRE(maxlen <= 8192, "mask_indices: segment longer than 8192");
+  dim3 grid(batch, segs->count);
+  const int threads = maxlen <= 64 ? 64 : (maxlen <= 128 ? 128 : 256);
+  mask_indices_kernel<<<grid, threads, maxlen * sizeof(float), (cudaStream_t)stream>>>(
+      noise, n_total, *segs, masked, nm, unmasked, nu, slot_of_token);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_patch_layernorm(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld,
+                                   int col0, int ncols, const float* gamma, const float* beta, float eps,
+                                   void* out_bf16, void* xhat_bf16, void* stream) {
+  M3L_REQUIRE(src && gamma && beta && out_bf16, "patch_layernorm: null pointer");
+  if (batch * ncols == 0) return M3L_OK;
+  PatchSrc ps = make_patch_src(src);
+  M3L_REQUIRE(ps.P * sizeof(float) <= 48 * 1024, "patch_layernorm: patch dim %d too large", ps.P);
+  patch_ln_kernel<<<batch * ncols, 128, ps.P * sizeof(float), (cudaStream_t)stream>>>(
+      ps, tok_idx, idx_ld, col0, ncols, gamma, beta, (bf16*)out_bf16, (bf16*)xhat_bf16, eps);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, const float* gamma,
+                                 const float* beta, float eps, void* y_bf16, float* stats,
+                                 const int32_t* dst_row, const float* add0, const int32_t* add0_row,
+                                 const float* add1, const int32_t* add1_row, void* stream) {
+  M3L_REQUIRE(x && gamma && beta && y_bf16, "layernorm_fwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0 && dim <= 1024, "layernorm_fwd: dim %d unsupported", dim);
+  if (rows == 0) return M3L_OK;
+  const int wpb = 8;
+  const int grid = ln_grid(rows, wpb);
+  if (x_fp32)
+    layernorm_fwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, stats, dst_row, add0, add0_row, add1, add1_row);
+  else
+    layernorm_fwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, stats, dst_row, add0, add0_row, add1, add1_row);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, const void* x, int x_fp32,
+                                 const float* stats, int rows, int dim, const float* gamma,
+                                 const void* skip_bf16, void* dx, int dx_fp32, float* dgamma, float* dbeta,
+                                 void* stream) {
+  M3L_REQUIRE(dy_bf16 && x && stats && gamma && dx, "layernorm_bwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0 && dim <= 1024, "layernorm_bwd: dim %d unsupported", dim);
+  M3L_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set");
+  if (rows == 0) return M3L_OK;
+  const int wpb = 8;
+  int grid = (rows + wpb - 1) / wpb;
+  const int cap = device_sm_count() * 2;
+  if (grid > cap) grid = cap;
+  const size_t smem = 2 * dim * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_fp32 && !dx_fp32)
+    layernorm_bwd_kernel<float, bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const float*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (bf16*)dx, dgamma, dbeta);
+  else if (!x_fp32 && !dx_fp32)
+    layernorm_bwd_kernel<bf16, bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const bf16*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (bf16*)dx, dgamma, dbeta);
+  else if (x_fp32 && dx_fp32)
+    layernorm_bwd_kernel<float, float><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const float*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (float*)dx, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<bf16, float><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const bf16*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (float*)dx, dgamma, dbeta);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const float* mask_token,
+                                        const int32_t* slot_of_token, int batch, int n_tokens, int dim,
+                                        const float* add0, const int32_t* tok_class, const float* add1,
+                                        void* z_bf16, void* stream) {
+  M3L_REQUIRE(d_bf16 && mask_token && slot_of_token && z_bf16, "decoder_assemble_fwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0, "decoder_assemble_fwd: dim %d not a multiple of 8", dim);
+  M3L_REQUIRE(add0 == nullptr || tok_class != nullptr, "decoder_assemble_fwd: add0 needs tok_class");
+  if (batch * n_tokens == 0) return M3L_OK;
+  const int wpb = 8;
+  assemble_fwd_kernel<<<ln_grid(batch * n_tokens, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      (const bf16*)d_bf16, n_visible, mask_token, slot_of_token, batch, n_tokens, dim, add0, tok_class, add1,
+      (bf16*)z_bf16);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot_of_token, int batch,
+                                        int n_tokens, int dim, int n_visible, void* dd_bf16,
+                                        float* dmask_token, float* dadd0, const int32_t* tok_class,
+                                        float* dadd1, void* stream) {
+  M3L_REQUIRE(dz_bf16 && slot_of_token && dd_bf16, "decoder_assemble_bwd: null pointer");
+  M3L_REQUIRE(dadd0 == nullptr || tok_class != nullptr, "decoder_assemble_bwd: dadd0 needs tok_class");
+  if (batch * n_tokens == 0) return M3L_OK;
+  assemble_bwd_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, n_visible, (bf16*)dd_bf16, dmask_token, dadd0,
+      tok_class, dadd1);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, int dim,
+                                const int32_t* slot_class, float* dclass, const int32_t* row_pos, float* dpos,
+                                void* stream) {
+  M3L_REQUIRE(dx_bf16, "rowclass_sum: null pointer");
+  if (batch * n_visible == 0) return M3L_OK;
+  rowclass_sum_kernel<<<n_visible, 256, 0, (cudaStream_t)stream>>>((const bf16*)dx_bf16, batch, n_visible, dim,
+                                                                   slot_class, dclass, row_pos, dpos);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
+                            int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
+                            void* stream) {
+  M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
+  if (batch * ncols == 0) return M3L_OK;
+  PatchSrc ps = make_patch_src(src);
+  mse_loss_kernel<<<batch * ncols, 128, 0, (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, pred, weight,
+                                                                   (bf16*)dpred_bf16, loss_acc);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream) {
+  M3L_REQUIRE(x_bf16 && out, "colsum: null pointer");
+  M3L_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "colsum: cols/ld must be multiples of 8");
+  if (rows == 0) return M3L_OK;
+  const int gx = (cols / 8 + 31) / 32;
+  int gy = (device_sm_count() * 4 + gx - 1) / gx;
+  if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x_bf16, rows, cols, ld, out);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int dim, float* dgamma,
+                                 float* dbeta, void* stream) {
+  M3L_REQUIRE(da_bf16 && xhat_bf16 && dgamma && dbeta, "ln_param_grad: null pointer");
+  if (rows == 0) return M3L_OK;
+  const int gx = (dim + 127) / 128;
+  int gy = (rows + 127) / 128;
+  if (gy > 64) gy = 64;
+  ln_param_grad_kernel<<<dim3(gx, gy), 128, 0, (cudaStream_t)stream>>>((const bf16*)da_bf16, (const bf16*)xhat_bf16,
+                                                                       rows, dim, dgamma, dbeta);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}

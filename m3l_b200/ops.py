@@ -68,3 +68,189 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
     args.alpha = alpha
     check(_lib.load().m3l_gemm_bf16(C.byref(args), current_stream()), "m3l_gemm_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# mask sampling / patch sources
+# ------------------------------------------------------------------------------------------
+def make_segments(segs):
+    """segs: list of (offset, length, n_masked)."""
+    s = _lib.MaskSegments()
+    s.count = len(segs)
+    for i, (o, l, m) in enumerate(segs):
+        s.offset[i], s.length[i], s.n_masked[i] = o, l, m
+    return s
+
+
+def mask_indices(noise: torch.Tensor, segs, want_slots: bool = True):
+    """noise fp32 [B, n_total] -> (masked int64 [B, nm], unmasked int64 [B, nu], slot_of_token int32 [B, n])."""
+    _req_cuda(noise)
+    assert noise.dtype == torch.float32 and noise.is_contiguous()
+    B, n = noise.shape
+    nm = sum(m for _, _, m in segs)
+    nu = sum(l - m for _, l, m in segs)
+    masked = torch.empty((B, nm), dtype=torch.int64, device=noise.device)
+    unmasked = torch.empty((B, nu), dtype=torch.int64, device=noise.device)
+    slots = torch.empty((B, n), dtype=torch.int32, device=noise.device) if want_slots else None
+    cs = make_segments(segs)
+    check(_lib.load().m3l_mask_indices(ptr(noise), B, n, C.byref(cs), ptr(masked), ptr(unmasked), ptr(slots),
+                                       current_stream()), "m3l_mask_indices")
+    return masked, unmasked, slots
+
+
+def make_patch_source(maps, patch_h: int, patch_w: int, token_base: int):
+    """maps: list of fp32 NCHW tensors of one modality (same shape)."""
+    ps = _lib.PatchSource()
+    assert 1 <= len(maps) <= 4
+    for i, m in enumerate(maps):
+        assert m.dtype == torch.float32 and m.is_contiguous() and m.is_cuda and m.shape == maps[0].shape
+        ps.src[i] = m.data_ptr()
+    _, ps.channels, ps.height, ps.width = maps[0].shape
+    ps.patch_h, ps.patch_w, ps.token_base = patch_h, patch_w, token_base
+    ps._keepalive = maps
+    return ps
+
+
+def patch_layernorm(ps, batch: int, ncols: int, gamma, beta, tok_idx=None, col0: int = 0, want_xhat=True,
+                    eps: float = 1e-5):
+    P = ps.patch_h * ps.patch_w * ps.channels
+    dev = gamma.device
+    out = torch.empty((batch * ncols, P), dtype=torch.bfloat16, device=dev)
+    xhat = torch.empty_like(out) if want_xhat else None
+    idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
+    check(_lib.load().m3l_patch_layernorm(C.byref(ps), batch, ptr(tok_idx), idx_ld, col0, ncols, ptr(gamma),
+                                          ptr(beta), C.c_float(eps), ptr(out), ptr(xhat), current_stream()),
+          "m3l_patch_layernorm")
+    return out, xhat
+
+
+def layernorm_fwd(x, gamma, beta, *, out=None, out_rows=None, stats=None, want_stats=True, dst_row=None,
+                  add0=None, add0_row=None, add1=None, add1_row=None, eps: float = 1e-5):
+    _req_cuda(x, gamma, beta)
+    M, D = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.bfloat16, torch.float32)
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, D), dtype=torch.bfloat16, device=x.device)
+    if stats is None and want_stats:
+        stats = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    check(_lib.load().m3l_layernorm_fwd(ptr(x), int(x.dtype == torch.float32), M, D, ptr(gamma), ptr(beta),
+                                        C.c_float(eps), ptr(out), ptr(stats), ptr(dst_row), ptr(add0),
+                                        ptr(add0_row), ptr(add1), ptr(add1_row), current_stream()),
+          "m3l_layernorm_fwd")
+    return out, stats
+
+
+def layernorm_bwd(dy, x, stats, gamma, *, dgamma=None, dbeta=None, skip=None, src_row=None, dx=None,
+                  dx_dtype=torch.bfloat16):
+    _req_cuda(dy, x, stats, gamma)
+    M, D = x.shape
+    if dx is None:
+        dx = torch.empty((M, D), dtype=dx_dtype, device=x.device)
+    check(_lib.load().m3l_layernorm_bwd(ptr(dy), ptr(src_row), ptr(x), int(x.dtype == torch.float32), ptr(stats),
+                                        M, D, ptr(gamma), ptr(skip), ptr(dx), int(dx.dtype == torch.float32),
+                                        ptr(dgamma), ptr(dbeta), current_stream()), "m3l_layernorm_bwd")
+    return dx
+
+
+def decoder_assemble_fwd(d, n_visible, mask_token, slots, batch, n_tokens, *, add0=None, tok_class=None,
+                         add1=None, out=None):
+    D = d.shape[-1]
+    if out is None:
+        out = torch.empty((batch * n_tokens, D), dtype=torch.bfloat16, device=d.device)
+    check(_lib.load().m3l_decoder_assemble_fwd(ptr(d), n_visible, ptr(mask_token), ptr(slots), batch, n_tokens, D,
+                                               ptr(add0), ptr(tok_class), ptr(add1), ptr(out), current_stream()),
+          "m3l_decoder_assemble_fwd")
+    return out
+
+
+def decoder_assemble_bwd(dz, slots, batch, n_tokens, n_visible, *, dmask_token=None, dadd0=None, tok_class=None,
+                         dadd1=None, out=None):
+    D = dz.shape[-1]
+    if out is None:
+        out = torch.empty((batch * n_visible, D), dtype=torch.bfloat16, device=dz.device)
+    check(_lib.load().m3l_decoder_assemble_bwd(ptr(dz), ptr(slots), batch, n_tokens, D, n_visible, ptr(out),
+                                               ptr(dmask_token), ptr(dadd0), ptr(tok_class), ptr(dadd1),
+                                               current_stream()), "m3l_decoder_assemble_bwd")
+    return out
+
+
+def rowclass_sum(dx, batch, n_visible, *, slot_class=None, dclass=None, row_pos=None, dpos=None):
+    check(_lib.load().m3l_rowclass_sum(ptr(dx), batch, n_visible, dx.shape[-1], ptr(slot_class), ptr(dclass),
+                                       ptr(row_pos), ptr(dpos), current_stream()), "m3l_rowclass_sum")
+
+
+def mse_loss(ps, batch, ncols, pred, weight, loss_acc, *, tok_idx=None, col0=0, dpred=None):
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    if dpred is None:
+        dpred = torch.empty(pred.shape, dtype=torch.bfloat16, device=pred.device)
+    idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
+    check(_lib.load().m3l_mse_loss(C.byref(ps), batch, ptr(tok_idx), idx_ld, col0, ncols, ptr(pred),
+                                   C.c_float(weight), ptr(dpred), ptr(loss_acc), current_stream()), "m3l_mse_loss")
+    return dpred
+
+
+def colsum(x, out):
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out.dtype == torch.float32
+    check(_lib.load().m3l_colsum(ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(out), current_stream()),
+          "m3l_colsum")
+    return out
+
+
+def ln_param_grad(da, xhat, dgamma, dbeta):
+    check(_lib.load().m3l_ln_param_grad(ptr(da), ptr(xhat), da.shape[0], da.shape[1], ptr(dgamma), ptr(dbeta),
+                                        current_stream()), "m3l_ln_param_grad")
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def attention_fwd(qkv, batch, n, heads, dim_head, scale, *, out=None, lse=None):
+    _req_cuda(qkv)
+    inner = heads * dim_head
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (batch * n, 3 * inner)
+    if out is None:
+        out = torch.empty((batch * n, inner), dtype=torch.bfloat16, device=qkv.device)
+    if lse is None:
+        lse = torch.empty((batch, heads, n), dtype=torch.float32, device=qkv.device)
+    check(_lib.load().m3l_attention_fwd(ptr(qkv), batch, n, heads, dim_head, C.c_float(scale), ptr(out), ptr(lse),
+                                        current_stream()), "m3l_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, batch, n, heads, dim_head, scale, *, dqkv=None):
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    assert dout.is_contiguous() and out.is_contiguous()
+    check(_lib.load().m3l_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), batch, n, heads, dim_head,
+                                        C.c_float(scale), ptr(dqkv), current_stream()), "m3l_attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------
+def grad_sumsq(grads, state):
+    check(_lib.load().m3l_grad_sumsq(ptr(grads), C.c_size_t(grads.numel()), ptr(state), current_stream()),
+          "m3l_grad_sumsq")
+
+
+def optimizer_step_begin(state):
+    check(_lib.load().m3l_optimizer_step_begin(ptr(state), current_stream()), "m3l_optimizer_step_begin")
+
+
+def clip_adamw(params, grads, exp_avg, exp_avg_sq, state, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+               max_norm=0.5, write_clipped_grad=True):
+    check(_lib.load().m3l_clip_adamw(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),
+                                     C.c_size_t(params.numel()), ptr(state), C.c_float(lr), C.c_float(betas[0]),
+                                     C.c_float(betas[1]), C.c_float(eps), C.c_float(weight_decay),
+                                     C.c_float(max_norm), int(write_clipped_grad), current_stream()),
+          "m3l_clip_adamw")
+
+
+def cast_bf16(src, dst):
+    check(_lib.load().m3l_cast_bf16(ptr(src), ptr(dst), C.c_size_t(src.numel()), current_stream()), "m3l_cast_bf16")
+
+
+def transpose_cast_bf16(src_base, dst_base, descs_dev, count):
+    check(_lib.load().m3l_transpose_cast_bf16(ptr(src_base), ptr(dst_base), ptr(descs_dev), count,
+                                              current_stream()), "m3l_transpose_cast_bf16")

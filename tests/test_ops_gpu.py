@@ -1,0 +1,320 @@
+"""GPU: every C-ABI kernel against a plain torch fp32 statement of the same op (bf16 tolerances
+stated per test).  Index-valued results are checked bit-exactly."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from m3l_b200 import ops as _ops
+    return _ops
+
+
+# --------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 520, 200), (2560, 768, 256), (1536, 256, 192)])
+def test_gemm_kmajor(ops, M, N, K, bn):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = torch.randn(N, K, device=DEV).bfloat16()
+    out = ops.gemm(a, b, bn=bn)
+    assert rel_err(out, a.float() @ b.float().T) < 1e-2  # bf16 output rounding
+
+
+@pytest.mark.parametrize("bn,splits", [(64, 1), (128, 4), (256, 7), (0, 3)])
+def test_gemm_wgrad_mnmajor_splitk(ops, bn, splits):
+    torch.manual_seed(1)
+    a = torch.randn(1000, 264, device=DEV).bfloat16()
+    b = torch.randn(1000, 200, device=DEV).bfloat16()
+    out = torch.ones(264, 200, device=DEV)
+    ops.gemm(a, b, mn_major=True, out=out, accumulate=True, splits=splits, bn=bn)
+    assert rel_err(out, 1 + a.float().T @ b.float()) < 1e-5  # fp32 accumulate of exact bf16 products
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(2)
+    M, N, K = 777, 512, 256
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    z = a.float() @ b.float().T
+    out = ops.gemm(a, b, bias=bias, residual=res)
+    assert rel_err(out, z + bias + res.float()) < 1e-2
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=pre)
+    assert rel_err(pre, z + bias) < 1e-2 and rel_err(h, F.gelu(z + bias)) < 1e-2
+    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre, out_dtype=torch.float32)
+    zz = pre.float().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    assert rel_err(g, z * zz.grad) < 1e-4
+    inplace = res.clone()
+    ops.gemm(a, b, bias=bias, residual=inplace, out=inplace)
+    assert rel_err(inplace, z + bias + res.float()) < 1e-2
+
+
+# ------------------------------------------------------------------------------- mask indices
+@pytest.mark.parametrize("B,segs", [(37, [(0, 64, 60), (64, 64, 61), (128, 64, 61)]), (5, [(0, 64, 60)]),
+                                    (9, [(0, 25, 20), (25, 25, 20)]), (3, [(0, 300, 17)])])
+def test_mask_indices_bit_exact(ops, B, segs):
+    g = torch.Generator().manual_seed(3)
+    n = sum(l for _, l, _ in segs)
+    noise = torch.rand(B, n, generator=g)
+    masked, unmasked, slots = ops.mask_indices(noise.to(DEV), segs)
+    m_ref, u_ref = [], []
+    for off, l, nm in segs:
+        perm = noise[:, off:off + l].argsort(dim=-1, stable=True) + off
+        m_ref.append(perm[:, :nm]); u_ref.append(perm[:, nm:])
+    m_ref, u_ref = torch.cat(m_ref, 1), torch.cat(u_ref, 1)
+    assert torch.equal(masked.cpu(), m_ref) and torch.equal(unmasked.cpu(), u_ref)
+    s = slots.cpu()
+    br = torch.arange(B)[:, None]
+    assert torch.equal(s[br, u_ref], torch.arange(u_ref.shape[1], dtype=torch.int32).expand(B, -1))
+    assert torch.equal(s[br, m_ref], -(1 + torch.arange(m_ref.shape[1], dtype=torch.int32)).expand(B, -1))
+
+
+def test_mask_indices_ties_are_stable(ops):
+    noise = torch.tensor([[0.5, 0.25, 0.5, 0.25, 0.0, 0.5, 1.0, 0.25]])
+    masked, unmasked, _ = ops.mask_indices(noise.to(DEV), [(0, 8, 5)], want_slots=False)
+    assert masked.cpu().tolist() == [[4, 1, 3, 7, 0]] and unmasked.cpu().tolist() == [[2, 5, 6]]
+
+
+# ------------------------------------------------------------------------ patchify + LayerNorm
+def _patchify(x, p1, p2):
+    b, c, H, W = x.shape
+    h, w = H // p1, W // p2
+    return x.reshape(b, c, h, p1, w, p2).permute(0, 2, 4, 3, 5, 1).reshape(b, h * w, p1 * p2 * c)
+
+
+def test_patch_layernorm_gather(ops):
+    torch.manual_seed(4)
+    B = 6
+    t1, t2 = torch.rand(B, 12, 32, 32, device=DEV), torch.rand(B, 12, 32, 32, device=DEV)
+    gamma, beta = torch.randn(192, device=DEV), torch.randn(192, device=DEV)
+    ps = ops.make_patch_source([t1, t2], 4, 4, token_base=64)
+    idx = torch.stack([torch.randperm(128)[:7] + 64 for _ in range(B)]).to(DEV)
+    pad = torch.zeros(B, 3, dtype=torch.int64, device=DEV)
+    idx_full = torch.cat([pad, idx], 1).contiguous()  # tactile columns start at col0 = 3
+    out, xhat = ops.patch_layernorm(ps, B, 7, gamma, beta, tok_idx=idx_full, col0=3)
+    patches = torch.cat([_patchify(t1, 4, 4), _patchify(t2, 4, 4)], 1)
+    sel = patches[torch.arange(B, device=DEV)[:, None], idx - 64].reshape(B * 7, 192)
+    assert rel_err(xhat, F.layer_norm(sel, (192,))) < 1e-2
+    assert rel_err(out, F.layer_norm(sel, (192,), gamma, beta)) < 1e-2
+    # all tokens (no index list), image geometry
+    img = torch.rand(3, 12, 64, 64, device=DEV)
+    g2, b2 = torch.randn(768, device=DEV), torch.randn(768, device=DEV)
+    ps2 = ops.make_patch_source([img], 8, 8, token_base=0)
+    out2, _ = ops.patch_layernorm(ps2, 3, 64, g2, b2, want_xhat=False)
+    assert rel_err(out2, F.layer_norm(_patchify(img, 8, 8).reshape(-1, 768), (768,), g2, b2)) < 1e-2
+
+
+# ----------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("D,fp32_in", [(256, False), (128, False), (384, True), (1024, False)])
+def test_layernorm_fwd_bwd(ops, D, fp32_in):
+    torch.manual_seed(5)
+    M = 1237
+    x = torch.randn(M, D, device=DEV) * 2 + 0.5
+    x = x if fp32_in else x.bfloat16()
+    gamma, beta = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    y, stats = ops.layernorm_fwd(x, gamma, beta)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br)
+    assert rel_err(y, yr) < 1e-2
+    dy = torch.randn(M, D, device=DEV).bfloat16()
+    skip = torch.randn(M, D, device=DEV).bfloat16()
+    yr.backward(dy.float())
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    dx = ops.layernorm_bwd(dy, x, stats, gamma, dgamma=dg, dbeta=db, skip=skip)
+    assert rel_err(dx, xr.grad + skip.float()) < 1e-2
+    assert rel_err(dg, gr.grad) < 1e-3 and rel_err(db, br.grad) < 1e-3
+
+
+def test_layernorm_row_remap_and_adds(ops):
+    torch.manual_seed(6)
+    M, D = 64, 256
+    x = torch.randn(M, D, device=DEV).bfloat16()
+    gamma, beta = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    dst = torch.full((M,), -1, dtype=torch.int32, device=DEV)
+    keep = torch.randperm(M)[:40]
+    dst[keep] = torch.arange(40, dtype=torch.int32, device=DEV)
+    a0, a1 = torch.randn(3, D, device=DEV), torch.randn(M, D, device=DEV)
+    r0 = torch.randint(0, 3, (M,), dtype=torch.int32, device=DEV)
+    r1 = torch.randperm(M).to(torch.int32).to(DEV)
+    y, _ = ops.layernorm_fwd(x, gamma, beta, out_rows=40, dst_row=dst, add0=a0, add0_row=r0, add1=a1, add1_row=r1)
+    ref = F.layer_norm(x.float(), (D,), gamma, beta) + a0[r0.long()] + a1[r1.long()]
+    assert rel_err(y, ref[keep.to(DEV)]) < 1e-2
+    # backward gather: rows without a source get zero dy
+    dy = torch.randn(40, D, device=DEV).bfloat16()
+    stats = torch.stack([x.float().mean(1), (x.float().var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+    dx = ops.layernorm_bwd(dy, x, stats, gamma, src_row=dst)
+    xr = x.float().requires_grad_(True)
+    full = torch.zeros(M, D, device=DEV)
+    full[keep.to(DEV)] = dy.float()
+    F.layer_norm(xr, (D,), gamma, beta).backward(full)
+    assert rel_err(dx, xr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, B, n, H, scale):
+    q, k, v = qkv.float().reshape(B, n, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * scale
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * n, H * 64), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,n,H", [(3, 10, 4), (5, 4, 4), (2, 50, 4), (3, 64, 2), (2, 192, 4), (1, 256, 1), (2, 130, 3)])
+def test_attention_fwd_bwd(ops, B, n, H):
+    torch.manual_seed(7)
+    scale = 64 ** -0.5
+    qkv = torch.randn(B * n, 3 * H * 64, device=DEV).bfloat16()
+    out, lse = ops.attention_fwd(qkv, B, n, H, 64, scale)
+    qr = qkv.float().requires_grad_(True)
+    oref, lref = _attn_ref(qr, B, n, H, scale)
+    assert rel_err(out, oref) < 2e-2
+    assert (lse - lref).abs().max().item() < 2e-2
+    dout = torch.randn(B * n, H * 64, device=DEV).bfloat16()
+    oref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, n, H, 64, scale)
+    inner = H * 64
+    for name, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
+        assert cos(dqkv[:, sl], qr.grad[:, sl]) > 0.999, name
+        assert rel_err(dqkv[:, sl], qr.grad[:, sl]) < 5e-2, name
+
+
+# ------------------------------------------------------------------- decoder assembly / sums
+def test_decoder_assemble_fwd_bwd(ops):
+    torch.manual_seed(8)
+    B, n, D, nv = 5, 192, 256, 10
+    noise = torch.rand(B, n)
+    segs = [(0, 64, 60), (64, 64, 61), (128, 64, 61)]
+    masked, unmasked, slots = ops.mask_indices(noise.to(DEV), segs)
+    d = torch.randn(B * nv, D, device=DEV).bfloat16()
+    mask_token = torch.randn(D, device=DEV)
+    mod = torch.randn(3, D, device=DEV)
+    pos = torch.randn(n, D, device=DEV)
+    cls = (torch.arange(n) // 64).to(torch.int32).to(DEV)
+    z = ops.decoder_assemble_fwd(d, nv, mask_token, slots, B, n, add0=mod, tok_class=cls, add1=pos)
+    br = torch.arange(B, device=DEV)[:, None]
+    ref = torch.zeros(B, n, D, device=DEV)
+    ref[br, unmasked] = d.float().reshape(B, nv, D)
+    ref[br, masked] = mask_token
+    ref = ref + mod[cls.long()] + pos
+    assert rel_err(z, ref.reshape(B * n, D)) < 1e-2
+    dz = torch.randn(B * n, D, device=DEV).bfloat16()
+    dmask, dmod, dpos = torch.zeros(D, device=DEV), torch.zeros(3, D, device=DEV), torch.zeros(n, D, device=DEV)
+    dd = ops.decoder_assemble_bwd(dz, slots, B, n, nv, dmask_token=dmask, dadd0=dmod, tok_class=cls, dadd1=dpos)
+    dzf = dz.float().reshape(B, n, D)
+    assert torch.equal(dd.reshape(B, nv, D), dz.reshape(B, n, D)[br, unmasked])
+    assert rel_err(dmask, dzf[br, masked].sum((0, 1))) < 1e-4
+    assert rel_err(dmod, torch.stack([dzf[:, 64 * i:64 * (i + 1)].sum((0, 1)) for i in range(3)])) < 1e-4
+    assert rel_err(dpos, dzf.sum(0)) < 1e-4
+
+
+def test_rowclass_colsum_lnparam(ops):
+    torch.manual_seed(9)
+    B, nv, D = 33, 10, 256
+    dx = torch.randn(B * nv, D, device=DEV).bfloat16()
+    cls = torch.tensor([0, 0, 0, 0, 1, 1, 1, 2, 2, 2], dtype=torch.int32, device=DEV)
+    pos = torch.randint(0, 192, (B * nv,), dtype=torch.int32, device=DEV)
+    dcls, dpos = torch.zeros(3, D, device=DEV), torch.zeros(192, D, device=DEV)
+    ops.rowclass_sum(dx, B, nv, slot_class=cls, dclass=dcls, row_pos=pos, dpos=dpos)
+    f = dx.float().reshape(B, nv, D)
+    assert rel_err(dcls, torch.stack([f[:, :4].sum((0, 1)), f[:, 4:7].sum((0, 1)), f[:, 7:].sum((0, 1))])) < 1e-4
+    ref = torch.zeros(192, D, device=DEV).index_add_(0, pos.long(), dx.float())
+    assert rel_err(dpos, ref) < 1e-4
+    x = torch.randn(5000, 776, device=DEV).bfloat16()
+    out = torch.ones(768, device=DEV)
+    ops.colsum(x[:, :768], out)
+    assert rel_err(out, 1 + x[:, :768].float().sum(0)) < 1e-4
+    da, xh = torch.randn(1030, 192, device=DEV).bfloat16(), torch.randn(1030, 192, device=DEV).bfloat16()
+    dg, db = torch.zeros(192, device=DEV), torch.zeros(192, device=DEV)
+    ops.ln_param_grad(da, xh, dg, db)
+    assert rel_err(dg, (da.float() * xh.float()).sum(0)) < 1e-4 and rel_err(db, da.float().sum(0)) < 1e-4
+
+
+def test_mse_loss_and_grad(ops):
+    torch.manual_seed(10)
+    B, nm = 7, 60
+    img = torch.rand(B, 12, 64, 64, device=DEV)
+    ps = ops.make_patch_source([img], 8, 8, token_base=0)
+    idx = torch.stack([torch.randperm(64)[:nm] for _ in range(B)]).to(DEV)
+    pred = torch.randn(B * nm, 768, device=DEV)
+    acc = torch.zeros(1, device=DEV)
+    w = 1.0 / pred.numel()
+    dpred = ops.mse_loss(ps, B, nm, pred, w, acc, tok_idx=idx)
+    tgt = _patchify(img, 8, 8)[torch.arange(B, device=DEV)[:, None], idx].reshape(B * nm, 768)
+    pr = pred.clone().requires_grad_(True)
+    l = F.mse_loss(pr, tgt)
+    l.backward()
+    assert abs(acc.item() - l.item()) < 1e-5 * abs(l.item())
+    assert rel_err(dpred, pr.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ optimizer
+def test_clip_adamw_matches_torch(ops):
+    torch.manual_seed(11)
+    n = 100003
+    p0 = torch.randn(n, device=DEV)
+    p = p0.clone()
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-3)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    state = torch.zeros(3, dtype=torch.float64, device=DEV)
+    for it in range(3):
+        g = torch.randn(n, device=DEV) * (3.0 if it < 2 else 1e-4)  # clip active, then inactive
+        p_ref.grad = g.clone()
+        total_ref = torch.nn.utils.clip_grad_norm_([p_ref], 0.5)
+        opt.step()
+        gg = g.clone()
+        state[1] = 0
+        ops.grad_sumsq(gg, state)
+        ops.optimizer_step_begin(state)
+        ops.clip_adamw(p, gg, m, v, state, lr=1e-3)
+        assert abs(state[2].item() - total_ref.item()) < 1e-5 * total_ref.item()
+        assert rel_err(gg, p_ref.grad) < 1e-5
+        assert rel_err(p, p_ref.data) < 1e-5
+    assert state[0].item() == 3.0
+
+
+def test_cast_and_transpose(ops):
+    from m3l_b200 import _lib
+    torch.manual_seed(12)
+    src = torch.randn(3000, device=DEV)
+    dst = torch.empty(3000, dtype=torch.bfloat16, device=DEV)
+    ops.cast_bf16(src, dst)
+    assert torch.equal(dst, src.bfloat16())
+    base = torch.randn(768 * 256 + 100 * 52, device=DEV)
+    out = torch.zeros(base.numel(), dtype=torch.bfloat16, device=DEV)
+    descs = (_lib.MatrixDesc * 2)()
+    descs[0].src_offset, descs[0].dst_offset, descs[0].rows, descs[0].cols = 0, 0, 768, 256
+    descs[1].src_offset, descs[1].dst_offset, descs[1].rows, descs[1].cols = 768 * 256, 768 * 256, 100, 52
+    dd = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(DEV)
+    ops.transpose_cast_bf16(base, out, dd, 2)
+    assert torch.equal(out[:768 * 256].reshape(256, 768), base[:768 * 256].reshape(768, 256).T.bfloat16())
+    assert torch.equal(out[768 * 256:].reshape(52, 100), base[768 * 256:].reshape(100, 52).T.bfloat16())
+
+
+def test_errors_are_loud(ops):
+    from m3l_b200._lib import M3LError
+    a = torch.randn(64, 64, device=DEV).bfloat16()
+    b = torch.randn(60, 64, device=DEV).bfloat16()  # N = 60 is not a multiple of 8
+    with pytest.raises(M3LError):
+        ops.gemm(a, b)
+    qkv = torch.randn(2 * 300, 3 * 64, device=DEV).bfloat16()  # n = 300 > 256
+    with pytest.raises(M3LError):
+        ops.attention_fwd(qkv, 2, 300, 1, 64, 0.125)
