@@ -68,6 +68,10 @@ int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);
  *   unmasked         int64 [batch, n_total - sum n_masked]
  *   slot_of_token    int32 [batch, n_total] or NULL: >= 0 -> position in `unmasked`,
  *                    < 0 -> -(1 + position in `masked`)
+ *   unmasked_i32     int32 copy of `unmasked` or NULL
+ *   masked_row_of_token  int32 [batch, n_total] or NULL: row of the token in the two stacked
+ *                    head-input matrices ([batch*n_masked_first rows of the first group (image) |
+ *                    batch*(n_masked - n_masked_first) rows of the rest]), -1 for unmasked tokens
  * ---------------------------------------------------------------------------------------- */
 #define M3L_MAX_SEGMENTS 8
 typedef struct m3l_mask_segments {
@@ -78,7 +82,9 @@ typedef struct m3l_mask_segments {
 } m3l_mask_segments;
 
 int m3l_mask_indices(const float* noise, int batch, int n_total, const m3l_mask_segments* segs,
-                     int64_t* masked, int64_t* unmasked, int32_t* slot_of_token, void* stream);
+                     int64_t* masked, int64_t* unmasked, int32_t* slot_of_token,
+                     int32_t* unmasked_i32, int32_t* masked_row_of_token, int n_masked_first,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch sources: up to 4 fp32 NCHW maps of one modality (the image, or tactile1..tactile{nt}),

@@ -1,2 +1,20 @@
-"""m3l_b200 — B200-native (sm_100a) implementation of M3L's VTMAE/VTT train step."""
+"""m3l_b200 — B200-native (sm_100a) implementation of M3L's VTMAE/VTT train step.
+
+    from m3l_b200 import VTT, VTMAE      # drop-in for models.pretrain_models.{VTT, VTMAE}
+"""
 __version__ = "0.1.0"
+
+from ._lib import M3LError  # noqa: F401
+
+
+def __getattr__(name):
+    if name in ("VTT", "VTMAE", "EarlyCNN", "Transformer", "pair"):
+        from . import vtmae
+        return getattr(vtmae, name)
+    if name == "vt_load":
+        from .data import vt_load
+        return vt_load
+    if name == "FusedTrainer":
+        from .trainer import FusedTrainer
+        return FusedTrainer
+    raise AttributeError(name)

@@ -20,7 +20,8 @@ namespace {
 __global__ void mask_indices_kernel(const float* __restrict__ noise, int n_total, m3l_mask_segments segs,
                                     int64_t* __restrict__ masked, int n_masked_total,
                                     int64_t* __restrict__ unmasked, int n_unmasked_total,
-                                    int32_t* __restrict__ slot_of_token) {
+                                    int32_t* __restrict__ slot_of_token, int32_t* __restrict__ unmasked_i32,
+                                    int32_t* __restrict__ masked_row_of_token, int n_masked_first, int batch) {
   extern __shared__ float keys[];
   const int b = blockIdx.x;
   const int s = blockIdx.y;
@@ -42,11 +43,19 @@ __global__ void mask_indices_kernel(const float* __restrict__ noise, int n_total
     }
     const int64_t tok = off + i;
     if (rank < nmask) {
-      masked[(size_t)b * n_masked_total + moff + rank] = tok;
-      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = -(1 + moff + rank);
+      const int k = moff + rank;
+      masked[(size_t)b * n_masked_total + k] = tok;
+      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = -(1 + k);
+      if (masked_row_of_token)
+        masked_row_of_token[(size_t)b * n_total + tok] =
+            k < n_masked_first ? b * n_masked_first + k
+                               : batch * n_masked_first + b * (n_masked_total - n_masked_first) + (k - n_masked_first);
     } else {
-      unmasked[(size_t)b * n_unmasked_total + uoff + rank - nmask] = tok;
-      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = uoff + rank - nmask;
+      const int k = uoff + rank - nmask;
+      unmasked[(size_t)b * n_unmasked_total + k] = tok;
+      if (unmasked_i32) unmasked_i32[(size_t)b * n_unmasked_total + k] = (int32_t)tok;
+      if (slot_of_token) slot_of_token[(size_t)b * n_total + tok] = k;
+      if (masked_row_of_token) masked_row_of_token[(size_t)b * n_total + tok] = -1;
     }
   }
 }
@@ -498,7 +507,9 @@ int ln_grid(int M, int warps_per_block) {
 using namespace m3l;
 
 extern "C" int m3l_mask_indices(const float* noise, int batch, int n_total, const m3l_mask_segments* segs,
-                                int64_t* masked, int64_t* unmasked, int32_t* slot_of_token, void* stream) {
+                                int64_t* masked, int64_t* unmasked, int32_t* slot_of_token,
+                                int32_t* unmasked_i32, int32_t* masked_row_of_token, int n_masked_first,
+                                void* stream) {
   M3L_REQUIRE(noise && segs && masked && unmasked, "mask_indices: null pointer");
   M3L_REQUIRE(segs->count >= 1 && segs->count <= M3L_MAX_SEGMENTS, "mask_indices: bad segment count %d", segs->count);
   if (batch == 0) return M3L_OK;
@@ -515,7 +526,8 @@ extern "C" int m3l_mask_indices(const float* noise, int batch, int n_total, cons
   dim3 grid(batch, segs->count);
   const int threads = maxlen <= 64 ? 64 : (maxlen <= 128 ? 128 : 256);
   mask_indices_kernel<<<grid, threads, maxlen * sizeof(float), (cudaStream_t)stream>>>(
-      noise, n_total, *segs, masked, nm, unmasked, nu, slot_of_token);
+      noise, n_total, *segs, masked, nm, unmasked, nu, slot_of_token, unmasked_i32, masked_row_of_token,
+      n_masked_first, batch);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -1,0 +1,396 @@
+"""Host-side sequencing of the CUDA kernels for the VTMAE step (forward, backward) and for the
+no-mask encoder pass.  Pure plumbing: every arithmetic step is a C-ABI kernel call (m3l_b200.ops);
+torch only allocates buffers and provides the stream, so the whole sequence can be captured in a
+CUDA graph (m3l_b200.trainer).
+
+Reference semantics followed (paths relative to /root/reference):
+  VTMAE.forward          models/pretrain_models.py:146-342   (early_conv_masking=False path)
+  VTMAE.get_embeddings   models/pretrain_models.py:588-668
+  vit_pytorch Transformer (pre-norm attention + feed-forward blocks, final LayerNorm): SURVEY.md A.2
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .arena import ParamArena
+
+_SM_COUNT = 148
+
+
+@dataclass
+class StackSpec:
+    prefix: str
+    dim: int
+    depth: int
+    heads: int
+    dim_head: int
+    mlp_dim: int
+
+    @property
+    def inner(self):
+        return self.heads * self.dim_head
+
+
+def _auto_splits(m_out: int, n_out: int, k_tokens: int) -> int:
+    bn = 256 if n_out % 256 == 0 else (128 if n_out % 128 == 0 else 64)
+    tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
+    kb = (k_tokens + 63) // 64
+    s = max(1, (_SM_COUNT + tiles - 1) // tiles)
+    return max(1, min(s, max(1, kb // 4)))
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, gview: torch.Tensor) -> None:
+    """gview[out, in] += dy[M, out]^T @ x[M, in]  (split-K over the token rows, fp32 red.add)."""
+    out_f, in_f = gview.shape
+    ops.gemm(dy, x, mn_major=True, out=gview, accumulate=True, splits=_auto_splits(out_f, in_f, dy.shape[0]))
+
+
+class GradView:
+    """Accessor of per-parameter views into a flat fp32 gradient buffer laid out like the arena."""
+
+    def __init__(self, arena: ParamArena, flat: torch.Tensor):
+        self.arena, self.flat = arena, flat
+
+    def __call__(self, name: str) -> torch.Tensor:
+        return self.arena.view(self.flat, name)
+
+
+# --------------------------------------------------------------------------------------------
+# transformer stack (vit_pytorch.vit.Transformer without its final LayerNorm)
+# --------------------------------------------------------------------------------------------
+def stack_fwd(A: ParamArena, spec: StackSpec, x: torch.Tensor, B: int, n: int, saved: Optional[list]):
+    """x: bf16 [B*n, dim].  Returns the residual stream after the last block."""
+    scale = spec.dim_head ** -0.5
+    M = x.shape[0]
+    for l in range(spec.depth):
+        pa, pf = f"{spec.prefix}.layers.{l}.0", f"{spec.prefix}.layers.{l}.1"
+        xn1, st1 = ops.layernorm_fwd(x, A.f32(pa + ".norm.weight"), A.f32(pa + ".norm.bias"),
+                                     want_stats=saved is not None)
+        qkv = ops.gemm(xn1, A.bf(pa + ".to_qkv.weight"))
+        o, lse = ops.attention_fwd(qkv, B, n, spec.heads, spec.dim_head, scale)
+        x_mid = ops.gemm(o, A.bf(pa + ".to_out.0.weight"), bias=A.f32(pa + ".to_out.0.bias"), residual=x)
+        xn2, st2 = ops.layernorm_fwd(x_mid, A.f32(pf + ".net.0.weight"), A.f32(pf + ".net.0.bias"),
+                                     want_stats=saved is not None)
+        pre = torch.empty((M, spec.mlp_dim), dtype=torch.bfloat16, device=x.device) if saved is not None else None
+        h = ops.gemm(xn2, A.bf(pf + ".net.1.weight"), bias=A.f32(pf + ".net.1.bias"), act=ops.GELU_FWD, aux_out=pre)
+        x_out = ops.gemm(h, A.bf(pf + ".net.4.weight"), bias=A.f32(pf + ".net.4.bias"), residual=x_mid)
+        if saved is not None:
+            saved.append((x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h))
+        x = x_out
+    return x
+
+
+def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: int, n: int, saved: list):
+    """dx: bf16 [B*n, dim] gradient w.r.t. the stack output.  Returns the gradient w.r.t. its input."""
+    scale = spec.dim_head ** -0.5
+    for l in reversed(range(spec.depth)):
+        pa, pf = f"{spec.prefix}.layers.{l}.0", f"{spec.prefix}.layers.{l}.1"
+        x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h = saved[l]
+        # ---- feed-forward branch: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
+        ops.colsum(dx, G(pf + ".net.4.bias"))
+        wgrad(dx, h, G(pf + ".net.4.weight"))
+        dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre)
+        ops.colsum(dpre, G(pf + ".net.1.bias"))
+        wgrad(dpre, xn2, G(pf + ".net.1.weight"))
+        dxn2 = ops.gemm(dpre, A.bf_t(pf + ".net.1.weight"))
+        dx_mid = ops.layernorm_bwd(dxn2, x_mid, st2, A.f32(pf + ".net.0.weight"), dgamma=G(pf + ".net.0.weight"),
+                                   dbeta=G(pf + ".net.0.bias"), skip=dx)
+        # ---- attention branch: x_mid = x + Wo attn(Wqkv LN1(x)) + bo
+        ops.colsum(dx_mid, G(pa + ".to_out.0.bias"))
+        wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
+        do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"))
+        dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale)
+        wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
+        dxn1 = ops.gemm(dqkv, A.bf_t(pa + ".to_qkv.weight"))
+        dx = ops.layernorm_bwd(dxn1, x, st1, A.f32(pa + ".norm.weight"), dgamma=G(pa + ".norm.weight"),
+                               dbeta=G(pa + ".norm.bias"), skip=dx_mid)
+    return dx
+
+
+# --------------------------------------------------------------------------------------------
+# geometry of one call (which modalities are present)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Geometry:
+    use_vision: bool
+    nt: int                      # tactile sensors present in this call
+    n_img: int
+    n_tac: int                   # per sensor
+    nm_img: int
+    nm_tac: int                  # per sensor
+    segs: List[Tuple[int, int, int]] = field(default_factory=list)
+
+    @property
+    def n(self):
+        return self.n_img + self.nt * self.n_tac
+
+    @property
+    def nv_img(self):
+        return self.n_img - self.nm_img
+
+    @property
+    def nv_tac(self):            # all sensors
+        return self.nt * (self.n_tac - self.nm_tac)
+
+    @property
+    def nv(self):
+        return self.nv_img + self.nv_tac
+
+    @property
+    def nm_tac_total(self):
+        return self.nt * self.nm_tac
+
+    @property
+    def nm(self):
+        return self.nm_img + self.nm_tac_total
+
+
+def make_geometry(cfg, use_vision: bool, use_tactile: bool) -> Geometry:
+    nt = cfg.num_tactiles if (cfg.num_tactiles > 0 and use_tactile) else 0
+    n_img = cfg.n_img if use_vision else 0
+    n_tac = cfg.n_tac if nt else 0
+    n = n_img + nt * n_tac
+    # Python-float truncations exactly as pretrain_models.py:223-227
+    num_masked = int(cfg.masking_ratio * n)
+    nm_img = int(num_masked * (n_img / n))
+    nm_tac = (num_masked - nm_img) // cfg.num_tactiles if nt else 0
+    segs = ([(0, n_img, nm_img)] if n_img else []) + [(n_img + i * n_tac, n_tac, nm_tac) for i in range(nt)]
+    return Geometry(use_vision, nt, n_img, n_tac, nm_img, nm_tac, segs)
+
+
+class Tables:
+    """Static per-(geometry, batch) index tables and additive position tables (device tensors)."""
+
+    def __init__(self, model, geo: Geometry, B: int, device):
+        cfg = model.cfg
+        i32 = dict(dtype=torch.int32, device=device)
+        self.B = B
+        # token class (modality) per present token and per visible slot
+        cls = [0] * geo.n_img + [1 + i for i in range(geo.nt) for _ in range(geo.n_tac)]
+        self.tok_class = torch.tensor(cls, **i32)
+        nv_t = geo.n_tac - geo.nm_tac
+        slot_cls = [0] * geo.nv_img + [1 + i for i in range(geo.nt) for _ in range(nv_t)]
+        self.slot_class = torch.tensor(slot_cls if slot_cls else [0], **i32)
+        # masked path: embedding rows -> encoder rows
+        b = torch.arange(B, device=device)[:, None]
+        self.enc_dst_img = (b * geo.nv + torch.arange(geo.nv_img, device=device)[None]).reshape(-1).to(torch.int32)
+        self.enc_dst_tac = (b * geo.nv + geo.nv_img + torch.arange(geo.nv_tac, device=device)[None]).reshape(-1).to(torch.int32)
+        self.enc_cls_img = torch.zeros(B * geo.nv_img, **i32)
+        self.enc_cls_tac = torch.tensor(slot_cls[geo.nv_img:] * B if geo.nv_tac else [0], **i32)
+        # all-token path (get_embeddings)
+        self.all_dst_img = (b * geo.n + torch.arange(geo.n_img, device=device)[None]).reshape(-1).to(torch.int32)
+        self.all_dst_tac = (b * geo.n + geo.n_img + torch.arange(geo.nt * geo.n_tac, device=device)[None]).reshape(-1).to(torch.int32)
+        self.all_cls_img = torch.zeros(max(B * geo.n_img, 1), **i32)
+        self.all_cls_tac = torch.tensor((cls[geo.n_img:] * B) if geo.nt else [0], **i32)
+        self.all_pos_img = torch.arange(geo.n_img, device=device).repeat(B).to(torch.int32)
+        self.all_pos_tac = (geo.n_img + torch.arange(geo.nt * geo.n_tac, device=device)).repeat(B).to(torch.int32)
+        # sin-cos tables of the present tokens (constants, fp32)
+        if cfg.use_sincosmod_encodings:
+            enc, dec = [], []
+            if geo.use_vision:
+                enc.append(model.image_enc_pos_embedding[0]); dec.append(model.image_dec_pos_embedding[0])
+            if geo.nt:
+                k = geo.nt * geo.n_tac
+                enc.append(model.tactile_enc_pos_embedding[0, :k]); dec.append(model.tactile_dec_pos_embedding[0, :k])
+            self.enc_pos = torch.cat(enc, 0).to(device=device, dtype=torch.float32).contiguous()
+            self.dec_pos = torch.cat(dec, 0).to(device=device, dtype=torch.float32).contiguous()
+        else:
+            self.enc_pos = self.dec_pos = None
+
+
+# --------------------------------------------------------------------------------------------
+# token embedding:  LN(P) -> Linear -> LN(D) (+ modality + position)   [early_conv_masking=False]
+# --------------------------------------------------------------------------------------------
+def _embed_fwd(model, A, geo, tabs, x, B, tok_idx, masked: bool, saved: Optional[dict], unmasked32=None):
+    """Returns the encoder input rows (bf16).  masked=True: only the visible tokens (rows [B, nv]);
+    masked=False: all tokens (rows [B, n])."""
+    cfg = model.cfg
+    dev = A.device
+    D = cfg.dim
+    n_rows = geo.nv if masked else geo.n
+    x0 = torch.empty((B * n_rows, D), dtype=torch.bfloat16, device=dev)
+    sincos = cfg.use_sincosmod_encodings
+    mods = []
+    if geo.use_vision:
+        ps = ops.make_patch_source([x["image"]], model.ph_img, model.pw_img, 0)
+        ncols = geo.nv_img if masked else geo.n_img
+        mods.append(("image", ps, 0, ncols, tabs.enc_dst_img if masked else tabs.all_dst_img,
+                     tabs.enc_cls_img if masked else tabs.all_cls_img, None if masked else tabs.all_pos_img))
+    if geo.nt:
+        ps = ops.make_patch_source([x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac, geo.n_img)
+        ncols = geo.nv_tac if masked else geo.nt * geo.n_tac
+        mods.append(("tactile", ps, geo.nv_img if masked else 0, ncols, tabs.enc_dst_tac if masked else tabs.all_dst_tac,
+                     tabs.enc_cls_tac if masked else tabs.all_cls_tac, None if masked else tabs.all_pos_tac))
+    for name, ps, col0, ncols, dst, cls_rows, pos_rows in mods:
+        pre = f"{name}_patch_to_emb"
+        a, xhat = ops.patch_layernorm(ps, B, ncols, A.f32(pre + ".0.weight"), A.f32(pre + ".0.bias"),
+                                      tok_idx=tok_idx if masked else None, col0=col0, want_xhat=saved is not None)
+        e = ops.gemm(a, A.bf(pre + ".1.weight"), bias=A.f32(pre + ".1.bias"), out_dtype=torch.float32)
+        if masked:
+            # position row of embedding row (b, jj) = unmasked[b, col0 + jj]
+            pos_rows = unmasked32[:, col0:col0 + ncols].contiguous().view(-1)
+        if sincos:
+            add0, add0_row, add1, add1_row = A.f32("encoder_modality_embedding.weight"), cls_rows, tabs.enc_pos, pos_rows
+        else:
+            add0 = add0_row = None
+            add1, add1_row = A.f32("encoder.pos_embedding")[0, 1:geo.n + 1], pos_rows
+        _, st = ops.layernorm_fwd(e, A.f32(pre + ".2.weight"), A.f32(pre + ".2.bias"), out=x0, dst_row=dst,
+                                  add0=add0, add0_row=add0_row, add1=add1, add1_row=add1_row,
+                                  want_stats=saved is not None)
+        if saved is not None:
+            saved[name] = (a, xhat, e, st, dst, pos_rows)
+    return x0
+
+
+def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
+    cfg = model.cfg
+    n_rows = geo.nv if masked else geo.n
+    # broadcast adds: modality embedding / learned positions
+    if cfg.use_sincosmod_encodings:
+        if masked:
+            ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.slot_class, dclass=G("encoder_modality_embedding.weight"))
+        else:
+            ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.tok_class, dclass=G("encoder_modality_embedding.weight"))
+    else:
+        gpos = G("encoder.pos_embedding")[0, 1:geo.n + 1]
+        if masked:
+            ops.rowclass_sum(dx0, B, n_rows, row_pos=saved["unmasked32"].view(-1), dpos=gpos)
+        else:
+            pos = torch.arange(geo.n, device=dx0.device, dtype=torch.int32).repeat(B)
+            ops.rowclass_sum(dx0, B, n_rows, row_pos=pos, dpos=gpos)
+    for name in ("image", "tactile"):
+        if name not in saved:
+            continue
+        pre = f"{name}_patch_to_emb"
+        a, xhat, e, st, dst, _ = saved[name]
+        de = ops.layernorm_bwd(dx0, e, st, A.f32(pre + ".2.weight"), dgamma=G(pre + ".2.weight"),
+                               dbeta=G(pre + ".2.bias"), src_row=dst)
+        ops.colsum(de, G(pre + ".1.bias"))
+        wgrad(de, a, G(pre + ".1.weight"))
+        da = ops.gemm(de, A.bf_t(pre + ".1.weight"))
+        ops.ln_param_grad(da, xhat, G(pre + ".0.weight"), G(pre + ".0.bias"))
+
+
+# --------------------------------------------------------------------------------------------
+# masked-autoencoder forward / backward
+# --------------------------------------------------------------------------------------------
+def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geometry, training: bool):
+    """Returns (loss_acc fp32[1], ctx).  ctx holds what mae_backward needs (None if not training)."""
+    cfg, A = model.cfg, model.arena
+    dev = A.device
+    B = noise.shape[0]
+    tabs = model.tables(geo, B)
+    ctx = {"geo": geo, "B": B, "x": x} if training else None
+    masked, unmasked, slots, unmasked32, mrow = ops.mask_indices(noise, geo.segs, extra=True, n_masked_first=geo.nm_img)
+    model.last_masked_indices, model.last_unmasked_indices = masked, unmasked
+    emb_saved = {"unmasked32": unmasked32} if training else None
+    x0 = _embed_fwd(model, A, geo, tabs, x, B, unmasked, True, emb_saved, unmasked32=unmasked32)
+    enc_saved = [] if training else None
+    xe = stack_fwd(A, model.enc_spec, x0, B, geo.nv, enc_saved)
+    enc_out, st_enc = ops.layernorm_fwd(xe, A.f32("encoder.transformer.norm.weight"), A.f32("encoder.transformer.norm.bias"),
+                                        want_stats=training)
+    if model.has_enc_to_dec:
+        d = ops.gemm(enc_out, A.bf("enc_to_dec.weight"), bias=A.f32("enc_to_dec.bias"))
+    else:
+        d = enc_out
+    if cfg.use_sincosmod_encodings:
+        z = ops.decoder_assemble_fwd(d, geo.nv, A.f32("mask_token"), slots, B, geo.n,
+                                     add0=A.f32("decoder_modality_embedding.weight"), tok_class=tabs.tok_class,
+                                     add1=tabs.dec_pos)
+    else:
+        z = ops.decoder_assemble_fwd(d, geo.nv, A.f32("mask_token"), slots, B, geo.n,
+                                     add1=A.f32("decoder_pos_emb.weight")[:geo.n])
+    dec_saved = [] if training else None
+    xd = stack_fwd(A, model.dec_spec, z, B, geo.n, dec_saved)
+    # final LayerNorm, written straight into the stacked head inputs (masked rows only)
+    gathered, st_dec = ops.layernorm_fwd(xd, A.f32("decoder.norm.weight"), A.f32("decoder.norm.bias"),
+                                         out_rows=B * geo.nm, dst_row=mrow, want_stats=training)
+    loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
+    heads = []
+    r_img = B * geo.nm_img
+    if geo.nt:
+        g_tac = gathered[r_img:]
+        pred = ops.gemm(g_tac, A.bf("to_tactiles.weight"), bias=A.f32("to_tactiles.bias"), out_dtype=torch.float32)
+        ps = ops.make_patch_source([x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac, geo.n_img)
+        dpred = ops.mse_loss(ps, B, geo.nm_tac_total, pred, 10.0 / pred.numel(), loss_acc, tok_idx=masked, col0=geo.nm_img)
+        heads.append(("to_tactiles", g_tac, dpred, r_img))
+    if geo.use_vision:
+        g_img = gathered[:r_img]
+        pred = ops.gemm(g_img, A.bf("to_pixels.weight"), bias=A.f32("to_pixels.bias"), out_dtype=torch.float32)
+        ps = ops.make_patch_source([x["image"]], model.ph_img, model.pw_img, 0)
+        dpred = ops.mse_loss(ps, B, geo.nm_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=masked, col0=0)
+        heads.append(("to_pixels", g_img, dpred, 0))
+    if training:
+        ctx.update(tabs=tabs, slots=slots, mrow=mrow, emb=emb_saved, enc=enc_saved, xe=xe, st_enc=st_enc,
+                   enc_out=enc_out, dec=dec_saved, xd=xd, st_dec=st_dec, heads=heads, n_gathered=gathered.shape[0])
+    return loss_acc, ctx
+
+
+def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
+    """Heads + decoder part of the backward (its gradients are final first: SURVEY.md §8e)."""
+    cfg, A = model.cfg, model.arena
+    G = GradView(A, gflat)
+    geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
+    Dd = cfg.decoder_dim
+    dgath = torch.empty((ctx["n_gathered"], Dd), dtype=torch.bfloat16, device=A.device)
+    for name, g_in, dpred, row0 in ctx["heads"]:
+        ops.colsum(dpred, G(name + ".bias"))
+        wgrad(dpred, g_in, G(name + ".weight"))
+        ops.gemm(dpred, A.bf_t(name + ".weight"), out=dgath[row0:row0 + g_in.shape[0]])
+    dxd = ops.layernorm_bwd(dgath, ctx["xd"], ctx["st_dec"], A.f32("decoder.norm.weight"),
+                            dgamma=G("decoder.norm.weight"), dbeta=G("decoder.norm.bias"), src_row=ctx["mrow"])
+    dz = stack_bwd(A, G, model.dec_spec, dxd, B, geo.n, ctx["dec"])
+    if cfg.use_sincosmod_encodings:
+        dd = ops.decoder_assemble_bwd(dz, ctx["slots"], B, geo.n, geo.nv, dmask_token=G("mask_token"),
+                                      dadd0=G("decoder_modality_embedding.weight"), tok_class=tabs.tok_class)
+    else:
+        dd = ops.decoder_assemble_bwd(dz, ctx["slots"], B, geo.n, geo.nv, dmask_token=G("mask_token"),
+                                      dadd1=G("decoder_pos_emb.weight")[:geo.n])
+    ctx["dd"] = dd
+
+
+def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
+    cfg, A = model.cfg, model.arena
+    G = GradView(A, gflat)
+    geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
+    dd = ctx["dd"]
+    if model.has_enc_to_dec:
+        ops.colsum(dd, G("enc_to_dec.bias"))
+        wgrad(dd, ctx["enc_out"], G("enc_to_dec.weight"))
+        denc = ops.gemm(dd, A.bf_t("enc_to_dec.weight"))
+    else:
+        denc = dd
+    dxe = ops.layernorm_bwd(denc, ctx["xe"], ctx["st_enc"], A.f32("encoder.transformer.norm.weight"),
+                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"))
+    dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
+    _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
+
+
+# --------------------------------------------------------------------------------------------
+# no-mask encoder pass (get_embeddings)
+# --------------------------------------------------------------------------------------------
+def embeddings_forward(model, x, geo: Geometry, B: int, training: bool):
+    A = model.arena
+    tabs = model.tables(geo, B)
+    emb_saved = {} if training else None
+    x0 = _embed_fwd(model, A, geo, tabs, x, B, None, False, emb_saved)
+    enc_saved = [] if training else None
+    xe = stack_fwd(A, model.enc_spec, x0, B, geo.n, enc_saved)
+    out, st = ops.layernorm_fwd(xe, A.f32("encoder.transformer.norm.weight"), A.f32("encoder.transformer.norm.bias"),
+                                want_stats=training)
+    ctx = dict(geo=geo, B=B, tabs=tabs, emb=emb_saved, enc=enc_saved, xe=xe, st=st) if training else None
+    return out, ctx
+
+
+def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor):
+    A = model.arena
+    G = GradView(A, gflat)
+    geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
+    dxe = ops.layernorm_bwd(dout, ctx["xe"], ctx["st"], A.f32("encoder.transformer.norm.weight"),
+                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"))
+    dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.n, ctx["enc"])
+    _embed_bwd(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])

@@ -82,8 +82,9 @@ def make_segments(segs):
     return s
 
 
-def mask_indices(noise: torch.Tensor, segs, want_slots: bool = True):
-    """noise fp32 [B, n_total] -> (masked int64 [B, nm], unmasked int64 [B, nu], slot_of_token int32 [B, n])."""
+def mask_indices(noise: torch.Tensor, segs, want_slots: bool = True, extra: bool = False, n_masked_first: int = 0):
+    """noise fp32 [B, n_total] -> (masked int64 [B, nm], unmasked int64 [B, nu], slot_of_token int32 [B, n]).
+    extra=True additionally returns (unmasked int32, masked_row_of_token int32 [B, n])."""
     _req_cuda(noise)
     assert noise.dtype == torch.float32 and noise.is_contiguous()
     B, n = noise.shape
@@ -93,8 +94,12 @@ def mask_indices(noise: torch.Tensor, segs, want_slots: bool = True):
     unmasked = torch.empty((B, nu), dtype=torch.int64, device=noise.device)
     slots = torch.empty((B, n), dtype=torch.int32, device=noise.device) if want_slots else None
     cs = make_segments(segs)
+    u32 = torch.empty((B, nu), dtype=torch.int32, device=noise.device) if extra else None
+    mrow = torch.empty((B, n), dtype=torch.int32, device=noise.device) if extra else None
     check(_lib.load().m3l_mask_indices(ptr(noise), B, n, C.byref(cs), ptr(masked), ptr(unmasked), ptr(slots),
-                                       current_stream()), "m3l_mask_indices")
+                                       ptr(u32), ptr(mrow), n_masked_first, current_stream()), "m3l_mask_indices")
+    if extra:
+        return masked, unmasked, slots, u32, mrow
     return masked, unmasked, slots
 
 
@@ -254,3 +259,32 @@ def cast_bf16(src, dst):
 def transpose_cast_bf16(src_base, dst_base, descs_dev, count):
     check(_lib.load().m3l_transpose_cast_bf16(ptr(src_base), ptr(dst_base), ptr(descs_dev), count,
                                               current_stream()), "m3l_transpose_cast_bf16")
+
+
+# ------------------------------------------------------------------------------------------
+# launch accounting (bench.py reports how many of our kernels run per step)
+# ------------------------------------------------------------------------------------------
+_launches = 0
+_orig_check = check
+
+
+def _counting_check(status, what):
+    global _launches
+    _launches += 1
+    _orig_check(status, what)
+
+
+class LaunchCounter:
+    """Counts C-ABI kernel launches issued inside the `with` block (each ops.* call = one launch)."""
+
+    def __enter__(self):
+        global check, _launches
+        self._start = _launches
+        check = _counting_check
+        return self
+
+    def __exit__(self, *exc):
+        global check
+        self.count = _launches - self._start
+        check = _orig_check
+        return False

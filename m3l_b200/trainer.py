@@ -1,0 +1,190 @@
+"""Fused VTMAE train step: zero_grad -> forward -> backward -> [gradient all-reduce] ->
+clip_grad_norm_(0.5) -> AdamW.step -> bf16 shadow refresh, as one kernel sequence over flat arenas,
+optionally replayed from CUDA graphs.  Semantics of /root/reference/models/pretrain_models.py:707-711
+with torch.optim.AdamW defaults (:670-676).
+
+Data parallel (one process per GPU): identical replicas, rank-sharded batch; the flat gradient arena
+is all-reduced (AVG) in two buckets — heads+decoder as soon as their backward is done, overlapping
+the encoder backward on a side stream, then encoder+embeddings.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import engine, ops
+from ._lib import M3LError
+
+
+class FusedAdamW:
+    """Minimal optimizer facade (param_groups / state_dict) over the trainer's flat moment arenas."""
+
+    def __init__(self, trainer, lr, betas, eps, weight_decay):
+        self._t = trainer
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                  params=[trainer.model.arena.params[n] for n in trainer.model.arena.names])]
+
+    def zero_grad(self, set_to_none: bool = True):
+        self._t.gflat.zero_()
+
+    def state_dict(self):
+        t = self._t
+        return dict(step=float(t.state[0].item()), exp_avg=t.m.clone(), exp_avg_sq=t.v.clone(),
+                    param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+
+    def load_state_dict(self, sd):
+        t = self._t
+        t.state[0] = sd["step"]
+        t.m.copy_(sd["exp_avg"]); t.v.copy_(sd["exp_avg_sq"])
+
+
+class FusedTrainer:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=0.5,
+                 process_group=None, use_cuda_graph=True):
+        self.model = model
+        A = model.arena
+        dev = A.device
+        self.gflat = torch.zeros(A.total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.gflat)
+        self.v = torch.zeros_like(self.gflat)
+        self.state = torch.zeros(3, dtype=torch.float64, device=dev)  # step, sumsq, total norm
+        self.max_norm = max_norm
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.use_graph = use_cuda_graph
+        self.opt = FusedAdamW(self, lr, betas, eps, weight_decay)
+        self._graphs: Dict = {}
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.kernel_launches_per_step = None
+
+    def optimizer_facade(self):
+        return self.opt
+
+    # ------------------------------------------------------------------------------------
+    def _plan(self, geo):
+        model, A = self.model, self.model.arena
+        live = model.live_param_names(geo, True)
+        dec_names = [k for k in live if k.startswith(("to_pixels", "to_tactiles", "decoder.", "mask_token",
+                                                      "decoder_modality_embedding", "enc_to_dec", "decoder_pos_emb"))]
+        enc_names = [k for k in live if k not in dec_names]
+        return live, A.ranges(live), A.ranges(dec_names), A.ranges(enc_names)
+
+    def _phase_a(self, xs, noise, geo, box):
+        self.gflat.zero_()
+        self.state[1:2].zero_()
+        loss_acc, ctx = engine.mae_forward(self.model, xs, noise, geo, training=True)
+        engine.mae_backward_decoder(self.model, ctx, self.gflat)
+        box["loss"], box["ctx"] = loss_acc, ctx
+
+    def _phase_b(self, box):
+        engine.mae_backward_encoder(self.model, box["ctx"], self.gflat)
+
+    def _phase_c(self, ranges):
+        A = self.model.arena
+        g = self.opt.param_groups[0]
+        for s, e in ranges:
+            ops.grad_sumsq(self.gflat[s:e], self.state)
+        ops.optimizer_step_begin(self.state)
+        for s, e in ranges:
+            ops.clip_adamw(A.flat[s:e], self.gflat[s:e], self.m[s:e], self.v[s:e], self.state, lr=g["lr"],
+                           betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], max_norm=self.max_norm)
+        A.refresh_shadows()
+
+    def _allreduce(self, ranges, after_event):
+        self.comm_stream.wait_event(after_event)
+        with torch.cuda.stream(self.comm_stream):
+            for s, e in ranges:
+                torch.distributed.all_reduce(self.gflat[s:e], op=torch.distributed.ReduceOp.AVG, group=self.pg)
+
+    # ------------------------------------------------------------------------------------
+    def step(self, x, noise=None, use_vision=True, use_tactile=True):
+        model = self.model
+        A = model._sync()
+        xs, geo, B = model._prep_inputs(x, use_vision, use_tactile)
+        if noise is None:
+            noise = torch.rand(B, geo.n, device=A.device)
+        noise = noise.to(device=A.device, dtype=torch.float32).contiguous()
+        live, ranges, dec_ranges, enc_ranges = self._plan(geo)
+        for k in live:
+            p = A.params[k]
+            if p.grad is None or p.grad.data_ptr() != A.view(self.gflat, k).data_ptr():
+                p.grad = A.view(self.gflat, k)
+        lr = self.opt.param_groups[0]["lr"]
+        if not self.use_graph:
+            box = {}
+            self._phase_a(xs, noise, geo, box)
+            if self.world > 1:
+                ev = torch.cuda.Event(); ev.record()
+                self._allreduce(dec_ranges, ev)
+            self._phase_b(box)
+            if self.world > 1:
+                ev2 = torch.cuda.Event(); ev2.record()
+                self._allreduce(enc_ranges, ev2)
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._phase_c(ranges)
+            A._version_seen = A.version()
+            return box["loss"].reshape(())
+        key = (geo.use_vision, geo.nt, B, lr)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(xs, noise, geo, ranges)
+            self._graphs[key] = g
+        for k, v in xs.items():
+            g["xs"][k].copy_(v, non_blocking=True)
+        g["noise"].copy_(noise, non_blocking=True)
+        if self.world == 1:
+            g["all"].replay()
+        else:
+            g["a"].replay()
+            ev = torch.cuda.Event(); ev.record()
+            self._allreduce(dec_ranges, ev)
+            g["b"].replay()
+            ev2 = torch.cuda.Event(); ev2.record()
+            self._allreduce(enc_ranges, ev2)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            g["c"].replay()
+        A._version_seen = A.version()
+        return g["box"]["loss"].reshape(())
+
+    def _capture(self, xs, noise, geo, ranges):
+        """Warm-up once eagerly (lazy kernel attributes, allocator), then capture."""
+        sx = {k: v.clone() for k, v in xs.items()}
+        sn = noise.clone()
+        # eager warm-up on a side stream must not advance the optimizer: snapshot & restore state
+        snap = (self.model.arena.flat.clone(), self.m.clone(), self.v.clone(), self.state.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            box = {}
+            self._phase_a(sx, sn, geo, box)
+            self._phase_b(box)
+            self._phase_c(ranges)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.model.arena.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.state.copy_(snap[3])
+        self.model.arena.refresh_shadows()
+        out = {"xs": sx, "noise": sn, "box": {}}
+        counter = ops.LaunchCounter()
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with counter, torch.cuda.graph(g):
+                self._phase_a(sx, sn, geo, out["box"])
+                self._phase_b(out["box"])
+                self._phase_c(ranges)
+            out["all"] = g
+        else:
+            ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            pool = torch.cuda.graph_pool_handle()
+            with counter:
+                with torch.cuda.graph(ga, pool=pool):
+                    self._phase_a(sx, sn, geo, out["box"])
+                with torch.cuda.graph(gb, pool=pool):
+                    self._phase_b(out["box"])
+                with torch.cuda.graph(gc, pool=pool):
+                    self._phase_c(ranges)
+            out.update(a=ga, b=gb, c=gc)
+        self.kernel_launches_per_step = counter.count
+        return out

@@ -1,0 +1,438 @@
+"""Drop-in `VTT` / `VTMAE` / `EarlyCNN` / `Transformer` modules with the reference's constructor
+arguments, attribute names, obs-dict inputs, loss / latent outputs and state_dict layout
+(/root/reference/models/pretrain_models.py:37-56,59-143,717-786; vit_pytorch.vit.Transformer),
+computing through the sm_100a kernels behind the C-ABI.  There is no CPU path: calling a module
+whose parameters are not on a CUDA device raises.
+
+    from m3l_b200 import VTT, VTMAE        # instead of: from models.pretrain_models import VTT, VTMAE
+
+Extra (optional) argument for parity testing: `forward(x, ..., noise=...)` supplies the uniform
+draws the reference takes from torch.rand (image, tactile1, tactile2 order; pretrain_models.py:229,237).
+"""
+from __future__ import annotations
+
+import math
+import random
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import engine, ops
+from ._lib import M3LError
+from .arena import ParamArena
+
+
+def pair(t):
+    return t if isinstance(t, tuple) else (t, t)
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers mirroring vit_pytorch's module tree (names matter for state_dict parity)
+# --------------------------------------------------------------------------------------------
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.0):
+        super().__init__()
+        self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads, self.dim_head = heads, dim_head
+        self.scale = dim_head ** -0.5
+        self.norm = nn.LayerNorm(dim)
+        self.attend = nn.Softmax(dim=-1)
+        self.dropout = nn.Dropout(dropout)
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        if heads == 1 and dim_head == dim:
+            raise M3LError("heads == 1 with dim_head == dim (identity output projection) is not supported")
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+
+
+class Transformer(nn.Module):
+    """vit_pytorch.vit.Transformer(dim, depth, heads, dim_head, mlp_dim, dropout=0.)."""
+
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.0):
+        super().__init__()
+        if dim_head != 64:
+            raise M3LError(f"dim_head={dim_head}: the sm_100a attention kernel supports dim_head == 64 only")
+        self.dim, self.depth, self.heads, self.dim_head, self.mlp_dim, self.p_drop = dim, depth, heads, dim_head, mlp_dim, dropout
+        self.norm = nn.LayerNorm(dim)
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout),
+                                              FeedForward(dim, mlp_dim, dropout=dropout)]))
+        self._arena: Optional[ParamArena] = None
+
+    def _own_arena(self) -> ParamArena:
+        dev = self.norm.weight.device
+        if dev.type != "cuda":
+            raise M3LError("m3l_b200.Transformer needs CUDA parameters (there is no CPU fallback)")
+        if self._arena is None or self._arena.device != dev:
+            self._arena = ParamArena([("t." + k, p) for k, p in self.named_parameters()], dev)
+        self._arena.sync()
+        return self._arena
+
+    def forward(self, x):
+        """x: (B, n, dim) -> (B, n, dim); differentiable w.r.t. x and the parameters."""
+        if self.p_drop > 0 and self.training:
+            raise M3LError("dropout > 0 in training mode is not supported by the fused kernels")
+        A = self._own_arena()
+        spec = engine.StackSpec("t", self.dim, self.depth, self.heads, self.dim_head, self.mlp_dim)
+        names = list(A.names)
+        return _TransformerFn.apply(self, A, spec, x, *[A.params[n] for n in names])
+
+
+class _TransformerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, A, spec, x, *params):
+        B, n, D = x.shape
+        need = any(ctx.needs_input_grad)
+        xb = x.detach().reshape(B * n, D).to(torch.bfloat16).contiguous()
+        saved = [] if need else None
+        xe = engine.stack_fwd(A, spec, xb, B, n, saved)
+        out, st = ops.layernorm_fwd(xe, A.f32("t.norm.weight"), A.f32("t.norm.bias"), want_stats=need)
+        ctx.c = (A, spec, saved, xe, st, B, n, D)
+        return out.float().reshape(B, n, D)
+
+    @staticmethod
+    def backward(ctx, gout):
+        A, spec, saved, xe, st, B, n, D = ctx.c
+        gflat = A.new_grad_buffer()
+        G = engine.GradView(A, gflat)
+        dout = gout.reshape(B * n, D).to(torch.bfloat16).contiguous()
+        dxe = ops.layernorm_bwd(dout, xe, st, A.f32("t.norm.weight"), dgamma=G("t.norm.weight"), dbeta=G("t.norm.bias"))
+        dx = engine.stack_bwd(A, G, spec, dxe, B, n, saved)
+        return (None, None, None, dx.float().reshape(B, n, D), *[A.view(gflat, nm) for nm in A.names])
+
+
+class Patchify(nn.Module):
+    """einops Rearrange('b c (h p1) (w p2) -> b (h w) (p1 p2 c)') (pretrain_models.py:768,775).
+    Parameter-free; on the hot path the rearrangement is fused into the gather kernels."""
+
+    def __init__(self, p1, p2):
+        super().__init__()
+        self.p1, self.p2 = p1, p2
+
+    def forward(self, x):
+        b, c, H, W = x.shape
+        h, w = H // self.p1, W // self.p2
+        return x.reshape(b, c, h, self.p1, w, self.p2).permute(0, 2, 4, 3, 5, 1).reshape(b, h * w, self.p1 * self.p2 * c)
+
+
+class EarlyCNN(nn.Module):
+    """Conv stem used when early_conv_masking=True (pretrain_models.py:37-56)."""
+
+    def __init__(self, in_channels, encoder_dim, key="image"):
+        super().__init__()
+        self.key = key
+        self.conv1 = nn.Conv2d(in_channels, encoder_dim // 8, 4, stride=2, padding=1)
+        self.conv2 = nn.Conv2d(encoder_dim // 8, encoder_dim // 4, 4, stride=2, padding=1)
+        if key == "image":
+            self.conv3 = nn.Conv2d(encoder_dim // 4, encoder_dim // 2, 4, stride=2, padding=1)
+        else:
+            self.conv3 = nn.Conv2d(encoder_dim // 4, encoder_dim // 2, 3, stride=1, padding=1)
+        self.conv4 = nn.Conv2d(encoder_dim // 2, encoder_dim, 1)
+
+
+class VTT(nn.Module):
+    """Encoder container (pretrain_models.py:717-786): patch embeddings, learned positions and the
+    transformer.  Same keyword-only constructor as the reference."""
+
+    def __init__(self, *, image_size, tactile_size, image_patch_size, tactile_patch_size, dim, depth, heads, mlp_dim,
+                 image_channels=3, tactile_channels=3, dim_head=64, dropout=0., emb_dropout=0, num_tactiles=2,
+                 frame_stack=1):
+        super().__init__()
+        image_height, image_width = pair(image_size)
+        tactile_height, tactile_width = pair(tactile_size)
+        image_patch_height, image_patch_width = pair(image_patch_size)
+        tactile_patch_height, tactile_patch_width = pair(tactile_patch_size)
+        self.image_height, self.image_width = image_height, image_width
+        self.tactile_height, self.tactile_width = tactile_height, tactile_width
+        self.image_patch_height, self.image_patch_width = image_patch_height, image_patch_width
+        self.tactile_patch_height, self.tactile_patch_width = tactile_patch_height, tactile_patch_width
+        self.image_channels, self.tactile_channels = image_channels, tactile_channels
+        self.frame_stack = frame_stack
+        assert image_height % image_patch_height == 0 and image_width % image_patch_width == 0, \
+            'Image dimensions must be divisible by the patch size.'
+        assert tactile_height % tactile_patch_height == 0 and tactile_width % tactile_patch_width == 0, \
+            'Tactile dimensions must be divisible by the patch size.'
+        num_patches_image = (image_height // image_patch_height) * (image_width // image_patch_width)
+        num_patches_tactile = (tactile_height // tactile_patch_height) * (tactile_width // tactile_patch_width) * num_tactiles
+        num_patches = num_patches_image + num_patches_tactile
+        image_patch_dim = image_channels * image_patch_height * image_patch_width
+        tactile_patch_dim = tactile_channels * tactile_patch_height * tactile_patch_width
+        self.image_to_patch_embedding = nn.Sequential(
+            Patchify(image_patch_height, image_patch_width), nn.LayerNorm(image_patch_dim),
+            nn.Linear(image_patch_dim, dim), nn.LayerNorm(dim))
+        self.tactile_to_patch_embedding = nn.Sequential(
+            Patchify(tactile_patch_height, tactile_patch_width), nn.LayerNorm(tactile_patch_dim),
+            nn.Linear(tactile_patch_dim, dim), nn.LayerNorm(dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.to_latent = nn.Identity()
+
+
+def _sincos_2d(nx: int, ny: int, gen_channels: int, out_channels: int) -> torch.Tensor:
+    """Fixed 2-D sin/cos table as positional_encodings.PositionalEncoding2D(gen_channels) produces for a
+    (1, nx, ny, out_channels) input, flattened to (nx*ny, C) (pretrain_models.py:120-140): interleaved
+    sin/cos of pos * 10000^(-2i/ch); first ch channels encode the row, next ch the column."""
+    ch = int(math.ceil(gen_channels / 4) * 2)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, ch, 2).float() / ch))
+
+    def enc(n):
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * inv_freq[None, :]
+        return torch.stack((ang.sin(), ang.cos()), dim=-1).flatten(-2, -1)
+
+    emb = torch.zeros(nx, ny, 2 * ch)
+    emb[:, :, :ch] = enc(nx)[:, None, :]
+    emb[:, :, ch:] = enc(ny)[None, :, :]
+    return emb[:, :, :out_channels].reshape(nx * ny, -1)
+
+
+class VTMAE(nn.Module):
+    """Masked multimodal autoencoder (pretrain_models.py:59-715), same keyword-only constructor."""
+
+    def __init__(self, *, encoder, decoder_dim, masking_ratio=0.75, decoder_depth=1, decoder_heads=8,
+                 decoder_dim_head=64, num_tactiles=2, early_conv_masking=False, use_sincosmod_encodings=True,
+                 frame_stack=1):
+        super().__init__()
+        assert masking_ratio > 0 and masking_ratio < 1, 'masking ratio must be kept between 0 and 1'
+        self.masking_ratio = masking_ratio
+        self.num_tactiles = num_tactiles
+        self.frame_stack = frame_stack
+        self.encoder = encoder
+        num_patches, encoder_dim = encoder.pos_embedding.shape[-2:]
+        num_decoder_patches = num_patches - 1
+        self.use_sincosmod_encodings = use_sincosmod_encodings
+        self.early_conv_masking = early_conv_masking
+        if self.early_conv_masking:
+            self.early_conv_vision = EarlyCNN(self.encoder.image_channels, encoder_dim, key='image')
+            self.early_conv_tactile = EarlyCNN(self.encoder.tactile_channels, encoder_dim, key='tactile')
+        self.image_to_patch = encoder.image_to_patch_embedding[0]
+        self.image_patch_to_emb = nn.Sequential(*encoder.image_to_patch_embedding[1:])
+        pixel_values_per_patch = encoder.image_to_patch_embedding[2].weight.shape[-1]
+        self.tactile_to_patch = encoder.tactile_to_patch_embedding[0]
+        self.tactile_patch_to_emb = nn.Sequential(*encoder.tactile_to_patch_embedding[1:])
+        tactile_values_per_patch = encoder.tactile_to_patch_embedding[2].weight.shape[-1]
+        self.encoder_dim = encoder_dim
+        self.decoder_dim = decoder_dim
+        self.enc_to_dec = nn.Linear(encoder_dim, decoder_dim) if encoder_dim != decoder_dim else nn.Identity()
+        self.mask_token = nn.Parameter(torch.randn(decoder_dim))
+        self.decoder = Transformer(dim=decoder_dim, depth=decoder_depth, heads=decoder_heads,
+                                   dim_head=decoder_dim_head, mlp_dim=decoder_dim * 4)
+        self.decoder_pos_emb = nn.Embedding(num_decoder_patches, decoder_dim)
+        self.to_pixels = nn.Linear(decoder_dim, pixel_values_per_patch)
+        self.to_tactiles = nn.Linear(decoder_dim, tactile_values_per_patch)
+        e = self.encoder
+        gi = (e.image_height // e.image_patch_height, e.image_width // e.image_patch_width)
+        gt = (e.tactile_height // e.tactile_patch_height, e.tactile_width // e.tactile_patch_width)
+        self.register_buffer('image_enc_pos_embedding', _sincos_2d(*gi, encoder_dim, encoder_dim)[None])
+        self.register_buffer('tactile_enc_pos_embedding',
+                             _sincos_2d(*gt, encoder_dim, encoder_dim).repeat(num_tactiles, 1)[None])
+        self.register_buffer('image_dec_pos_embedding', _sincos_2d(*gi, encoder_dim, decoder_dim)[None])
+        self.register_buffer('tactile_dec_pos_embedding',
+                             _sincos_2d(*gt, encoder_dim, decoder_dim).repeat(num_tactiles, 1)[None])
+        self.encoder_modality_embedding = nn.Embedding((1 + self.num_tactiles), encoder_dim)
+        self.decoder_modality_embedding = nn.Embedding((1 + self.num_tactiles), decoder_dim)
+
+        # ---- derived constants for the kernel path
+        self.cfg = SimpleNamespace(
+            dim=encoder_dim, decoder_dim=decoder_dim, masking_ratio=masking_ratio, num_tactiles=num_tactiles,
+            n_img=gi[0] * gi[1], n_tac=gt[0] * gt[1], use_sincosmod_encodings=use_sincosmod_encodings,
+            early_conv_masking=early_conv_masking, p_img=pixel_values_per_patch, p_tac=tactile_values_per_patch)
+        self.ph_img, self.pw_img = e.image_patch_height, e.image_patch_width
+        self.ph_tac, self.pw_tac = e.tactile_patch_height, e.tactile_patch_width
+        t = e.transformer
+        self.enc_spec = engine.StackSpec("encoder.transformer", t.dim, t.depth, t.heads, t.dim_head, t.mlp_dim)
+        d = self.decoder
+        self.dec_spec = engine.StackSpec("decoder", d.dim, d.depth, d.heads, d.dim_head, d.mlp_dim)
+        self.has_enc_to_dec = encoder_dim != decoder_dim
+        self.arena: Optional[ParamArena] = None
+        self._tables: Dict = {}
+        self._trainer = None
+        self.last_masked_indices = self.last_unmasked_indices = None
+
+    # ------------------------------------------------------------------------------ plumbing
+    def _canonical_named_params(self):
+        """(name, param) in arena order: decoder-side first (their gradients are final first in the
+        backward pass), then encoder side; shared patch-embedding modules once, under the
+        `*_patch_to_emb` names."""
+        named = dict(self.named_parameters(remove_duplicate=False))
+        dec_side = [k for k in named if k.startswith(("to_pixels", "to_tactiles", "decoder.", "mask_token",
+                                                      "decoder_modality_embedding", "enc_to_dec"))]
+        skip = ("encoder.image_to_patch_embedding", "encoder.tactile_to_patch_embedding")
+        rest = [k for k in named if k not in dec_side and not k.startswith(skip)]
+        return [(k, named[k]) for k in dec_side + rest]
+
+    LATE = ("encoder.pos_embedding", "decoder_pos_emb.weight")
+
+    def _sync(self) -> ParamArena:
+        dev = self.mask_token.device
+        if dev.type != "cuda":
+            raise M3LError("m3l_b200.VTMAE needs its parameters on a CUDA device: the compute path is the sm_100a "
+                           "kernel library and there is no CPU fallback (call .cuda() first)")
+        if self.arena is None or self.arena.device != dev:
+            late = [k for k, _ in self._canonical_named_params()
+                    if k in self.LATE or k.startswith("early_conv")] if self.use_sincosmod_encodings else \
+                   [k for k, _ in self._canonical_named_params() if k.startswith("early_conv")]
+            self.arena = ParamArena(self._canonical_named_params(), dev, late_names=late)
+            self._tables = {}
+            self._trainer = None
+        self.arena.sync()
+        return self.arena
+
+    def tables(self, geo, B):
+        key = (geo.use_vision, geo.nt, B)
+        if key not in self._tables:
+            self._tables[key] = engine.Tables(self, geo, B, self.arena.device)
+        return self._tables[key]
+
+    def live_param_names(self, geo, masked: bool):
+        """Parameters that receive a gradient in this mode (the reference leaves .grad None on the rest)."""
+        names = []
+        for k in self.arena.names:
+            if k.startswith("early_conv"):
+                continue  # TODO(next): early_conv_masking=True path
+            if k == "encoder.pos_embedding" and self.use_sincosmod_encodings:
+                continue
+            if k == "decoder_pos_emb.weight" and (self.use_sincosmod_encodings or not masked):
+                continue
+            if k == "encoder_modality_embedding.weight" and not self.use_sincosmod_encodings:
+                continue
+            if k == "decoder_modality_embedding.weight" and (not self.use_sincosmod_encodings or not masked):
+                continue
+            if k.startswith("image_patch_to_emb") and not geo.use_vision:
+                continue
+            if k.startswith("tactile_patch_to_emb") and not geo.nt:
+                continue
+            if k.startswith("to_pixels") and not (geo.use_vision and masked):
+                continue
+            if k.startswith("to_tactiles") and not (geo.nt and masked):
+                continue
+            if not masked and k.startswith(("decoder.", "mask_token", "enc_to_dec")):
+                continue
+            names.append(k)
+        return names
+
+    def _prep_inputs(self, x, use_vision, use_tactile):
+        if 'image' not in x:
+            use_vision = False
+        geo = engine.make_geometry(self.cfg, use_vision, use_tactile)
+        if self.early_conv_masking:
+            raise M3LError("early_conv_masking=True is not implemented in the kernel path yet (DESIGN.md: next)")
+        xs = {}
+        keys = (['image'] if geo.use_vision else []) + [f'tactile{i + 1}' for i in range(geo.nt)]
+        for k in keys:
+            t = x[k]
+            if not t.is_cuda:
+                raise M3LError(f"input '{k}' is not on a CUDA device (no CPU fallback)")
+            xs[k] = t.detach().to(torch.float32).contiguous()
+        B = xs[keys[0]].shape[0]
+        return xs, geo, B
+
+    # ------------------------------------------------------------------------------ reference API
+    def forward(self, x, use_vision=True, use_tactile=True, noise=None):
+        """Masked reconstruction loss (0-dim fp32 tensor with grad_fn), pretrain_models.py:146-342."""
+        A = self._sync()
+        xs, geo, B = self._prep_inputs(x, use_vision, use_tactile)
+        if noise is None:
+            noise = torch.rand(B, geo.n, device=A.device)
+        noise = noise.to(device=A.device, dtype=torch.float32).contiguous()
+        assert noise.shape == (B, geo.n), f"noise must be ({B}, {geo.n})"
+        live = self.live_param_names(geo, True)
+        return _MAEFn.apply(self, xs, noise, geo, tuple(live), *[A.params[k] for k in live])
+
+    def get_embeddings(self, x, eval=True, use_vision=True, use_tactile=True):
+        """Encoder over all tokens, no masking (pretrain_models.py:588-668) -> (B, N, dim) fp32."""
+        if eval:
+            self.eval()
+        else:
+            self.train()
+        A = self._sync()
+        xs, geo, B = self._prep_inputs(x, use_vision, use_tactile)
+        live = self.live_param_names(geo, False)
+        return _EmbFn.apply(self, xs, geo, B, tuple(live), *[A.params[k] for k in live])
+
+    def reconstruct(self, x, mask_ratio=None, use_vision=True, use_tactile=True):
+        raise M3LError("reconstruct() (visualisation helper, pretrain_models.py:344-586) is not part of the "
+                       "accelerated hot path yet; see DESIGN.md")
+
+    def initialize_training(self, train_args):
+        """pretrain_models.py:670-676: AdamW(lr) + batch size; the optimizer is the fused flat-arena one."""
+        from .trainer import FusedTrainer
+        self._sync()
+        self.batch_size = train_args['batch_size']
+        self._trainer = FusedTrainer(self, lr=train_args['lr'])
+        self.optimizer = self._trainer.optimizer_facade()
+
+    def train_step(self, x, noise=None, use_vision=True, use_tactile=True):
+        """zero_grad + forward + backward + clip_grad_norm_(0.5) + AdamW.step (pretrain_models.py:707-711)
+        as one fused kernel sequence.  Returns the loss (device tensor, no sync)."""
+        if self._trainer is None:
+            raise M3LError("call initialize_training({'lr': ..., 'batch_size': ...}) first")
+        return self._trainer.step(x, noise=noise, use_vision=use_vision, use_tactile=use_tactile)
+
+    def train_iterations(self, iterations, replay_buffer, no_tactile=False):
+        """pretrain_models.py:679-715 (host-side batch assembly kept as in the reference)."""
+        from .data import vt_load
+        if len(replay_buffer) < self.batch_size:
+            print("Not enough samples in replay buffer")
+            return
+        self.train()
+        for _ in range(iterations):
+            xb = random.choices(replay_buffer, k=self.batch_size)
+            new_x = {}
+            keys = ['image'] if no_tactile else ['image', 'tactile']
+            for key in keys:
+                new_x[key] = np.stack([xb[j][key] for j in range(self.batch_size)])
+            if 'image' in new_x:
+                new_x['image'] = new_x['image'].transpose((0, 2, 3, 1, 4))
+                new_x['image'] = new_x['image'].reshape((new_x['image'].shape[0], new_x['image'].shape[1], new_x['image'].shape[2], -1))
+            if 'tactile' in new_x:
+                new_x['tactile'] = new_x['tactile'].reshape((new_x['tactile'].shape[0], -1, new_x['tactile'].shape[3], new_x['tactile'].shape[4]))
+            xd = vt_load(new_x, frame_stack=self.frame_stack)
+            xd = {k: v.to(self.mask_token.device, non_blocking=True) for k, v in xd.items()}
+            self.train_step(xd)
+        self.eval()
+
+
+class _MAEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, xs, noise, geo, live, *params):
+        need = any(ctx.needs_input_grad)
+        loss_acc, c = engine.mae_forward(model, xs, noise, geo, training=need)
+        ctx.model, ctx.c, ctx.live = model, c, live
+        return loss_acc.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, A = ctx.model, ctx.model.arena
+        gflat = A.new_grad_buffer()
+        engine.mae_backward_decoder(model, ctx.c, gflat)
+        engine.mae_backward_encoder(model, ctx.c, gflat)
+        gflat.mul_(gout)
+        return (None, None, None, None, None, *[A.view(gflat, k) for k in ctx.live])
+
+
+class _EmbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, xs, geo, B, live, *params):
+        need = any(ctx.needs_input_grad)
+        out, c = engine.embeddings_forward(model, xs, geo, B, training=need)
+        ctx.model, ctx.c, ctx.live = model, c, live
+        return out.float().reshape(B, geo.n, model.cfg.dim)
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, A = ctx.model, ctx.model.arena
+        gflat = A.new_grad_buffer()
+        dout = gout.reshape(-1, model.cfg.dim).to(torch.bfloat16).contiguous()
+        engine.embeddings_backward(model, ctx.c, dout, gflat)
+        return (None, None, None, None, None, *[A.view(gflat, k) for k in ctx.live])

@@ -1,0 +1,188 @@
+"""GPU parity of the product VTMAE (CUDA kernels through the C-ABI) against
+(i) the golden vectors frozen from the unmodified reference and (ii) the CPU oracle run live.
+
+Tolerances (north_star): mask / shuffle indices bit-exact; loss <= 1e-2 relative; gradient cosine
+>= 0.999 (bf16 tensor-core compute, fp32 accumulation / LayerNorm / softmax / loss)."""
+import pytest
+import torch
+
+from oracle import vtmae_oracle as O
+from tests._build import build_product
+from tests._golden import CASES, Golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+KERNEL_CASES = [c for c in CASES if "ecm" not in c]
+
+
+def cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(a @ b / (a.norm() * b.norm() + 1e-300))
+
+
+def to_dev(x):
+    return {k: v.to(DEV) for k, v in x.items()}
+
+
+@pytest.mark.parametrize("name", KERNEL_CASES)
+def test_forward_backward_vs_reference_golden(name):
+    g = Golden(name)
+    mae = build_product(g.cfg, weights=g.weights())
+    mae.train()
+    loss = mae(to_dev(g.inputs()), noise=g.noise().to(DEV))
+    assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.grad_fn is not None
+    # integer results: bit-exact
+    assert torch.equal(mae.last_masked_indices.cpu(), g.t("masked_indices"))
+    assert torch.equal(mae.last_unmasked_indices.cpu(), g.t("unmasked_indices"))
+    ref = float(g.t("loss"))
+    assert abs(loss.item() - ref) <= 1e-2 * abs(ref), (loss.item(), ref)
+    loss.backward()
+    named = dict(mae.named_parameters())
+    present = g.grad_present()
+    for k, has in present.items():
+        assert (named[k].grad is not None) == has, f"{k}: grad presence differs from the reference"
+    for k, gn in g.grad_norms().items():
+        if present[k] and gn > 1e-6:
+            mine = float(named[k].grad.double().norm())
+            assert abs(mine - gn) <= 3e-2 * gn, (k, mine, gn)
+    for k, gr in g.full_grads().items():
+        assert cos(named[k].grad, gr) >= 0.999, (k, cos(named[k].grad, gr))
+
+
+@pytest.mark.parametrize("name", KERNEL_CASES)
+def test_embeddings_vs_reference_golden(name):
+    g = Golden(name)
+    mae = build_product(g.cfg, weights=g.weights())
+    with torch.no_grad():
+        emb = mae.get_embeddings(to_dev(g.inputs()), eval=False)
+    assert emb.shape[1:] == g.t("embeddings").shape[1:] and emb.dtype == torch.float32
+    assert mae.training
+    ref = g.t("embeddings")
+    assert cos(emb[:1], ref) >= 0.9995
+    assert (emb[:1].cpu() - ref).abs().max() <= 3e-2 * ref.abs().max()
+    if g.has("embeddings_vision_only"):
+        with torch.no_grad():
+            e2 = mae.get_embeddings(to_dev(g.inputs()), eval=True, use_tactile=False)
+        assert not mae.training
+        assert cos(e2[:1], g.t("embeddings_vision_only")) >= 0.9995
+
+
+def _oracle_grads(cfg, sd, x, noise):
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    loss = O.vtmae_forward(sd, cfg, x, noise)
+    loss.backward()
+    return loss.detach(), {k: sd[k].grad for k in O.param_keys(sd)}
+
+
+@pytest.mark.parametrize("nt", [2, 0])
+def test_all_gradients_vs_oracle_canonical(nt):
+    """Every parameter gradient of the canonical model against the CPU oracle, same inputs."""
+    cfg = O.VTMAEConfig(num_tactiles=nt)
+    sd = O.init_state_dict(cfg, seed=1)
+    gen = torch.Generator().manual_seed(99)
+    B = 16
+    x = {"image": torch.rand(B, 12, 64, 64, generator=gen)}
+    for i in range(nt):
+        x[f"tactile{i + 1}"] = torch.rand(B, 12, 32, 32, generator=gen)
+    noise = O.tie_free_noise(B, cfg.n_img + nt * cfg.n_tac, gen, [64] * (1 + nt))
+    mae = build_product(cfg, weights=sd)
+    loss = mae(to_dev(x), noise=noise.to(DEV))
+    loss.backward()
+    lref, gref = _oracle_grads(cfg, sd, x, noise)
+    assert abs(loss.item() - lref.item()) <= 1e-2 * abs(lref.item())
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    flat_a, flat_b = [], []
+    for k, gr in gref.items():
+        if gr is None:
+            assert named[k].grad is None, k
+            continue
+        c = cos(named[k].grad, gr)
+        assert c >= 0.999, (k, c)
+        flat_a.append(named[k].grad.flatten().cpu()); flat_b.append(gr.flatten())
+    assert cos(torch.cat(flat_a), torch.cat(flat_b)) >= 0.9995
+
+
+def test_embeddings_backward_vs_oracle():
+    cfg = O.VTMAEConfig(depth=2)
+    sd = O.init_state_dict(cfg, seed=2)
+    gen = torch.Generator().manual_seed(5)
+    B = 4
+    x = {"image": torch.rand(B, 12, 64, 64, generator=gen), "tactile1": torch.rand(B, 12, 32, 32, generator=gen),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=gen)}
+    w = torch.randn(B, 192, 256, generator=gen)
+    mae = build_product(cfg, weights=sd)
+    emb = mae.get_embeddings(to_dev(x), eval=False)
+    (emb * w.to(DEV)).sum().backward()
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    (O.vtmae_embeddings(sd, cfg, x) * w).sum().backward()
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    for k in O.param_keys(sd):
+        if sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0:
+            assert named[k].grad is None, k
+        else:
+            assert cos(named[k].grad, sd[k].grad) >= 0.999, (k, cos(named[k].grad, sd[k].grad))
+
+
+def test_standalone_transformer_matches_oracle():
+    """MAEExtractor's extra block (pretrain_models.py:807-817,836): Transformer(dim, 1, 4, 64, 2*dim)."""
+    from m3l_b200 import Transformer
+    torch.manual_seed(3)
+    t = Transformer(256, 1, 4, 64, 512).to(DEV)
+    sd = {"transformer." + k: v.detach().cpu().clone() for k, v in t.state_dict().items()}
+    x = torch.randn(3, 192, 256)
+    w = torch.randn(3, 192, 256)
+    xg = x.to(DEV).requires_grad_(True)
+    y = t(xg)
+    (y * w.to(DEV)).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    for v in sd.values():
+        v.requires_grad_(True)
+    yr = O.transformer(xr, sd, "transformer", 1, 4, 64)
+    (yr * w).sum().backward()
+    assert cos(y, yr.detach()) >= 0.9995
+    assert cos(xg.grad, xr.grad) >= 0.999
+    for k, p in t.named_parameters():
+        assert cos(p.grad, sd["transformer." + k].grad) >= 0.999, k
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_train_steps_vs_oracle(use_graph):
+    """zero_grad + fwd + bwd + clip(0.5) + AdamW (pretrain_models.py:707-711): loss trajectory and
+    updated weights against the oracle's restatement of torch AdamW, 3 steps."""
+    from m3l_b200.trainer import FusedTrainer
+    cfg = O.VTMAEConfig()
+    sd = O.init_state_dict(cfg, seed=4)
+    gen = torch.Generator().manual_seed(17)
+    B = 8
+    x = {"image": torch.rand(B, 12, 64, 64, generator=gen), "tactile1": torch.rand(B, 12, 32, 32, generator=gen),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=gen)}
+    noise = O.tie_free_noise(B, 192, gen, [64, 64, 64])
+    mae = build_product(cfg, weights=sd)
+    mae.initialize_training({"lr": 1e-4, "batch_size": B})
+    mae._trainer.use_graph = use_graph
+    st = O.AdamWState()
+    xd, nd = to_dev(x), noise.to(DEV)
+    w0 = {k: v.detach().clone() for k, v in sd.items()}
+    for it in range(3):
+        l = mae.train_step(xd, noise=nd)
+        lo, norm, _ = O.train_step(sd, cfg, x, noise, st)
+        assert abs(l.item() - lo.item()) <= 1e-2 * abs(lo.item()), (it, l.item(), lo.item())
+        assert abs(mae._trainer.state[2].item() - norm.item()) <= 3e-2 * norm.item()
+    named = dict(mae.named_parameters())
+    for k in ("decoder.layers.0.1.net.1.weight", "to_pixels.weight", "mask_token", "encoder.transformer.layers.0.0.to_qkv.weight"):
+        upd_ref = sd[k].detach() - w0[k]
+        upd = named[k].detach().cpu() - w0[k]
+        assert cos(upd, upd_ref) >= 0.99, (k, cos(upd, upd_ref))
+    # parameters the reference leaves without gradient are untouched (no weight decay either)
+    assert torch.equal(named["encoder.pos_embedding"].detach().cpu(), w0["encoder.pos_embedding"])
+    assert mae._trainer.state[0].item() == 3.0
+
+
+def test_cpu_module_fails_loudly():
+    from m3l_b200 import M3LError
+    mae = build_product(O.VTMAEConfig(depth=1, decoder_depth=1), device="cpu")
+    with pytest.raises(M3LError):
+        mae({"image": torch.zeros(1, 12, 64, 64)})
