@@ -115,11 +115,13 @@ int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, const float*
                       const float* add1, const int32_t* add1_row, void* stream);
 
 /* LayerNorm backward: dx = dLN(dy) (+ skip), dgamma/dbeta += column sums (fp32 atomics).
- * src_row (optional): dy row gather, negative = zero gradient row. */
+ * src_row (optional): dy row gather, negative = zero gradient row.
+ * dx_colsum (optional): += column sums of dx, i.e. the bias gradient of the nn.Linear whose output
+ * gradient dx is (saves a separate reduction pass over dx). */
 int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, const void* x, int x_fp32,
                       const float* stats, int rows, int dim, const float* gamma,
                       const void* skip_bf16, void* dx, int dx_fp32, float* dgamma, float* dbeta,
-                      void* stream);
+                      float* dx_colsum, void* stream);
 
 /* Decoder input assembly (pretrain_models.py:270-307): z[b,t] = (visible ? d[b, slot] : mask_token)
  * + add0[tok_class[t]] + add1[t].  Backward scatters / reduces the gradient accordingly. */

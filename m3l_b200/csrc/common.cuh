@@ -77,11 +77,31 @@ M3L_DEVINL float warp_max(float v) {
   return v;
 }
 
-M3L_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() default, as vit_pytorch's FeedForward uses).  erf through Abramowitz &
+// Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level): one MUFU.RCP + one MUFU.EX2 + 5 FMA; the
+// same exp(-x^2/2) serves the Gaussian pdf of the derivative.
+struct GeluParts {
+  float cdf;   // Phi(x)
+  float pdf;   // phi(x)
+};
+M3L_DEVINL GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);                       // exp(-x^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);       // erf(|x| / sqrt 2)
+  GeluParts g;
+  g.cdf = 0.5f + copysignf(0.5f * erf_abs, x);
+  g.pdf = 0.39894228040143268f * e;
+  return g;
+}
+M3L_DEVINL float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 M3L_DEVINL float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const GeluParts g = gelu_parts(x);
+  return fmaf(x, g.pdf, g.cdf);
 }
 
 M3L_DEVINL uint32_t pack_bf16x2(float lo, float hi) {

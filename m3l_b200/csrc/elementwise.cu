@@ -244,32 +244,34 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, co
 
 // LayerNorm backward.  dy: bf16 rows (optionally gathered: src_row[r] < 0 -> dy row is zero),
 // x: TIn LN input, stats (mean, rstd).  dx = LN'(dy) (+ skip[r]) written as TOut;
-// dgamma / dbeta accumulated with atomics (fp32).
-template <typename TIn, typename TOut>
-__global__ void layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_row,
-                                     const TIn* __restrict__ x, const float* __restrict__ stats, int M, int D,
-                                     const float* __restrict__ gamma, const bf16* __restrict__ skip,
-                                     TOut* __restrict__ dx, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  extern __shared__ float sacc[];  // [2][D] block accumulators
+// dgamma / dbeta (and optionally the column sums of dx: the bias gradient of the Linear whose
+// output gradient dx is) accumulated block-locally, then with fp32 atomics.
+template <typename TIn, typename TOut, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_row,
+                     const TIn* __restrict__ x, const float* __restrict__ stats, int M, int D,
+                     const float* __restrict__ gamma, const bf16* __restrict__ skip,
+                     TOut* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  extern __shared__ float sacc[];  // [3][D] block accumulators
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  float ag[kMaxChunks][8], ab[kMaxChunks][8];
+  float ag[NCH][8], ab[NCH][8], ac[NCH][8];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c)
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = 0.f;
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ac[c][i] = 0.f;
 
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
     const int sr = src_row ? src_row[r] : r;
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float xh[kMaxChunks][8], g[kMaxChunks][8];
+    float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
         float xv[8], dv[8], gm[8];
@@ -295,7 +297,7 @@ __global__ void layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t*
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
         float o[8];
@@ -307,27 +309,33 @@ __global__ void layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t*
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] += t[i];
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ac[c][i] += o[i];
         store8(dx + (size_t)r * D + ch * 8, o);
       }
     }
   }
-  if (dgamma) {
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nchunk) {
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
+        if (dgamma) {
           atomicAdd(&sacc[ch * 8 + i], ag[c][i]);
           atomicAdd(&sacc[D + ch * 8 + i], ab[c][i]);
         }
+        if (dx_colsum) atomicAdd(&sacc[2 * D + ch * 8 + i], ac[c][i]);
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dgamma) {
       atomicAdd(&dgamma[i], sacc[i]);
       atomicAdd(&dbeta[i], sacc[D + i]);
     }
+    if (dx_colsum) atomicAdd(&dx_colsum[i], sacc[2 * D + i]);
   }
 }
 
@@ -368,26 +376,33 @@ __global__ void assemble_fwd_kernel(const bf16* __restrict__ d, int nv, const fl
 
 // backward: dd[b*nv+slot] = dz[b,t] (visible); d mask_token += sum(masked rows);
 // d add0[class] += sum rows of the class; d add1[t] += sum over b (only if dadd1 != null).
-// One block per token position t: loops over the batch so every sum is block-local.
+// Block = (token position t, chunk of 32 samples); thread = 2 adjacent columns.
 __global__ void assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slot_of_token,
                                     int B, int n, int D, int nv, bf16* __restrict__ dd,
                                     float* __restrict__ dmask_token, float* __restrict__ dadd0,
                                     const int32_t* __restrict__ tok_class, float* __restrict__ dadd1) {
   const int t = blockIdx.x;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float sum_all = 0.f, sum_masked = 0.f;
-    for (int b = 0; b < B; ++b) {
+  const int b0 = blockIdx.y * 32, b1 = min(b0 + 32, B);
+  for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
+    float2 sum_all = make_float2(0.f, 0.f), sum_masked = make_float2(0.f, 0.f);
+    for (int b = b0; b < b1; ++b) {
       const size_t r = (size_t)b * n + t;
       const int slot = slot_of_token[r];
-      const bf16 g = dz[r * D + c];
-      const float gf = __bfloat162float(g);
-      sum_all += gf;
-      if (slot >= 0) dd[((size_t)b * nv + slot) * D + c] = g;
-      else sum_masked += gf;
+      const uint32_t raw = *reinterpret_cast<const uint32_t*>(dz + r * D + c);
+      const float2 g = unpack_bf16x2(raw);
+      sum_all.x += g.x; sum_all.y += g.y;
+      if (slot >= 0) *reinterpret_cast<uint32_t*>(dd + ((size_t)b * nv + slot) * D + c) = raw;
+      else { sum_masked.x += g.x; sum_masked.y += g.y; }
     }
-    if (dmask_token) atomicAdd(&dmask_token[c], sum_masked);
-    if (dadd0) atomicAdd(&dadd0[(size_t)tok_class[t] * D + c], sum_all);
-    if (dadd1) atomicAdd(&dadd1[(size_t)t * D + c], sum_all);
+    if (dmask_token) { atomicAdd(&dmask_token[c], sum_masked.x); atomicAdd(&dmask_token[c + 1], sum_masked.y); }
+    if (dadd0) {
+      float* d0 = dadd0 + (size_t)tok_class[t] * D + c;
+      atomicAdd(d0, sum_all.x); atomicAdd(d0 + 1, sum_all.y);
+    }
+    if (dadd1) {
+      float* d1 = dadd1 + (size_t)t * D + c;
+      atomicAdd(d1, sum_all.x); atomicAdd(d1 + 1, sum_all.y);
+    }
   }
 }
 
@@ -416,18 +431,29 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
 __global__ void mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0,
                                 int ncols, const float* __restrict__ pred, float weight,
                                 bf16* __restrict__ dpred, float* __restrict__ loss_acc) {
+  extern __shared__ float patch[];   // P floats, destination order (p1, p2, c)
   __shared__ float red[32];
   const int r = blockIdx.x;
   const int b = r / ncols, jj = r - b * ncols;
   const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
   int sensor;
   const float* origin = patch_origin(ps, b, tok, &sensor);
-  const int P = ps.P;
+  const int P = ps.P, ppw = ps.ph * ps.pw;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {   // source order: p2 contiguous along W
+    const int c = i / ppw;
+    const int pp = i - c * ppw;
+    const int p1 = pp / ps.pw, p2 = pp - p1 * ps.pw;
+    patch[pp * ps.C + c] = origin[((size_t)c * ps.H + p1) * ps.W + p2];
+  }
+  __syncthreads();
   float acc = 0.f;
-  for (int e = threadIdx.x; e < P; e += blockDim.x) {
-    const float diff = pred[(size_t)r * P + e] - patch_elem(ps, origin, e);
-    acc += diff * diff;
-    dpred[(size_t)r * P + e] = __float2bfloat16(2.f * weight * diff);
+  const float w2 = 2.f * weight;
+  for (int e = threadIdx.x * 4; e < P; e += blockDim.x * 4) {   // P is a multiple of 4 (checked on the host)
+    const float4 pv = *reinterpret_cast<const float4*>(pred + (size_t)r * P + e);
+    const float d0 = pv.x - patch[e], d1 = pv.y - patch[e + 1], d2 = pv.z - patch[e + 2], d3 = pv.w - patch[e + 3];
+    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    *reinterpret_cast<uint2*>(dpred + (size_t)r * P + e) =
+        make_uint2(pack_bf16x2(w2 * d0, w2 * d1), pack_bf16x2(w2 * d2, w2 * d3));
   }
   const float tot = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(loss_acc, weight * tot);
@@ -437,7 +463,7 @@ __global__ void mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx
 // 7. column sums of a bf16 matrix: out[n] += sum_m x[m, n]   (bias gradients)
 // ------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
-  // block: 32 x 8 threads; each thread owns 8 consecutive columns
+  // block: 32 x 8 threads; each thread owns 8 consecutive columns, 4 rows in flight
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   __shared__ float part[8][32][8];
   float acc[8];
@@ -447,7 +473,17 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, 
     const int rows_per_block = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(r0 + rows_per_block, M);
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8<bf16>(x + (size_t)r * ld + col, v0);
+      load8<bf16>(x + (size_t)(r + 8) * ld + col, v1);
+      load8<bf16>(x + (size_t)(r + 16) * ld + col, v2);
+      load8<bf16>(x + (size_t)(r + 24) * ld + col, v3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       load8<bf16>(x + (size_t)r * ld + col, v);
 #pragma unroll
@@ -564,30 +600,45 @@ extern "C" int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, c
   return M3L_OK;
 }
 
+template <typename TIn, typename TOut>
+static int launch_ln_bwd(int nch, int grid, size_t smem, cudaStream_t st, const bf16* dy, const int32_t* src_row,
+                         const TIn* x, const float* stats, int rows, int dim, const float* gamma, const bf16* skip,
+                         TOut* dx, float* dgamma, float* dbeta, float* dx_colsum) {
+  if (nch == 1)
+    layernorm_bwd_kernel<TIn, TOut, 1><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+  else if (nch == 2)
+    layernorm_bwd_kernel<TIn, TOut, 2><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+  else
+    layernorm_bwd_kernel<TIn, TOut, 4><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
 extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, const void* x, int x_fp32,
                                  const float* stats, int rows, int dim, const float* gamma,
                                  const void* skip_bf16, void* dx, int dx_fp32, float* dgamma, float* dbeta,
-                                 void* stream) {
+                                 float* dx_colsum, void* stream) {
   M3L_REQUIRE(dy_bf16 && x && stats && gamma && dx, "layernorm_bwd: null pointer");
   M3L_REQUIRE(dim % 8 == 0 && dim <= 1024, "layernorm_bwd: dim %d unsupported", dim);
   M3L_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set");
   if (rows == 0) return M3L_OK;
   const int wpb = 8;
-  int grid = (rows + wpb - 1) / wpb;
-  const int cap = device_sm_count() * 2;
+  int grid = (rows + 4 * wpb - 1) / (4 * wpb);   // >= 4 rows per warp so the block-level reduction amortises
+  const int cap = device_sm_count() * 8;
   if (grid > cap) grid = cap;
-  const size_t smem = 2 * dim * sizeof(float);
+  if (grid < 1) grid = 1;
+  const size_t smem = 3 * dim * sizeof(float);
+  const int nch = dim <= 256 ? 1 : (dim <= 512 ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
+  const bf16* dy = (const bf16*)dy_bf16;
+  const bf16* skip = (const bf16*)skip_bf16;
   if (x_fp32 && !dx_fp32)
-    layernorm_bwd_kernel<float, bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const float*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (bf16*)dx, dgamma, dbeta);
-  else if (!x_fp32 && !dx_fp32)
-    layernorm_bwd_kernel<bf16, bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const bf16*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (bf16*)dx, dgamma, dbeta);
-  else if (x_fp32 && dx_fp32)
-    layernorm_bwd_kernel<float, float><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const float*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (float*)dx, dgamma, dbeta);
-  else
-    layernorm_bwd_kernel<bf16, float><<<grid, wpb * 32, smem, st>>>((const bf16*)dy_bf16, src_row, (const bf16*)x, stats, rows, dim, gamma, (const bf16*)skip_bf16, (float*)dx, dgamma, dbeta);
-  M3L_CUDA(cudaGetLastError());
-  return M3L_OK;
+    return launch_ln_bwd<float, bf16>(nch, grid, smem, st, dy, src_row, (const float*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+  if (!x_fp32 && !dx_fp32)
+    return launch_ln_bwd<bf16, bf16>(nch, grid, smem, st, dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+  if (x_fp32 && dx_fp32)
+    return launch_ln_bwd<float, float>(nch, grid, smem, st, dy, src_row, (const float*)x, stats, rows, dim, gamma, skip, (float*)dx, dgamma, dbeta, dx_colsum);
+  return launch_ln_bwd<bf16, float>(nch, grid, smem, st, dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (float*)dx, dgamma, dbeta, dx_colsum);
 }
 
 extern "C" int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const float* mask_token,
@@ -613,7 +664,8 @@ extern "C" int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot
   M3L_REQUIRE(dz_bf16 && slot_of_token && dd_bf16, "decoder_assemble_bwd: null pointer");
   M3L_REQUIRE(dadd0 == nullptr || tok_class != nullptr, "decoder_assemble_bwd: dadd0 needs tok_class");
   if (batch * n_tokens == 0) return M3L_OK;
-  assemble_bwd_kernel<<<n_tokens, 256, 0, (cudaStream_t)stream>>>(
+  M3L_REQUIRE(dim % 2 == 0, "decoder_assemble_bwd: dim must be even");
+  assemble_bwd_kernel<<<dim3(n_tokens, (batch + 31) / 32), 128, 0, (cudaStream_t)stream>>>(
       (const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, n_visible, (bf16*)dd_bf16, dmask_token, dadd0,
       tok_class, dadd1);
   M3L_CUDA(cudaGetLastError());
@@ -637,7 +689,8 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
   M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
   if (batch * ncols == 0) return M3L_OK;
   PatchSrc ps = make_patch_src(src);
-  mse_loss_kernel<<<batch * ncols, 128, 0, (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, pred, weight,
+  M3L_REQUIRE(ps.P % 4 == 0 && ps.P * sizeof(float) <= 48 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
+  mse_loss_kernel<<<batch * ncols, 128, ps.P * sizeof(float), (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, pred, weight,
                                                                    (bf16*)dpred_bf16, loss_acc);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;

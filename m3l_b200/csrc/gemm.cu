@@ -57,7 +57,56 @@ M3L_DEVINL void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// Epilogue flavours (compile time, so the inner loops carry no mode branches):
+enum : int {
+  EPI_BF16 = 0,      // out bf16 = acc (+ bias) (+ residual)
+  EPI_GELU_FWD = 1,  // aux_out bf16 = acc + bias ; out bf16 = GELU(acc + bias)
+  EPI_GELU_BWD = 2,  // out bf16 = acc * GELU'(aux_in)
+  EPI_F32 = 3,       // out fp32 = acc (+ bias)
+  EPI_F32_RED = 4,   // out fp32 += acc  (red.global.add, split-K)
+};
+
+// ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) ------------
+// "row" mapping: thread `lane` owns row `lane` (this is how tcgen05.ld hands out the accumulator);
+// "co" mapping : iteration i, row 4*i + (lane >> 3), chunk lane & 7 (8 lanes cover one 128 B row,
+//                so global accesses are full-line coalesced).  Both mappings are bank-conflict free.
+M3L_DEVINL void stg_store_row(uint32_t stg, int lane, const uint32_t* w) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * j]), "r"(w[4 * j + 1]),
+                 "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                 : "memory");
+  }
+}
+M3L_DEVINL void stg_load_row(uint32_t stg, int lane, uint32_t* w) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                 : "r"(addr)
+                 : "memory");
+  }
+}
+M3L_DEVINL uint4 stg_load_co(uint32_t stg, int lane, int i) {
+  const int r = 4 * i + (lane >> 3);
+  const uint32_t addr = stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+M3L_DEVINL void stg_store_co(uint32_t stg, int lane, int i, uint4 v) {
+  const int r = 4 * i + (lane >> 3);
+  const uint32_t addr = stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const GemmArgs p) {
@@ -171,10 +220,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ------------------------------- epilogue -------------------------------------------
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int col_half = ew >> 2;              // which half of the BN columns
-    constexpr int kChunks = BN / 64;           // 32-column chunks per warp
-    uint8_t* stg = staging + ew * kStagingBytesPerWarp;
-    const uint32_t stg_u32 = smem_u32(stg);
+    const int col_half = ew >> 2;
+    // columns of the tile this warp drains: BN >= 128 -> its half; BN == 64 -> half 0 takes all
+    constexpr int kSpan = BN >= 128 ? BN / 2 : 64;
+    const bool active = BN >= 128 || col_half == 0;
+    const int span0 = BN >= 128 ? col_half * kSpan : 0;
+    constexpr bool kF32 = (EPI == EPI_F32 || EPI == EPI_F32_RED);
+    constexpr int kRoundCols = kF32 ? 32 : 64;
+    constexpr int kRounds = kSpan / kRoundCols;
+    const uint32_t stg = smem_u32(staging + ew * kStagingBytesPerWarp);
+    const bool has_bias = (EPI != EPI_GELU_BWD && EPI != EPI_F32_RED) && p.bias != nullptr;
+    const bool has_res = (EPI == EPI_BF16) && p.residual != nullptr;
+    const int co_row = lane >> 3, co_chunk = lane & 7;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int t = item / p.splits;
@@ -185,76 +242,153 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&bars->tmem_full[buf], acc_phase);
       tc_fence_after_sync();
       const int row_base = m0 + quad * 32;
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int col0 = (col_half * kChunks + c) * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + col0, v);
-        tmem_ld_wait();
-        if (c == kChunks - 1) {
-          // all TMEM reads of this warp for this accumulator are done -> hand it back early
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = stg_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]),
-                       "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                       : "memory");
-        }
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN;
+      if (!active) {
+        tc_fence_before_sync();
         __syncwarp();
-        const int cc = lane & 7;
-        const int gcol = n0 + col0 + cc * 4;
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+        continue;
+      }
+#pragma unroll 1
+      for (int r = 0; r < kRounds; ++r) {
+        const int c0 = span0 + r * kRoundCols;        // first tile column of this round
+        if constexpr (!kF32) {
+          // ---------------- bf16 outputs: 64 columns per round ----------------
+          const int gcol = n0 + c0 + co_chunk * 8;      // this lane's 8 columns in the co mapping
+          const bool col_ok = gcol < p.N;
+          uint4 side[8];
+          if (EPI == EPI_GELU_BWD || has_res) {
+            const bf16* sp = (EPI == EPI_GELU_BWD) ? p.aux_in : p.residual;
+            const int ld = (EPI == EPI_GELU_BWD) ? p.ld_aux : p.ldr;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = (lane >> 3) + 4 * i;
-          const int grow = row_base + r;
-          float4 a;
-          const uint32_t addr = stg_u32 + r * 128 + ((cc ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                       : "r"(addr)
-                       : "memory");
-          if (grow < p.M && gcol < p.N) {
-            a.x *= p.alpha; a.y *= p.alpha; a.z *= p.alpha; a.w *= p.alpha;
-            if (p.bias != nullptr) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + gcol);
-              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            if (p.act == 1) {
-              if (p.aux_out != nullptr) {
-                uint2 pk = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-                *reinterpret_cast<uint2*>(p.aux_out + (size_t)grow * p.ld_aux + gcol) = pk;
-              }
-              a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
-            } else if (p.act == 2) {
-              const uint2 pk =
-                  *reinterpret_cast<const uint2*>(p.aux_in + (size_t)grow * p.ld_aux + gcol);
-              const float2 p0 = unpack_bf16x2(pk.x), p1 = unpack_bf16x2(pk.y);
-              a.x *= gelu_erf_grad(p0.x); a.y *= gelu_erf_grad(p0.y);
-              a.z *= gelu_erf_grad(p1.x); a.w *= gelu_erf_grad(p1.y);
-            }
-            if (p.residual != nullptr) {
-              const uint2 pk =
-                  *reinterpret_cast<const uint2*>(p.residual + (size_t)grow * p.ldr + gcol);
-              const float2 r0 = unpack_bf16x2(pk.x), r1 = unpack_bf16x2(pk.y);
-              a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
-            }
-            if (p.out_mode == 0) {
-              uint2 pk = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo +
-                                        gcol) = pk;
-            } else if (p.out_mode == 1) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo +
-                                         gcol) = a;
-            } else {
-              red_add_v4(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + gcol, a);
+            for (int i = 0; i < 8; ++i) {
+              const int grow = row_base + 4 * i + co_row;
+              side[i] = (col_ok && grow < p.M)
+                            ? *reinterpret_cast<const uint4*>(sp + (size_t)grow * ld + gcol)
+                            : make_uint4(0, 0, 0, 0);
             }
           }
+          uint32_t v[64];
+          tmem_ld_32x32(t_acc + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(t_acc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (r == kRounds - 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const int c = n0 + c0 + j;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+            }
+          }
+          uint32_t w[32];
+          if constexpr (EPI == EPI_GELU_FWD) {
+            if (p.aux_out != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              stg_store_row(stg, lane, w);
+              __syncwarp();
+              uint4 u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int grow = row_base + 4 * i + co_row;
+                if (col_ok && grow < p.M)
+                  *reinterpret_cast<uint4*>(p.aux_out + (size_t)grow * p.ld_aux + gcol) = u[i];
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+          }
+          if (EPI == EPI_GELU_BWD || has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stg_store_co(stg, lane, i, side[i]);
+            __syncwarp();
+            stg_load_row(stg, lane, w);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 s2 = unpack_bf16x2(w[j]);
+              if constexpr (EPI == EPI_GELU_BWD) {
+                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) * gelu_erf_grad(s2.x));
+                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) * gelu_erf_grad(s2.y));
+              } else {
+                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + s2.x);
+                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + s2.y);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          stg_store_row(stg, lane, w);
+          __syncwarp();
+          uint4 u[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
+          bf16* outp = reinterpret_cast<bf16*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row_base + 4 * i + co_row;
+            if (col_ok && grow < p.M) *reinterpret_cast<uint4*>(outp + (size_t)grow * p.ldo + gcol) = u[i];
+          }
+          __syncwarp();
+        } else {
+          // ---------------- fp32 outputs: 32 columns per round ----------------
+          const int gcol = n0 + c0 + co_chunk * 4;
+          const bool col_ok = gcol < p.N;
+          uint32_t v[32];
+          tmem_ld_32x32(t_acc + c0, v);
+          tmem_ld_wait();
+          if (r == kRounds - 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int c = n0 + c0 + j;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+            }
+          }
+          stg_store_row(stg, lane, v);
+          __syncwarp();
+          uint4 u[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
+          float* outp = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row_base + 4 * i + co_row;
+            if (col_ok && grow < p.M) {
+              float* dst = outp + (size_t)grow * p.ldo + gcol;
+              if constexpr (EPI == EPI_F32_RED) {
+                red_add_v4(dst, make_float4(__uint_as_float(u[i].x), __uint_as_float(u[i].y),
+                                            __uint_as_float(u[i].z), __uint_as_float(u[i].w)));
+              } else {
+                *reinterpret_cast<uint4*>(dst) = u[i];
+              }
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -267,20 +401,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& p, int grid,
-                   cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch_variant(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
-    M3L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
+    M3L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ma, mb, p);
+  kern<<<plan.grid, kNumThreads, Cfg::kSmemBytes, stream>>>(plan.map_a, plan.map_b, plan.args);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
+}
+
+template <int BN>
+int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
+  const GemmArgs& p = plan.args;
+  if (p.a_mn_major) return launch_variant<BN, true, true, EPI_F32_RED>(plan, stream);
+  if (p.out_mode == 1) return launch_variant<BN, false, false, EPI_F32>(plan, stream);
+  if (p.act == 1) return launch_variant<BN, false, false, EPI_GELU_FWD>(plan, stream);
+  if (p.act == 2) return launch_variant<BN, false, false, EPI_GELU_BWD>(plan, stream);
+  return launch_variant<BN, false, false, EPI_BF16>(plan, stream);
 }
 
 }  // namespace
@@ -309,6 +451,18 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   while (p.splits > 1 && ((kb_total + p.splits - 1) / p.splits) * (p.splits - 1) >= kb_total)
     --p.splits;
   M3L_REQUIRE(p.splits == 1 || p.out_mode == 2, "gemm: split-K requires the atomic output mode");
+  M3L_REQUIRE(p.alpha == 1.0f, "gemm: alpha != 1 is not supported");
+  M3L_REQUIRE((p.out_mode == 2) == (p.a_mn_major != 0),
+              "gemm: the accumulate output mode goes with MN-major operands (wgrad) and vice versa");
+  M3L_REQUIRE(p.a_mn_major == 0 || (p.bias == nullptr && p.residual == nullptr && p.act == 0),
+              "gemm: wgrad mode takes no bias / residual / activation");
+  M3L_REQUIRE(p.out_mode != 1 || (p.act == 0 && p.residual == nullptr),
+              "gemm: fp32 store mode supports bias only");
+  M3L_REQUIRE(p.act == 0 || p.residual == nullptr, "gemm: activation and residual cannot be combined");
+  M3L_REQUIRE(p.act != 2 || (p.aux_in != nullptr && p.bias == nullptr), "gemm: GELU' needs aux_in and no bias");
+  M3L_REQUIRE(p.ldo % 8 == 0 && (p.residual == nullptr || p.ldr % 8 == 0) &&
+                  ((p.aux_in == nullptr && p.aux_out == nullptr) || p.ld_aux % 8 == 0),
+              "gemm: output / residual / aux leading dimensions must be multiples of 8");
   if (bn == 0) bn = gemm_pick_bn(p.M, p.N);
   M3L_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
   plan->bn = bn;
@@ -331,17 +485,10 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
 }
 
 int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
-  const bool mn = plan.args.a_mn_major != 0;
   switch (plan.bn) {
-    case 64:
-      return mn ? launch_variant<64, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
-                : launch_variant<64, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
-    case 128:
-      return mn ? launch_variant<128, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
-                : launch_variant<128, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
-    case 256:
-      return mn ? launch_variant<256, true, true>(plan.map_a, plan.map_b, plan.args, plan.grid, stream)
-                : launch_variant<256, false, false>(plan.map_a, plan.map_b, plan.args, plan.grid, stream);
+    case 64: return launch_bn<64>(plan, stream);
+    case 128: return launch_bn<128>(plan, stream);
+    case 256: return launch_bn<256>(plan, stream);
   }
   set_last_error("gemm: BN=%d unsupported", plan.bn);
   return M3L_ERR_INVALID;

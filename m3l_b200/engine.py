@@ -84,30 +84,36 @@ def stack_fwd(A: ParamArena, spec: StackSpec, x: torch.Tensor, B: int, n: int, s
     return x
 
 
+def last_ff_bias(spec: StackSpec) -> str:
+    """Name of the bias whose gradient is the column sum of the stack-output gradient."""
+    return f"{spec.prefix}.layers.{spec.depth - 1}.1.net.4.bias"
+
+
 def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: int, n: int, saved: list):
-    """dx: bf16 [B*n, dim] gradient w.r.t. the stack output.  Returns the gradient w.r.t. its input."""
+    """dx: bf16 [B*n, dim] gradient w.r.t. the stack output.  Returns the gradient w.r.t. its input.
+    The producer of dx (the final-LayerNorm backward) must already have accumulated its column sums
+    into G(last_ff_bias(spec)) (dx_colsum= of ops.layernorm_bwd)."""
     scale = spec.dim_head ** -0.5
     for l in reversed(range(spec.depth)):
         pa, pf = f"{spec.prefix}.layers.{l}.0", f"{spec.prefix}.layers.{l}.1"
         x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h = saved[l]
         # ---- feed-forward branch: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
-        ops.colsum(dx, G(pf + ".net.4.bias"))
         wgrad(dx, h, G(pf + ".net.4.weight"))
         dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre)
         ops.colsum(dpre, G(pf + ".net.1.bias"))
         wgrad(dpre, xn2, G(pf + ".net.1.weight"))
         dxn2 = ops.gemm(dpre, A.bf_t(pf + ".net.1.weight"))
         dx_mid = ops.layernorm_bwd(dxn2, x_mid, st2, A.f32(pf + ".net.0.weight"), dgamma=G(pf + ".net.0.weight"),
-                                   dbeta=G(pf + ".net.0.bias"), skip=dx)
+                                   dbeta=G(pf + ".net.0.bias"), skip=dx, dx_colsum=G(pa + ".to_out.0.bias"))
         # ---- attention branch: x_mid = x + Wo attn(Wqkv LN1(x)) + bo
-        ops.colsum(dx_mid, G(pa + ".to_out.0.bias"))
         wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
         do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"))
         dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale)
         wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
         dxn1 = ops.gemm(dqkv, A.bf_t(pa + ".to_qkv.weight"))
+        prev_bias = G(f"{spec.prefix}.layers.{l - 1}.1.net.4.bias") if l > 0 else None
         dx = ops.layernorm_bwd(dxn1, x, st1, A.f32(pa + ".norm.weight"), dgamma=G(pa + ".norm.weight"),
-                               dbeta=G(pa + ".norm.bias"), skip=dx_mid)
+                               dbeta=G(pa + ".norm.bias"), skip=dx_mid, dx_colsum=prev_bias)
     return dx
 
 
@@ -342,7 +348,8 @@ def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
         wgrad(dpred, g_in, G(name + ".weight"))
         ops.gemm(dpred, A.bf_t(name + ".weight"), out=dgath[row0:row0 + g_in.shape[0]])
     dxd = ops.layernorm_bwd(dgath, ctx["xd"], ctx["st_dec"], A.f32("decoder.norm.weight"),
-                            dgamma=G("decoder.norm.weight"), dbeta=G("decoder.norm.bias"), src_row=ctx["mrow"])
+                            dgamma=G("decoder.norm.weight"), dbeta=G("decoder.norm.bias"), src_row=ctx["mrow"],
+                            dx_colsum=G(last_ff_bias(model.dec_spec)))
     dz = stack_bwd(A, G, model.dec_spec, dxd, B, geo.n, ctx["dec"])
     if cfg.use_sincosmod_encodings:
         dd = ops.decoder_assemble_bwd(dz, ctx["slots"], B, geo.n, geo.nv, dmask_token=G("mask_token"),
@@ -365,7 +372,8 @@ def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
     else:
         denc = dd
     dxe = ops.layernorm_bwd(denc, ctx["xe"], ctx["st_enc"], A.f32("encoder.transformer.norm.weight"),
-                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"))
+                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
+                            dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
     _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
 
@@ -391,6 +399,7 @@ def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor):
     G = GradView(A, gflat)
     geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
     dxe = ops.layernorm_bwd(dout, ctx["xe"], ctx["st"], A.f32("encoder.transformer.norm.weight"),
-                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"))
+                            dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
+                            dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.n, ctx["enc"])
     _embed_bwd(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])

@@ -146,14 +146,15 @@ def layernorm_fwd(x, gamma, beta, *, out=None, out_rows=None, stats=None, want_s
 
 
 def layernorm_bwd(dy, x, stats, gamma, *, dgamma=None, dbeta=None, skip=None, src_row=None, dx=None,
-                  dx_dtype=torch.bfloat16):
+                  dx_dtype=torch.bfloat16, dx_colsum=None):
     _req_cuda(dy, x, stats, gamma)
     M, D = x.shape
     if dx is None:
         dx = torch.empty((M, D), dtype=dx_dtype, device=x.device)
     check(_lib.load().m3l_layernorm_bwd(ptr(dy), ptr(src_row), ptr(x), int(x.dtype == torch.float32), ptr(stats),
                                         M, D, ptr(gamma), ptr(skip), ptr(dx), int(dx.dtype == torch.float32),
-                                        ptr(dgamma), ptr(dbeta), current_stream()), "m3l_layernorm_bwd")
+                                        ptr(dgamma), ptr(dbeta), ptr(dx_colsum), current_stream()),
+          "m3l_layernorm_bwd")
     return dx
 
 

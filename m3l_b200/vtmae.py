@@ -106,7 +106,8 @@ class _TransformerFn(torch.autograd.Function):
         gflat = A.new_grad_buffer()
         G = engine.GradView(A, gflat)
         dout = gout.reshape(B * n, D).to(torch.bfloat16).contiguous()
-        dxe = ops.layernorm_bwd(dout, xe, st, A.f32("t.norm.weight"), dgamma=G("t.norm.weight"), dbeta=G("t.norm.bias"))
+        dxe = ops.layernorm_bwd(dout, xe, st, A.f32("t.norm.weight"), dgamma=G("t.norm.weight"), dbeta=G("t.norm.bias"),
+                                dx_colsum=G(engine.last_ff_bias(spec)))
         dx = engine.stack_bwd(A, G, spec, dxe, B, n, saved)
         return (None, None, None, dx.float().reshape(B, n, D), *[A.view(gflat, nm) for nm in A.names])
 

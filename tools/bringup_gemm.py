@@ -55,7 +55,7 @@ def epi():
     h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=pre)
     z = a.float() @ b.float().T + bias
     e2 = max(ref_err(h, torch.nn.functional.gelu(z)), ref_err(pre, z))
-    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre, out_dtype=torch.float32)
+    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre)
     zz = pre.float().requires_grad_(True); torch.nn.functional.gelu(zz).sum().backward()
     e3 = ref_err(g, (a.float() @ b.float().T) * zz.grad)
     print(f"  epi errs: bias+res {e1:.2e} gelu {e2:.2e} gelu' {e3:.2e}")
