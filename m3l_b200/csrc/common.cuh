@@ -86,7 +86,7 @@ struct GeluParts {
 };
 M3L_DEVINL GeluParts gelu_parts(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP
   const float e = __expf(-z * z);                       // exp(-x^2 / 2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);

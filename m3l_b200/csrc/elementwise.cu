@@ -89,6 +89,26 @@ M3L_DEVINL float patch_elem(const PatchSrc& ps, const float* origin, int e) {
   return origin[((size_t)c * ps.H + p1) * ps.W + p2];
 }
 
+// Loads one patch into smem in destination order (p1, p2, c): one thread per (c, p1) source row,
+// which is pw contiguous floats along W.
+M3L_DEVINL void load_patch_smem(const PatchSrc& ps, const float* origin, float* patch) {
+  const int rows = ps.C * ps.ph;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    const int c = i / ps.ph, p1 = i - c * ps.ph;
+    const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
+    float* dst = patch + (p1 * ps.pw) * ps.C + c;
+    if ((ps.pw & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      for (int p2 = 0; p2 < ps.pw; p2 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + p2);
+        dst[(p2 + 0) * ps.C] = v.x; dst[(p2 + 1) * ps.C] = v.y;
+        dst[(p2 + 2) * ps.C] = v.z; dst[(p2 + 3) * ps.C] = v.w;
+      }
+    } else {
+      for (int p2 = 0; p2 < ps.pw; ++p2) dst[p2 * ps.C] = src[p2];
+    }
+  }
+}
+
 M3L_DEVINL float block_sum(float v, float* red) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,14 +135,8 @@ __global__ void patch_ln_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx
   const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
   int sensor;
   const float* origin = patch_origin(ps, b, tok, &sensor);
-  // read in source order (c, p1, p2): p2 runs along W, contiguous in memory
-  const int P = ps.P, ppw = ps.ph * ps.pw;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    const int c = i / ppw;
-    const int pp = i - c * ppw;
-    const int p1 = pp / ps.pw, p2 = pp - p1 * ps.pw;
-    patch[pp * ps.C + c] = origin[((size_t)c * ps.H + p1) * ps.W + p2];
-  }
+  const int P = ps.P;
+  load_patch_smem(ps, origin, patch);
   __syncthreads();
   float s = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) s += patch[i];
@@ -169,61 +183,98 @@ M3L_DEVINL void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// raw (unconverted) 8-element chunk, so the next row can be prefetched into registers
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 a; };
+template <> struct Raw8<float> { float4 a, b; };
+M3L_DEVINL void raw_load(const bf16* p, Raw8<bf16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
+M3L_DEVINL void raw_load(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+M3L_DEVINL void raw_cvt(const Raw8<bf16>& r, float (&v)[8]) {
+  float2 a = unpack_bf16x2(r.a.x), b = unpack_bf16x2(r.a.y), c = unpack_bf16x2(r.a.z), d = unpack_bf16x2(r.a.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+M3L_DEVINL void raw_cvt(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+M3L_DEVINL void raw_zero(Raw8<bf16>& r) { r.a = make_uint4(0, 0, 0, 0); }
+
 // 3./4. LayerNorm forward.  x: TIn [M, D]; y: bf16.  Optional additive terms (token embedding
 // finish / nothing for plain LN): add0[row_class[r]] and add1[row_pos[r]] fp32 rows of D.
-// Optional output row remap (dst_row[r] < 0 -> row skipped).
-template <typename TIn>
-__global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, float eps, bf16* __restrict__ y,
-                                     float* __restrict__ stats, const int32_t* __restrict__ dst_row,
-                                     const float* __restrict__ add0, const int32_t* __restrict__ add0_row,
-                                     const float* __restrict__ add1, const int32_t* __restrict__ add1_row) {
+// Optional output row remap (dst_row[r] < 0 -> row skipped).  NCH = 8-element chunks per lane.
+template <typename TIn, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, bf16* __restrict__ y,
+                     float* __restrict__ stats, const int32_t* __restrict__ dst_row,
+                     const float* __restrict__ add0, const int32_t* __restrict__ add0_row,
+                     const float* __restrict__ add1, const int32_t* __restrict__ add1_row) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
-    float v[kMaxChunks][8];
+  const float inv_d = 1.0f / D;
+  float g[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      load8<float>(gamma + ch * 8, g[c]);
+      load8<float>(beta + ch * 8, bt[c]);
+    }
+  }
+  const int rstride = gridDim.x * warps_per_block;
+  int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  Raw8<TIn> nxt[NCH];
+  if (r < M) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (lane + 32 * c < nchunk) raw_load(x + (size_t)r * D + (lane + 32 * c) * 8, nxt[c]);
+  }
+  for (; r < M; r += rstride) {
+    float v[NCH][8];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
-        load8<TIn>(x + (size_t)r * D + ch * 8, v[c]);
+        raw_cvt(nxt[c], v[c]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[c][i];
       }
     }
-    const float mean = warp_sum(s) / D;
+    if (r + rstride < M) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (lane + 32 * c < nchunk) raw_load(x + (size_t)(r + rstride) * D + (lane + 32 * c) * 8, nxt[c]);
+    }
+    const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float d = v[c][i] - mean;
-          q += d * d;
+          v[c][i] -= mean;
+          q += v[c][i] * v[c][i];
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
-    if (stats && lane == 0) {
-      stats[2 * r] = mean;
-      stats[2 * r + 1] = rstd;
-    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (stats && lane == 0) *reinterpret_cast<float2*>(stats + 2 * r) = make_float2(mean, rstd);
     const int dr = dst_row ? dst_row[r] : r;
     if (dr < 0) continue;
     const float* a0 = add0 ? add0 + (size_t)(add0_row ? add0_row[r] : 0) * D : nullptr;
     const float* a1 = add1 ? add1 + (size_t)(add1_row ? add1_row[r] : 0) * D : nullptr;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
-        float g[8], bt[8], o[8];
-        load8<float>(gamma + ch * 8, g);
-        load8<float>(beta + ch * 8, bt);
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mean) * rstd * g[i] + bt[i];
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(v[c][i] * rstd, g[c][i], bt[c][i]);
         if (a0) {
           float t[8];
           load8<float>(a0 + ch * 8, t);
@@ -245,7 +296,7 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, co
 // LayerNorm backward.  dy: bf16 rows (optionally gathered: src_row[r] < 0 -> dy row is zero),
 // x: TIn LN input, stats (mean, rstd).  dx = LN'(dy) (+ skip[r]) written as TOut;
 // dgamma / dbeta (and optionally the column sums of dx: the bias gradient of the Linear whose
-// output gradient dx is) accumulated block-locally, then with fp32 atomics.
+// output gradient dx is) reduced per warp in registers, per block through smem, then fp32 atomics.
 template <typename TIn, typename TOut, int NCH>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_row,
@@ -253,49 +304,64 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ sr
                      const float* __restrict__ gamma, const bf16* __restrict__ skip,
                      TOut* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
-  extern __shared__ float sacc[];  // [3][D] block accumulators
+  extern __shared__ float spart[];  // [warps][3][D]
   const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
-  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  float ag[NCH][8], ab[NCH][8], ac[NCH][8];
+  const float inv_d = 1.0f / D;
+  float gm[NCH][8], ag[NCH][8], ab[NCH][8], ac[NCH][8];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) load8<float>(gamma + ch * 8, gm[c]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ac[c][i] = 0.f;
-
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < M; r += gridDim.x * warps_per_block) {
-    const int sr = src_row ? src_row[r] : r;
-    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float xh[NCH][8], g[NCH][8];
+  }
+  const int rstride = gridDim.x * warps_per_block;
+  int r = blockIdx.x * warps_per_block + warp;
+  Raw8<TIn> nx[NCH];
+  Raw8<bf16> nd[NCH], nk[NCH];
+  float2 nms = make_float2(0.f, 0.f);
+  auto prefetch = [&](int row) {
+    const int sr = src_row ? src_row[row] : row;
+    nms = *reinterpret_cast<const float2*>(stats + 2 * row);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        raw_load(x + (size_t)row * D + ch * 8, nx[c]);
+        if (sr >= 0) raw_load(dy + (size_t)sr * D + ch * 8, nd[c]); else raw_zero(nd[c]);
+        if (skip) raw_load(skip + (size_t)row * D + ch * 8, nk[c]);
+      }
+    }
+  };
+  if (r < M) prefetch(r);
+  for (; r < M; r += rstride) {
+    const float mean = nms.x, rstd = nms.y;
+    float xh[NCH][8], g[NCH][8], sk[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
-        float xv[8], dv[8], gm[8];
-        load8<TIn>(x + (size_t)r * D + ch * 8, xv);
-        if (sr >= 0) {
-          load8<bf16>(dy + (size_t)sr * D + ch * 8, dv);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dv[i] = 0.f;
-        }
-        load8<float>(gamma + ch * 8, gm);
+        float xv[8], dv[8];
+        raw_cvt(nx[c], xv);
+        raw_cvt(nd[c], dv);
+        if (skip) raw_cvt(nk[c], sk[c]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[c][i] = (xv[i] - mean) * rstd;
-          g[c][i] = dv[i] * gm[i];
+          g[c][i] = dv[i] * gm[c][i];
           s1 += g[c][i];
-          s2 += g[c][i] * xh[c][i];
-          ag[c][i] += dv[i] * xh[c][i];
+          s2 = fmaf(g[c][i], xh[c][i], s2);
+          ag[c][i] = fmaf(dv[i], xh[c][i], ag[c][i]);
           ab[c][i] += dv[i];
         }
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    if (r + rstride < M) prefetch(r + rstride);
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
@@ -304,10 +370,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ sr
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
         if (skip) {
-          float t[8];
-          load8<bf16>(skip + (size_t)r * D + ch * 8, t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += t[i];
+          for (int i = 0; i < 8; ++i) o[i] += sk[c][i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) ac[c][i] += o[i];
@@ -315,27 +379,25 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ sr
       }
     }
   }
+  if (dgamma == nullptr && dx_colsum == nullptr) return;
+  float* mine = spart + (size_t)warp * 3 * D;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (dgamma) {
-          atomicAdd(&sacc[ch * 8 + i], ag[c][i]);
-          atomicAdd(&sacc[D + ch * 8 + i], ab[c][i]);
-        }
-        if (dx_colsum) atomicAdd(&sacc[2 * D + ch * 8 + i], ac[c][i]);
-      }
+      store8(mine + ch * 8, ag[c]);
+      store8(mine + D + ch * 8, ab[c]);
+      store8(mine + 2 * D + ch * 8, ac[c]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    if (dgamma) {
-      atomicAdd(&dgamma[i], sacc[i]);
-      atomicAdd(&dbeta[i], sacc[D + i]);
-    }
-    if (dx_colsum) atomicAdd(&dx_colsum[i], sacc[2 * D + i]);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) t += spart[(size_t)w * 3 * D + i];
+    const int which = i / D, col = i - which * D;
+    if (which == 0) { if (dgamma) atomicAdd(&dgamma[col], t); }
+    else if (which == 1) { if (dbeta) atomicAdd(&dbeta[col], t); }
+    else if (dx_colsum) atomicAdd(&dx_colsum[col], t);
   }
 }
 
@@ -428,35 +490,48 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
 // 6. masked-patch MSE: pred fp32 [rows, P]; target gathered from the raw maps.
 //    loss_acc[slot] += weight * sum((pred - tgt)^2) ; dpred = 2 * weight * (pred - tgt)  (bf16)
 // ------------------------------------------------------------------------------------------
-__global__ void mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0,
-                                int ncols, const float* __restrict__ pred, float weight,
-                                bf16* __restrict__ dpred, float* __restrict__ loss_acc) {
-  extern __shared__ float patch[];   // P floats, destination order (p1, p2, c)
-  __shared__ float red[32];
-  const int r = blockIdx.x;
-  const int b = r / ncols, jj = r - b * ncols;
-  const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
-  int sensor;
-  const float* origin = patch_origin(ps, b, tok, &sensor);
-  const int P = ps.P, ppw = ps.ph * ps.pw;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {   // source order: p2 contiguous along W
-    const int c = i / ppw;
-    const int pp = i - c * ppw;
-    const int p1 = pp / ps.pw, p2 = pp - p1 * ps.pw;
-    patch[pp * ps.C + c] = origin[((size_t)c * ps.H + p1) * ps.W + p2];
-  }
-  __syncthreads();
-  float acc = 0.f;
+__global__ void __launch_bounds__(256)
+mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols, int rows,
+                const float* __restrict__ pred, float weight, bf16* __restrict__ dpred,
+                float* __restrict__ loss_acc) {
+  extern __shared__ float patches[];   // [warps][P] floats, destination order (p1, p2, c)
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int P = ps.P;
+  float* patch = patches + (size_t)warp * P;
+  const int src_rows = ps.C * ps.ph;
   const float w2 = 2.f * weight;
-  for (int e = threadIdx.x * 4; e < P; e += blockDim.x * 4) {   // P is a multiple of 4 (checked on the host)
-    const float4 pv = *reinterpret_cast<const float4*>(pred + (size_t)r * P + e);
-    const float d0 = pv.x - patch[e], d1 = pv.y - patch[e + 1], d2 = pv.z - patch[e + 2], d3 = pv.w - patch[e + 3];
-    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-    *reinterpret_cast<uint2*>(dpred + (size_t)r * P + e) =
-        make_uint2(pack_bf16x2(w2 * d0, w2 * d1), pack_bf16x2(w2 * d2, w2 * d3));
+  float acc = 0.f;
+  for (int r = blockIdx.x * nwarps + warp; r < rows; r += gridDim.x * nwarps) {
+    const int b = r / ncols, jj = r - b * ncols;
+    const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+    int sensor;
+    const float* origin = patch_origin(ps, b, tok, &sensor);
+    for (int i = lane; i < src_rows; i += 32) {      // one (channel, patch row) per lane: pw contiguous floats
+      const int c = i / ps.ph, p1 = i - c * ps.ph;
+      const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
+      float* dst = patch + (p1 * ps.pw) * ps.C + c;
+      for (int p2 = 0; p2 < ps.pw; ++p2) dst[p2 * ps.C] = src[p2];
+    }
+    __syncwarp();
+    const float* prow = pred + (size_t)r * P;
+    bf16* drow = dpred + (size_t)r * P;
+    for (int e = lane * 4; e < P; e += 128) {
+      const float4 pv = *reinterpret_cast<const float4*>(prow + e);
+      const float d0 = pv.x - patch[e], d1 = pv.y - patch[e + 1], d2 = pv.z - patch[e + 2], d3 = pv.w - patch[e + 3];
+      acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      *reinterpret_cast<uint2*>(drow + e) = make_uint2(pack_bf16x2(w2 * d0, w2 * d1), pack_bf16x2(w2 * d2, w2 * d3));
+    }
+    __syncwarp();
   }
-  const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, weight * tot);
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w];
+    atomicAdd(loss_acc, weight * t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -474,14 +549,17 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, 
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(r0 + rows_per_block, M);
     int r = r0 + threadIdx.y;
-    for (; r + 24 < r1; r += 32) {
-      float v0[8], v1[8], v2[8], v3[8];
-      load8<bf16>(x + (size_t)r * ld + col, v0);
-      load8<bf16>(x + (size_t)(r + 8) * ld + col, v1);
-      load8<bf16>(x + (size_t)(r + 16) * ld + col, v2);
-      load8<bf16>(x + (size_t)(r + 24) * ld + col, v3);
+    for (; r + 56 < r1; r += 64) {
+      Raw8<bf16> raw[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+      for (int u = 0; u < 8; ++u) raw_load(x + (size_t)(r + 8 * u) * ld + col, raw[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float v[8];
+        raw_cvt(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
     }
     for (; r < r1; r += 8) {
       float v[8];
@@ -589,13 +667,21 @@ extern "C" int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, c
   M3L_REQUIRE(dim % 8 == 0 && dim <= 1024, "layernorm_fwd: dim %d unsupported", dim);
   if (rows == 0) return M3L_OK;
   const int wpb = 8;
-  const int grid = ln_grid(rows, wpb);
-  if (x_fp32)
-    layernorm_fwd_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const float*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, stats, dst_row, add0, add0_row, add1, add1_row);
-  else
-    layernorm_fwd_kernel<bf16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, stats, dst_row, add0, add0_row, add1, add1_row);
+  int grid = (rows + 2 * wpb - 1) / (2 * wpb);
+  const int cap = device_sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  const int nch = dim <= 256 ? 1 : (dim <= 512 ? 2 : 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define M3L_LN_FWD(T, N)                                                                                   \
+  layernorm_fwd_kernel<T, N><<<grid, wpb * 32, 0, st>>>((const T*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, \
+                                                        stats, dst_row, add0, add0_row, add1, add1_row)
+  if (x_fp32) {
+    if (nch == 1) M3L_LN_FWD(float, 1); else if (nch == 2) M3L_LN_FWD(float, 2); else M3L_LN_FWD(float, 4);
+  } else {
+    if (nch == 1) M3L_LN_FWD(bf16, 1); else if (nch == 2) M3L_LN_FWD(bf16, 2); else M3L_LN_FWD(bf16, 4);
+  }
+#undef M3L_LN_FWD
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -604,6 +690,12 @@ template <typename TIn, typename TOut>
 static int launch_ln_bwd(int nch, int grid, size_t smem, cudaStream_t st, const bf16* dy, const int32_t* src_row,
                          const TIn* x, const float* stats, int rows, int dim, const float* gamma, const bf16* skip,
                          TOut* dx, float* dgamma, float* dbeta, float* dx_colsum) {
+  static bool configured = false;
+  if (!configured) {   // dim 1024: 8 warps x 3 x 1024 floats = 96 KB of reduction scratch
+    M3L_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TIn, TOut, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    M3L_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TIn, TOut, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
   if (nch == 1)
     layernorm_bwd_kernel<TIn, TOut, 1><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
   else if (nch == 2)
@@ -623,11 +715,11 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
   M3L_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set");
   if (rows == 0) return M3L_OK;
   const int wpb = 8;
-  int grid = (rows + 4 * wpb - 1) / (4 * wpb);   // >= 4 rows per warp so the block-level reduction amortises
-  const int cap = device_sm_count() * 8;
+  int grid = (rows + 8 * wpb - 1) / (8 * wpb);   // >= 8 rows per warp so the block-level reduction amortises
+  const int cap = device_sm_count() * 4;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  const size_t smem = 3 * dim * sizeof(float);
+  const size_t smem = (size_t)wpb * 3 * dim * sizeof(float);
   const int nch = dim <= 256 ? 1 : (dim <= 512 ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
   const bf16* dy = (const bf16*)dy_bf16;
@@ -689,8 +781,16 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
   M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
   if (batch * ncols == 0) return M3L_OK;
   PatchSrc ps = make_patch_src(src);
-  M3L_REQUIRE(ps.P % 4 == 0 && ps.P * sizeof(float) <= 48 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
-  mse_loss_kernel<<<batch * ncols, 128, ps.P * sizeof(float), (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, pred, weight,
+  M3L_REQUIRE(ps.P % 4 == 0 && ps.P * sizeof(float) * 8 <= 96 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
+  static bool configured = false;
+  if (!configured) {
+    M3L_CUDA(cudaFuncSetAttribute(mse_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  const int rows = batch * ncols;
+  int grid = (rows + 7) / 8;
+  if (grid > device_sm_count() * 4) grid = device_sm_count() * 4;
+  mse_loss_kernel<<<grid, 256, ps.P * sizeof(float) * 8, (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, rows, pred, weight,
                                                                    (bf16*)dpred_bf16, loss_acc);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;

@@ -35,18 +35,21 @@ class StackSpec:
         return self.heads * self.dim_head
 
 
-def _auto_splits(m_out: int, n_out: int, k_tokens: int) -> int:
+def _wgrad_tiling(m_out: int, n_out: int, k_tokens: int):
+    """(BN, split-K) for a wgrad product: the widest N tile that divides n_out and as many splits as
+    keep the whole problem in ONE wave of CTAs (measured best on B200: tools/sweep_wgrad.py)."""
     bn = 256 if n_out % 256 == 0 else (128 if n_out % 128 == 0 else 64)
     tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
     kb = (k_tokens + 63) // 64
-    s = max(1, (_SM_COUNT + tiles - 1) // tiles)
-    return max(1, min(s, max(1, kb // 4)))
+    s = max(1, _SM_COUNT // tiles)
+    return bn, max(1, min(s, kb))
 
 
 def wgrad(dy: torch.Tensor, x: torch.Tensor, gview: torch.Tensor) -> None:
     """gview[out, in] += dy[M, out]^T @ x[M, in]  (split-K over the token rows, fp32 red.add)."""
     out_f, in_f = gview.shape
-    ops.gemm(dy, x, mn_major=True, out=gview, accumulate=True, splits=_auto_splits(out_f, in_f, dy.shape[0]))
+    bn, splits = _wgrad_tiling(out_f, in_f, dy.shape[0])
+    ops.gemm(dy, x, mn_major=True, out=gview, accumulate=True, splits=splits, bn=bn)
 
 
 class GradView:
