@@ -31,11 +31,6 @@ M3L_DEVINL uint32_t round_up_pow2_cols(int c) {
   return r;
 }
 
-struct AttnFwdBars {
-  uint64_t qk, v, s, p, o;
-  uint32_t tmem_base;
-};
-
 // store 8 bf16 (one 16-byte chunk) of row `row`, logical chunk `chunk` (0..7) into a [rows x 128 B]
 // 128B-swizzled K-major slab
 M3L_DEVINL void st_swz_chunk(uint32_t slab_u32, int row, int chunk, uint4 v) {
@@ -55,434 +50,520 @@ M3L_DEVINL uint4 ld_swz_chunk(uint32_t slab_u32, int row, int chunk) {
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// forward: persistent CTA, warp-specialised and software-pipelined over (sample, head) items
+//   warp 0       TMA loader: K,V of item i (double-buffered when it fits) and the Q tiles
+//   warp 1       MMA issuer: S(j) = Q_j K^T is issued BEFORE O(j-1) = P(j-1) V, so the tensor core
+//                works on the next tile's scores while a softmax group is busy with the previous tile
+//   warps 2..5   softmax group 0 (TMEM slot 0)     one TMEM lane (= query row) per thread;
+//   warps 6..9   softmax group 1 (TMEM slot 1)     tiles alternate between the two groups
+// Query rows of an item are split evenly over its tiles (n = 192 -> 2 tiles of 96 valid rows, both
+// issued as 128-row MMAs) so the two softmax groups carry equal exp2 work (the MUFU-bound part).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160)
+struct AttnFwdBars {
+  uint64_t kv_full[2], kv_empty[2], q_full[2], q_empty[2], s_full[2], p_full[2], o_full[2], slot_free[2];
+  uint32_t tmem_base;
+};
+
+struct AttnFwdParams {
+  bf16* out;
+  float* lse;
+  int n, heads, inner, q_tiles, tile_rows, num_items, kv_bufs, slot_cols;
+  float scale;
+};
+
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                bf16* __restrict__ out, float* __restrict__ lse, int n, int heads, int inner,
-                int q_tiles, float scale) {
+                const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int n = p.n;
   const int NK = (n + 15) & ~15;                 // keys padded to the MMA granularity
   const int kv_bytes = NK * 128;                 // [NK rows x 64 d] bf16
   const int kv_region = (kv_bytes + 1023) & ~1023;
   const int p_slabs = (NK + 63) / 64;
-  const int regA = max(16384 + kv_region, p_slabs * 16384);   // (Q | K) aliased with P
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sP = smem;
-  uint8_t* sV = smem + regA;
-  AttnFwdBars* bars = reinterpret_cast<AttnFwdBars*>(sV + kv_region);
+  uint8_t* sKV = smem;                                           // [kv_bufs][K | V]
+  uint8_t* sQ = sKV + p.kv_bufs * 2 * kv_region;                 // [2][128 x 64]
+  uint8_t* sP = sQ + 2 * 16384;                                  // [2][p_slabs][128 x 64]
+  AttnFwdBars* bars = reinterpret_cast<AttnFwdBars*>(sP + 2 * p_slabs * 16384);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % q_tiles;
-  const int bh = blockIdx.x / q_tiles;
-  const int h = bh % heads, b = bh / heads;
-  const uint32_t tmem_cols = round_up_pow2_cols(max(NK, 64));
+  const uint32_t tmem_cols = 2 * p.slot_cols;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&map_q);
-      tma_prefetch_desc(&map_kv);
-      mbar_init(&bars->qk, 1);
-      mbar_init(&bars->v, 1);
-      mbar_init(&bars->s, 1);
-      mbar_init(&bars->p, 128);
-      mbar_init(&bars->o, 1);
-      fence_barrier_init();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
+      mbar_init(&bars->q_full[i], 1);
+      mbar_init(&bars->q_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->o_full[i], 1);
+      mbar_init(&bars->slot_free[i], 128);
     }
-    __syncwarp();
-    tmem_alloc(&bars->tmem_base, tmem_cols);
+    fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, tmem_cols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == 0) {
+    // ------------------------------- TMA loader -----------------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->qk, 16384 + kv_bytes);
-      tma_load_3d(sQ, &map_q, &bars->qk, h * kDh, qt * 128, b);
-      tma_load_3d(sK, &map_kv, &bars->qk, inner + h * kDh, 0, b);
-      mbar_arrive_expect_tx(&bars->v, kv_bytes);
-      tma_load_3d(sV, &map_kv, &bars->v, 2 * inner + h * kDh, 0, b);
-      // S = Q K^T
-      mbar_wait(&bars->qk, 0);
-      tc_fence_after_sync();
-      const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK);
-#pragma unroll
-      for (int k = 0; k < kDh / 16; ++k)
-        umma_bf16(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024),
-                  umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(&bars->s);
-      // O = P V
-      mbar_wait(&bars->p, 0);
-      tc_fence_after_sync();
-      mbar_wait(&bars->v, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(128, kDh, 0, 1);
-      const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(sV);
-      for (int kk = 0; kk < NK / 16; ++kk)
-        umma_bf16(tmem_base, umma_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                  umma_smem_desc(v_addr + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
-      umma_commit(&bars->o);
-    }
-  } else {
-    const int row = warp * 32 + lane;            // TMEM lane == query row inside the tile
-    const int grow = qt * 128 + row;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const float sl2 = scale * kLog2e;
-    mbar_wait(&bars->s, 0);
-    tc_fence_after_sync();
-    const int nchunks = (NK + 31) / 32;
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    float sum = 0.f;
-    const uint32_t p_u32 = smem_u32(sP);
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + c * 32, v);
-      tmem_ld_wait();
-      float pv[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float p = (c * 32 + j < n) ? exp2f((__uint_as_float(v[j]) - mx) * sl2) : 0.f;
-        sum += p;
-        pv[j] = p;
-      }
-      const int col0 = c * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (col0 + g * 8 < NK) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          u.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          u.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          u.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          const int col = col0 + g * 8;
-          st_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, u);
+      int it = 0, jt = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int h = item % p.heads, b = item / p.heads;
+        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
+        const uint32_t kph = (it / p.kv_bufs) & 1;
+        mbar_wait(&bars->kv_empty[kb], kph ^ 1);
+        uint8_t* k_dst = sKV + kb * 2 * kv_region;
+        mbar_arrive_expect_tx(&bars->kv_full[kb], 2 * kv_bytes);
+        tma_load_3d(k_dst, &map_kv, &bars->kv_full[kb], p.inner + h * kDh, 0, b);
+        tma_load_3d(k_dst + kv_region, &map_kv, &bars->kv_full[kb], 2 * p.inner + h * kDh, 0, b);
+        for (int t = 0; t < p.q_tiles; ++t, ++jt) {
+          const int slot = jt & 1;
+          const uint32_t ph = (jt >> 1) & 1;
+          mbar_wait(&bars->q_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&bars->q_full[slot], 16384);
+          tma_load_3d(sQ + slot * 16384, &map_q, &bars->q_full[slot], h * kDh, t * p.tile_rows, b);
         }
       }
     }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    mbar_arrive(&bars->p);
-    // epilogue
-    mbar_wait(&bars->o, 0);
-    tc_fence_after_sync();
-    const float inv = 1.0f / sum;
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(t_row, o0);
-    tmem_ld_32x32(t_row + 32, o1);
-    tmem_ld_wait();
-    if (grow < n) {
-      bf16* dst = out + ((size_t)b * n + grow) * inner + h * kDh;
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -----------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, kDh, 0, 1);
+      int pv_slot = -1, pv_kb = 0, pv_last = 0;
+      uint32_t pv_ph = 0;
+      auto issue_pv = [&]() {
+        mbar_wait(&bars->p_full[pv_slot], pv_ph);
+        tc_fence_after_sync();
+        const uint32_t p_addr = smem_u32(sP + pv_slot * p_slabs * 16384);
+        const uint32_t v_addr = smem_u32(sKV + pv_kb * 2 * kv_region + kv_region);
+        const uint32_t tmem_o = tmem_base + pv_slot * p.slot_cols;
+        for (int kk = 0; kk < NK / 16; ++kk)
+          umma_bf16(tmem_o, umma_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc(v_addr + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
+        umma_commit(&bars->o_full[pv_slot]);
+        if (pv_last) umma_commit(&bars->kv_empty[pv_kb]);
+        pv_slot = -1;
+      };
+      int it = 0, jt = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
+        const uint32_t kph = (it / p.kv_bufs) & 1;
+        if (p.kv_bufs == 1 && pv_slot >= 0) issue_pv();   // single K/V buffer: drain before it is reloaded
+        mbar_wait(&bars->kv_full[kb], kph);
+        const uint32_t k_addr = smem_u32(sKV + kb * 2 * kv_region);
+        for (int t = 0; t < p.q_tiles; ++t, ++jt) {
+          const int slot = jt & 1;
+          const uint32_t ph = (jt >> 1) & 1;
+          mbar_wait(&bars->q_full[slot], ph);
+          mbar_wait(&bars->slot_free[slot], ph ^ 1);
+          tc_fence_after_sync();
+          const uint32_t q_addr = smem_u32(sQ + slot * 16384);
+          const uint32_t tmem_s = tmem_base + slot * p.slot_cols;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_s, umma_smem_desc(q_addr + k * 32, 16, 1024),
+                      umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&bars->s_full[slot]);
+          umma_commit(&bars->q_empty[slot]);
+          if (pv_slot >= 0) issue_pv();
+          pv_slot = slot; pv_ph = ph; pv_kb = kb; pv_last = (t == p.q_tiles - 1);
+        }
       }
+      if (pv_slot >= 0) issue_pv();
+    }
+  } else {
+    // ------------------------------- softmax groups -------------------------------------
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;              // TMEM lane == query row inside the tile
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + wg * p.slot_cols;
+    const uint32_t p_u32 = smem_u32(sP + wg * p_slabs * 16384);
+    const float sl2 = p.scale * kLog2e;
+    const int nchunks = (NK + 31) / 32;
+    int it = 0, jt = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int h = item % p.heads, b = item / p.heads;
+      for (int t = 0; t < p.q_tiles; ++t, ++jt) {
+        if ((jt & 1) != wg) continue;
+        const uint32_t ph = (jt >> 1) & 1;
+        const int grow = t * p.tile_rows + row;
+        const bool warp_active = (quad * 32 < p.tile_rows) && (t * p.tile_rows + quad * 32 < n);
+        const bool valid = row < p.tile_rows && grow < n;
+        mbar_wait(&bars->s_full[wg], ph);
+        tc_fence_after_sync();
+        float mx = -INFINITY, sum = 0.f;
+        if (warp_active) {
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+          const float mxs = mx * sl2;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            const int col0 = c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (col0 + g * 8 < NK) {
+                float pv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float e = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), sl2, -mxs));
+                  pv[j] = (col0 + g * 8 + j < n) ? e : 0.f;
+                  sum += pv[j];
+                }
+                uint4 u;
+                u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
+                u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
+                const int col = col0 + g * 8;
+                st_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, u);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->p_full[wg]);
+        // ---- epilogue
+        mbar_wait(&bars->o_full[wg], ph);
+        tc_fence_after_sync();
+        if (warp_active) {
+          const float inv = 1.0f / sum;
+          uint32_t o0[32], o1[32];
+          tmem_ld_32x32(t_row, o0);
+          tmem_ld_32x32(t_row + 32, o1);
+          tmem_ld_wait();
+          if (valid) {
+            bf16* dst = p.out + ((size_t)b * n + grow) * p.inner + h * kDh;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + g * 8) = u;
+              u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
+            }
+            if (p.lse) p.lse[((size_t)b * p.heads + h) * n + grow] = mx * p.scale + __logf(sum);
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&bars->slot_free[wg]);
       }
-      if (lse) lse[((size_t)b * heads + h) * n + grow] = mx * scale + __logf(sum);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// backward
+// backward: persistent CTA over (sample, head) items; key tiles (128) outer, query tiles (128) inner.
+//   P_ij = exp(S_ij * scale - LSE_i) and dS_ij = P_ij (dP_ij - delta_i) scale are element-wise given
+//   LSE / delta, so no row-wide pass is needed and S_ij, dP_ij sit in TMEM side by side:
+//     TMEM columns: [0,128) S_ij  [128,256) dP_ij  [256,320) dQ_0  [320,384) dQ_1  [384,448) dV_j  [448,512) dK_j
+//   warp 0      TMA loader (K,V double-buffered across items when they fit; Q / dO tiles per item)
+//   warp 1      MMA issuer: [S, dP](step) ; wait P/dS ; [dV += P^T dO, dK += dS^T Q, dQ += dS K](step)
+//               followed immediately by [S, dP](step+1), so the tensor core never waits for the epilogues
+//   warps 2..9  two groups of 128 threads; thread = (query row, 64-key half): both read their half of
+//               S and dP from TMEM and write the P and dS slabs (bf16, swizzled) the MMAs consume as
+//               K-major (dQ) and MN-major (dV, dK) operands.  Group 0 drains dV_j / dQ_0, group 1 dK_j / dQ_1.
 // ------------------------------------------------------------------------------------------
 struct AttnBwdBars {
-  uint64_t kv;        // K and V landed
-  uint64_t qdo;       // Q tile and dO tile landed (per q tile)
-  uint64_t mma;       // MMA group finished (reused; phases tracked)
-  uint64_t warps;     // softmax warps finished a stage (count 128)
+  uint64_t kv_full[2], kv_empty[2], qdo_full, qdo_empty, sdp_full, pds_full, dkv_full, dkv_free, item_done;
   uint32_t tmem_base;
 };
 
-// TMEM column map (512 allocated): [0, 256) scratch (S_t, then dP_t, then dQ_t), [256, 320) dV keys 0..127,
-// [320, 384) dV keys 128..255, [384, 448) dK keys 0..127, [448, 512) dK keys 128..255.
-__global__ void __launch_bounds__(160)
+struct AttnBwdParams {
+  const bf16* o;
+  const bf16* dout;
+  const float* lse;
+  bf16* dqkv;
+  int n, heads, inner, q_tiles, key_tiles, num_items, kv_bufs;
+  float scale;
+};
+
+M3L_DEVINL void store_row64(bf16* dst, const uint32_t (&a0)[32], const uint32_t (&a1)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(a0[g * 8 + 0]), __uint_as_float(a0[g * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(a0[g * 8 + 2]), __uint_as_float(a0[g * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(a0[g * 8 + 4]), __uint_as_float(a0[g * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(a0[g * 8 + 6]), __uint_as_float(a0[g * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+    u.x = pack_bf16x2(__uint_as_float(a1[g * 8 + 0]), __uint_as_float(a1[g * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(a1[g * 8 + 2]), __uint_as_float(a1[g * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(a1[g * 8 + 4]), __uint_as_float(a1[g * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(a1[g * 8 + 6]), __uint_as_float(a1[g * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
+  }
+}
+
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ o,
-                const bf16* __restrict__ dout, const float* __restrict__ lse, bf16* __restrict__ dqkv,
-                int n, int heads, int inner, float scale) {
+                const __grid_constant__ CUtensorMap map_do, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int n = p.n;
   const int NK = (n + 15) & ~15;
   const int kv_bytes = NK * 128;
   const int kv_region = (kv_bytes + 1023) & ~1023;
-  const int slabs = 2 * ((NK + 127) / 128);  // 64-key slabs, whole 128-key tiles (unused keys zeroed)
-  uint8_t* sQ = smem;                       // 16 KB  [128 q][64 d]
-  uint8_t* sDO = sQ + 16384;                // 16 KB  [128 q][64 d]
-  uint8_t* sK = sDO + 16384;                // [NK][64]
-  uint8_t* sV = sK + kv_region;             // [NK][64]
-  uint8_t* sP = sV + kv_region;             // slabs x 16 KB  [128 q][64 keys]
-  uint8_t* sDS = sP + slabs * 16384;        // slabs x 16 KB
-  AttnBwdBars* bars = reinterpret_cast<AttnBwdBars*>(sDS + slabs * 16384);
+  uint8_t* sQ = smem;                                 // [2][128 q][64 d]
+  uint8_t* sDO = sQ + 2 * 16384;                      // [2][128 q][64 d]
+  uint8_t* sP = sDO + 2 * 16384;                      // [2 slabs][128 q][64 keys]
+  uint8_t* sDS = sP + 2 * 16384;                      // [2 slabs][128 q][64 keys]
+  uint8_t* sKV = sDS + 2 * 16384;                     // [kv_bufs][K | V]
+  AttnBwdBars* bars = reinterpret_cast<AttnBwdBars*>(sKV + p.kv_bufs * 2 * kv_region);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % heads, b = blockIdx.x / heads;
-  const int q_tiles = (n + 127) / 128;
-  const int key_tiles = (NK + 127) / 128;
   constexpr uint32_t kTmemCols = 512;
-  constexpr uint32_t kColDV = 256, kColDK = 384;
+  constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDV = 384, kColDK = 448;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&map_q);
-      tma_prefetch_desc(&map_kv);
-      tma_prefetch_desc(&map_do);
-      mbar_init(&bars->kv, 1);
-      mbar_init(&bars->qdo, 1);
-      mbar_init(&bars->mma, 1);
-      mbar_init(&bars->warps, 128);
-      fence_barrier_init();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    tma_prefetch_desc(&map_do);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
     }
-    __syncwarp();
-    tmem_alloc(&bars->tmem_base, kTmemCols);
+    mbar_init(&bars->qdo_full, 1);
+    mbar_init(&bars->qdo_empty, 1);
+    mbar_init(&bars->sdp_full, 1);
+    mbar_init(&bars->pds_full, 256);
+    mbar_init(&bars->dkv_full, 1);
+    mbar_init(&bars->dkv_free, 256);
+    mbar_init(&bars->item_done, 256);
+    fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
-  const float sl2 = scale * kLog2e;
 
-  if (warp == 4) {
+  if (warp == 0) {
+    // ------------------------------- TMA loader -----------------------------------------
     if (lane == 0) {
-      uint32_t ph_mma = 0, ph_warps = 0;
-      mbar_arrive_expect_tx(&bars->kv, 2 * kv_bytes);
-      tma_load_3d(sK, &map_kv, &bars->kv, inner + h * kDh, 0, b);
-      tma_load_3d(sV, &map_kv, &bars->kv, 2 * inner + h * kDh, 0, b);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK),
-                     v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-      const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);       // S / dP: K-major x K-major
-      const uint32_t idesc_dq = umma_idesc_bf16(128, kDh, 0, 1);     // dQ: A K-major, B (=K) MN-major
-      const uint32_t idesc_dkv = umma_idesc_bf16(128, kDh, 1, 1);    // dK/dV: both MN-major
-      for (int t = 0; t < q_tiles; ++t) {
-        if (t > 0) {
-          // previous tile's dQ epilogue + operand reads must be finished before Q/dO are overwritten
-          mbar_wait(&bars->warps, ph_warps); ph_warps ^= 1;
+      auto load_kv = [&](int it, int item) {
+        const int h = item % p.heads, b = item / p.heads;
+        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
+        const uint32_t kph = (it / p.kv_bufs) & 1;
+        mbar_wait(&bars->kv_empty[kb], kph ^ 1);
+        uint8_t* k_dst = sKV + kb * 2 * kv_region;
+        mbar_arrive_expect_tx(&bars->kv_full[kb], 2 * kv_bytes);
+        tma_load_3d(k_dst, &map_kv, &bars->kv_full[kb], p.inner + h * kDh, 0, b);
+        tma_load_3d(k_dst + kv_region, &map_kv, &bars->kv_full[kb], 2 * p.inner + h * kDh, 0, b);
+      };
+      int it = 0;
+      if ((int)blockIdx.x < p.num_items) load_kv(0, blockIdx.x);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int h = item % p.heads, b = item / p.heads;
+        mbar_wait(&bars->qdo_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->qdo_full, p.q_tiles * 2 * 16384);
+        for (int i = 0; i < p.q_tiles; ++i) {
+          tma_load_3d(sQ + i * 16384, &map_q, &bars->qdo_full, h * kDh, i * 128, b);
+          tma_load_3d(sDO + i * 16384, &map_do, &bars->qdo_full, h * kDh, i * 128, b);
         }
-        mbar_arrive_expect_tx(&bars->qdo, 2 * 16384);
-        tma_load_3d(sQ, &map_q, &bars->qdo, h * kDh, t * 128, b);
-        tma_load_3d(sDO, &map_do, &bars->qdo, h * kDh, t * 128, b);
-        if (t == 0) mbar_wait(&bars->kv, 0);
-        mbar_wait(&bars->qdo, t & 1);
+        if (item + (int)gridDim.x < p.num_items) load_kv(it + 1, item + gridDim.x);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -----------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_dq = umma_idesc_bf16(128, kDh, 0, 1);     // A K-major (dS), B MN-major (K)
+      const uint32_t idesc_dkv = umma_idesc_bf16(128, kDh, 1, 1);    // both MN-major
+      const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      int it = 0, st = 0, dk = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
+        const uint32_t kph = (it / p.kv_bufs) & 1;
+        mbar_wait(&bars->kv_full[kb], kph);
+        mbar_wait(&bars->qdo_full, it & 1);
         tc_fence_after_sync();
-        // ---- S_t = Q_t K^T -> scratch
+        const uint32_t k_base = smem_u32(sKV + kb * 2 * kv_region), v_base = k_base + kv_region;
+        for (int j = 0; j < p.key_tiles; ++j) {
+          const int nkj = min(128, NK - j * 128);                    // valid (padded) keys of this tile
+          const uint32_t idesc_s = umma_idesc_bf16(128, nkj, 0, 0);
+          const uint32_t kj = k_base + j * 128 * 128, vj = v_base + j * 128 * 128;
+          for (int i = 0; i < p.q_tiles; ++i, ++st) {
+            const uint32_t qi = q_base + i * 16384, doi = do_base + i * 16384;
+            // ---- S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base, umma_smem_desc(q_addr + k * 32, 16, 1024),
-                    umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&bars->mma);
-        // warps: read S, write P
-        mbar_wait(&bars->warps, ph_warps); ph_warps ^= 1;
-        tc_fence_after_sync();
-        // ---- dP_t = dO_t V^T -> scratch
+            for (int k = 0; k < kDh / 16; ++k)
+              umma_bf16(tmem_base + kColS, umma_smem_desc(qi + k * 32, 16, 1024),
+                        umma_smem_desc(kj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_bf16(tmem_base, umma_smem_desc(do_addr + k * 32, 16, 1024),
-                    umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&bars->mma);
-        // warps: read dP, write dS
-        mbar_wait(&bars->warps, ph_warps); ph_warps ^= 1;
-        tc_fence_after_sync();
-        // ---- dQ_t = dS_t K   (A = dS K-major slabs, B = K as MN-major [keys][d])
-        for (int kk = 0; kk < NK / 16; ++kk)
-          umma_bf16(tmem_base, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc(k_addr + kk * 2048, 8192, 1024), idesc_dq, kk > 0 ? 1u : 0u);
-        // ---- dV += P_t^T dO_t ; dK += dS_t^T Q_t   (A = slabs as MN-major [q][keys], 128 keys per tile)
-        for (int kt = 0; kt < key_tiles; ++kt) {
-          for (int kk = 0; kk < 128 / 16; ++kk) {       // contraction over the 128 query rows
-            const uint32_t acc = (t > 0 || kk > 0) ? 1u : 0u;
-            umma_bf16(tmem_base + kColDV + kt * 64,
-                      umma_smem_desc(p_addr + kt * 2 * 16384 + kk * 2048, 16384, 1024),
-                      umma_smem_desc(do_addr + kk * 2048, 8192, 1024), idesc_dkv, acc);
-            umma_bf16(tmem_base + kColDK + kt * 64,
-                      umma_smem_desc(ds_addr + kt * 2 * 16384 + kk * 2048, 16384, 1024),
-                      umma_smem_desc(q_addr + kk * 2048, 8192, 1024), idesc_dkv, acc);
+            for (int k = 0; k < kDh / 16; ++k)
+              umma_bf16(tmem_base + kColDP, umma_smem_desc(doi + k * 32, 16, 1024),
+                        umma_smem_desc(vj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&bars->sdp_full);
+            // ---- wait for P_ij / dS_ij, then the three accumulating products
+            mbar_wait(&bars->pds_full, st & 1);
+            if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);   // dV/dK accumulators drained
+            if (j == 0 && i == 0 && it > 0) mbar_wait(&bars->item_done, (it - 1) & 1);   // dQ accumulators drained
+            tc_fence_after_sync();
+            for (int kk = 0; kk < 128 / 16; ++kk) {                  // contraction over the 128 query rows
+              const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+              umma_bf16(tmem_base + kColDV, umma_smem_desc(p_addr + kk * 2048, 16384, 1024),
+                        umma_smem_desc(doi + kk * 2048, 8192, 1024), idesc_dkv, acc);
+              umma_bf16(tmem_base + kColDK, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024),
+                        umma_smem_desc(qi + kk * 2048, 8192, 1024), idesc_dkv, acc);
+            }
+            for (int kk = 0; kk < nkj / 16; ++kk)                    // contraction over this tile's keys
+              umma_bf16(tmem_base + kColDQ + i * 64,
+                        umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_smem_desc(kj + kk * 2048, 8192, 1024), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+            if (i == p.q_tiles - 1) {
+              umma_commit(&bars->dkv_full);
+              ++dk;
+            }
           }
         }
-        umma_commit(&bars->mma);
+        umma_commit(&bars->kv_empty[kb]);
+        umma_commit(&bars->qdo_empty);
       }
-      (void)ph_mma;
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const uint32_t p_u32 = smem_u32(sP), ds_u32 = smem_u32(sDS);
-    const int nchunks = (NK + 31) / 32;
-    const int ncols_slab = slabs * 64;
-    uint32_t ph_mma = 0;
-    for (int t = 0; t < q_tiles; ++t) {
-      const int grow = t * 128 + row;
-      const bool valid = grow < n;
-      // delta = rowsum(dO * O), LSE
-      float delta = 0.f, l2 = 0.f;
-      if (valid) {
-        const bf16* po = o + ((size_t)b * n + grow) * inner + h * kDh;
-        const bf16* pd = dout + ((size_t)b * n + grow) * inner + h * kDh;
+    // ------------------------------- P / dS producers + epilogues ------------------------
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t p_slab = smem_u32(sP + wg * 16384), ds_slab = smem_u32(sDS + wg * 16384);
+    const float sl2 = p.scale * kLog2e;
+    int it = 0, st = 0, dk = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int h = item % p.heads, b = item / p.heads;
+      // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile
+      float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
+      for (int i = 0; i < p.q_tiles; ++i) {
+        const int grow = i * 128 + row;
+        if (grow < n) {
+          const bf16* po = p.o + ((size_t)b * n + grow) * p.inner + h * kDh;
+          const bf16* pd = p.dout + ((size_t)b * n + grow) * p.inner + h * kDh;
+          float acc = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint4 a = *reinterpret_cast<const uint4*>(po + g * 8);
-          const uint4 d = *reinterpret_cast<const uint4*>(pd + g * 8);
-          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-          const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-          delta += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y +
+          for (int g = 0; g < 8; ++g) {
+            const uint4 a = *reinterpret_cast<const uint4*>(po + g * 8);
+            const uint4 d = *reinterpret_cast<const uint4*>(pd + g * 8);
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+            const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+            acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y +
                    a3.x * d3.x + a3.y * d3.y;
+          }
+          delta[i] = acc;
+          l2[i] = p.lse[((size_t)b * p.heads + h) * n + grow] * kLog2e;
         }
-        l2 = lse[((size_t)b * heads + h) * n + grow] * kLog2e;
       }
-      // ---- P_t
-      mbar_wait(&bars->mma, ph_mma); ph_mma ^= 1;
-      tc_fence_after_sync();
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
+      for (int j = 0; j < p.key_tiles; ++j) {
+        for (int i = 0; i < p.q_tiles; ++i, ++st) {
+          const int grow = i * 128 + row;
+          const bool valid = grow < n;
+          const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
+          const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
+          const bool cols_any = key0 < n;
+          const float dl = delta[i], lg = l2[i];
+          mbar_wait(&bars->sdp_full, st & 1);
+          tc_fence_after_sync();
+          if (warp_rows && cols_any) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = c * 32 + g * 8;
-          if (col < ncols_slab) {
-            float pv[8];
+            for (int c = 0; c < 2; ++c) {
+              uint32_t sv[32], dv[32];
+              tmem_ld_32x32(t_row + kColS + wg * 64 + c * 32, sv);
+              tmem_ld_32x32(t_row + kColDP + wg * 64 + c * 32, dv);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              pv[j] = (valid && col + j < n) ? exp2f(__uint_as_float(v[g * 8 + j]) * sl2 - l2) : 0.f;
-            uint4 u;
-            u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-            u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-            st_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, u);
+              for (int g = 0; g < 4; ++g) {
+                float pv[8], ds[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int key = key0 + c * 32 + g * 8 + e;
+                  const float pe = exp2f(fmaf(__uint_as_float(sv[g * 8 + e]), sl2, -lg));
+                  const bool ok = valid && key < n;
+                  pv[e] = ok ? pe : 0.f;
+                  ds[e] = ok ? pe * (__uint_as_float(dv[g * 8 + e]) - dl) * p.scale : 0.f;
+                }
+                uint4 u, w;
+                u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
+                u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
+                w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
+                w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
+                st_swz_chunk(p_slab, row, c * 4 + g, u);
+                st_swz_chunk(ds_slab, row, c * 4 + g, w);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              st_swz_chunk(p_slab, row, ch, make_uint4(0, 0, 0, 0));
+              st_swz_chunk(ds_slab, row, ch, make_uint4(0, 0, 0, 0));
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(&bars->pds_full);
+          if (i == p.q_tiles - 1) {
+            // ---- dV_j (group 0) / dK_j (group 1) epilogue
+            mbar_wait(&bars->dkv_full, dk & 1);
+            tc_fence_after_sync();
+            const int key = j * 128 + row;
+            if (j * 128 + quad * 32 < n) {
+              uint32_t a0[32], a1[32];
+              const uint32_t col = wg == 0 ? kColDV : kColDK;
+              tmem_ld_32x32(t_row + col, a0);
+              tmem_ld_32x32(t_row + col + 32, a1);
+              tmem_ld_wait();
+              if (key < n)
+                store_row64(p.dqkv + ((size_t)b * n + key) * (3 * p.inner) + (wg == 0 ? 2 : 1) * p.inner + h * kDh,
+                            a0, a1);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&bars->dkv_free);
+            ++dk;
           }
         }
       }
-      // zero the slab tail beyond the last 32-column chunk (keys in [nchunks*32, slabs*64))
-      for (int col = nchunks * 32; col < ncols_slab; col += 8) {
-        st_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, make_uint4(0, 0, 0, 0));
-        st_swz_chunk(ds_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, make_uint4(0, 0, 0, 0));
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->warps);
-      // ---- dS_t
-      mbar_wait(&bars->mma, ph_mma); ph_mma ^= 1;
-      tc_fence_after_sync();
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = c * 32 + g * 8;
-          if (col < ncols_slab) {
-            const uint4 pk = ld_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3);
-            const float2 p0 = unpack_bf16x2(pk.x), p1 = unpack_bf16x2(pk.y), p2 = unpack_bf16x2(pk.z),
-                         p3 = unpack_bf16x2(pk.w);
-            const float pp[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
-            float ds[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ds[j] = (valid && col + j < n) ? pp[j] * (__uint_as_float(v[g * 8 + j]) - delta) * scale : 0.f;
-            uint4 u;
-            u.x = pack_bf16x2(ds[0], ds[1]); u.y = pack_bf16x2(ds[2], ds[3]);
-            u.z = pack_bf16x2(ds[4], ds[5]); u.w = pack_bf16x2(ds[6], ds[7]);
-            st_swz_chunk(ds_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, u);
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->warps);
-      // ---- dQ_t epilogue
-      mbar_wait(&bars->mma, ph_mma); ph_mma ^= 1;
-      tc_fence_after_sync();
-      {
+      // ---- dQ epilogue: group w drains query tile w (the last dkv_full commit covered every MMA)
+      if (wg < p.q_tiles && (wg * 128 + quad * 32) < n) {
         uint32_t a0[32], a1[32];
-        tmem_ld_32x32(t_row, a0);
-        tmem_ld_32x32(t_row + 32, a1);
+        tmem_ld_32x32(t_row + kColDQ + wg * 64, a0);
+        tmem_ld_32x32(t_row + kColDQ + wg * 64 + 32, a1);
         tmem_ld_wait();
-        if (valid) {
-          bf16* dst = dqkv + ((size_t)b * n + grow) * (3 * inner) + h * kDh;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(a0[g * 8 + 0]), __uint_as_float(a0[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a0[g * 8 + 2]), __uint_as_float(a0[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a0[g * 8 + 4]), __uint_as_float(a0[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a0[g * 8 + 6]), __uint_as_float(a0[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + g * 8) = u;
-            u.x = pack_bf16x2(__uint_as_float(a1[g * 8 + 0]), __uint_as_float(a1[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a1[g * 8 + 2]), __uint_as_float(a1[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a1[g * 8 + 4]), __uint_as_float(a1[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a1[g * 8 + 6]), __uint_as_float(a1[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
-          }
-        }
+        const int grow = wg * 128 + row;
+        if (grow < n) store_row64(p.dqkv + ((size_t)b * n + grow) * (3 * p.inner) + h * kDh, a0, a1);
       }
-      if (t + 1 < q_tiles) {
-        tc_fence_before_sync();
-        mbar_arrive(&bars->warps);   // Q / dO / P / dS / scratch may be reused
-      }
-    }
-    // ---- dK / dV epilogue (the last commit covered every MMA)
-    for (int kt = 0; kt < key_tiles; ++kt) {
-      const int key = kt * 128 + row;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {     // 0: dV, 1: dK
-        uint32_t a0[32], a1[32];
-        const uint32_t col = (which == 0 ? kColDV : kColDK) + kt * 64;
-        tmem_ld_32x32(t_row + col, a0);
-        tmem_ld_32x32(t_row + col + 32, a1);
-        tmem_ld_wait();
-        if (key < n) {
-          bf16* dst = dqkv + ((size_t)b * n + key) * (3 * inner) + (which == 0 ? 2 : 1) * inner + h * kDh;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(a0[g * 8 + 0]), __uint_as_float(a0[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a0[g * 8 + 2]), __uint_as_float(a0[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a0[g * 8 + 4]), __uint_as_float(a0[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a0[g * 8 + 6]), __uint_as_float(a0[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + g * 8) = u;
-            u.x = pack_bf16x2(__uint_as_float(a1[g * 8 + 0]), __uint_as_float(a1[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a1[g * 8 + 2]), __uint_as_float(a1[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a1[g * 8 + 4]), __uint_as_float(a1[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a1[g * 8 + 6]), __uint_as_float(a1[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
-          }
-        }
-      }
+      tc_fence_before_sync();
+      mbar_arrive(&bars->item_done);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -513,18 +594,27 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
   if (s) return s;
   s = make_tmap_3d_bf16(&map_kv, qkv_bf16, 3 * inner, n, batch, 3 * inner, (uint64_t)n * 3 * inner, NK);
   if (s) return s;
+  AttnFwdParams p;
+  p.out = (bf16*)out_bf16; p.lse = lse; p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
+  p.q_tiles = (n + 127) / 128;
+  const int per_tile = (n + p.q_tiles - 1) / p.q_tiles;
+  p.tile_rows = std::min(128, (per_tile + 31) & ~31);
+  p.num_items = batch * heads;
+  p.slot_cols = 64;
+  while (p.slot_cols < NK) p.slot_cols <<= 1;
   const int kv_region = (NK * 128 + 1023) & ~1023;
   const int p_slabs = (NK + 63) / 64;
-  const int regA = std::max(16384 + kv_region, p_slabs * 16384);
-  const int smem = 1024 + regA + kv_region + 128;
-  static int configured = 0;
-  if (configured < smem) {
-    M3L_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+  const int fixed = 1024 + 2 * 16384 + 2 * p_slabs * 16384 + 256;
+  p.kv_bufs = (fixed + 2 * 2 * kv_region <= 227 * 1024) ? 2 : 1;
+  const int smem = fixed + p.kv_bufs * 2 * kv_region;
+  M3L_REQUIRE(smem <= 227 * 1024, "attention_fwd: shared memory budget exceeded (n=%d)", n);
+  static bool configured = false;
+  if (!configured) {
+    M3L_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
-  const int q_tiles = (n + 127) / 128;
-  attn_fwd_kernel<<<batch * heads * q_tiles, 160, smem, (cudaStream_t)stream>>>(
-      map_q, map_kv, (bf16*)out_bf16, lse, n, heads, inner, q_tiles, scale);
+  const int grid = std::min(p.num_items, device_sm_count());
+  attn_fwd_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(map_q, map_kv, p);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -545,17 +635,24 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
   if (s) return s;
   s = make_tmap_3d_bf16(&map_do, dout_bf16, inner, n, batch, inner, (uint64_t)n * inner, 128);
   if (s) return s;
+  AttnBwdParams p;
+  p.o = (const bf16*)out_bf16; p.dout = (const bf16*)dout_bf16; p.lse = lse; p.dqkv = (bf16*)dqkv_bf16;
+  p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
+  p.q_tiles = (n + 127) / 128;
+  p.key_tiles = (NK + 127) / 128;
+  p.num_items = batch * heads;
   const int kv_region = (NK * 128 + 1023) & ~1023;
-  const int slabs = 2 * ((NK + 127) / 128);
-  const int smem = 1024 + 2 * 16384 + 2 * kv_region + 2 * slabs * 16384 + 128;
+  const int fixed = 1024 + 8 * 16384 + 256;
+  p.kv_bufs = (fixed + 2 * 2 * kv_region <= 227 * 1024) ? 2 : 1;
+  const int smem = fixed + p.kv_bufs * 2 * kv_region;
+  M3L_REQUIRE(smem <= 227 * 1024, "attention_bwd: shared memory budget exceeded (n=%d)", n);
   static bool configured = false;
   if (!configured) {
     M3L_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  attn_bwd_kernel<<<batch * heads, 160, smem, (cudaStream_t)stream>>>(
-      map_q, map_kv, map_do, (const bf16*)out_bf16, (const bf16*)dout_bf16, lse, (bf16*)dqkv_bf16, n, heads,
-      inner, scale);
+  const int grid = std::min(p.num_items, device_sm_count());
+  attn_bwd_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(map_q, map_kv, map_do, p);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -180,7 +180,9 @@ def _attn_ref(qkv, B, n, H, scale):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * n, H * 64), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,n,H", [(3, 10, 4), (5, 4, 4), (2, 50, 4), (3, 64, 2), (2, 192, 4), (1, 256, 1), (2, 130, 3)])
+@pytest.mark.parametrize("B,n,H", [(3, 10, 4), (5, 4, 4), (2, 50, 4), (3, 64, 2), (2, 192, 4), (1, 256, 1), (2, 130, 3),
+                                   # persistent kernels: several (sample, head) items per CTA
+                                   (96, 192, 4), (120, 10, 4), (45, 256, 4), (50, 100, 8)])
 def test_attention_fwd_bwd(ops, B, n, H):
     torch.manual_seed(7)
     scale = 64 ** -0.5
