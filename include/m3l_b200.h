@@ -114,7 +114,8 @@ int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, const float*
                       const int32_t* dst_row, const float* add0, const int32_t* add0_row,
                       const float* add1, const int32_t* add1_row, void* stream);
 
-/* LayerNorm backward: dx = dLN(dy) (+ skip), dgamma/dbeta += column sums (fp32 atomics).
+/* LayerNorm backward: dx = dLN(dy) (+ skip), dgamma/dbeta += column sums (block-reduced, then
+ * fp32 atomics; grids are sized so each address sees at most a few hundred of them).
  * src_row (optional): dy row gather, negative = zero gradient row.
  * dx_colsum (optional): += column sums of dx, i.e. the bias gradient of the nn.Linear whose output
  * gradient dx is (saves a separate reduction pass over dx). */
@@ -132,7 +133,7 @@ int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const float* mas
 int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot_of_token, int batch,
                              int n_tokens, int dim, int n_visible, void* dd_bf16,
                              float* dmask_token, float* dadd0, const int32_t* tok_class,
-                             float* dadd1, void* stream);
+                             int n_classes, float* dadd1, void* stream);
 
 /* Gradient of the broadcast embedding adds on the encoder side: dclass[slot_class[j]] += sum_b dx[b,j],
  * dpos[row_pos[b,j]] += dx[b,j] (either may be NULL). */
@@ -141,10 +142,13 @@ int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, int dim,
                      void* stream);
 
 /* Masked-patch MSE (pretrain_models.py:327-340): target rows are gathered from the raw maps;
- * *loss_acc += weight * sum((pred - target)^2); dpred = 2 * weight * (pred - target) (bf16). */
+ * *loss_acc += weight * sum((pred - target)^2); dpred = 2 * weight * (pred - target) (bf16).
+ * workspace: device scratch (>= 256 + 4 * blocks bytes; 1 MiB is always enough) whose first 4 bytes
+ * are zero on entry and zero again on exit; per-block partial losses are summed by the last block
+ * to finish, which makes the loss bit-reproducible run to run. */
 int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
                  int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
-                 void* stream);
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[n] += sum_m x[m, n] (bias gradients). */
 int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);

@@ -109,6 +109,50 @@ M3L_DEVINL void load_patch_smem(const PatchSrc& ps, const float* origin, float* 
   }
 }
 
+// Two-stage column reduction without contended atomics (same-sector fp32 atomics serialise at
+// roughly one per 10 ns on B200 and dominated these kernels): every block stores its partial
+// vector to ws_part[block][nv]; the block that draws the last ticket sums all partials and adds
+// them into out[] (plain adds: kernels on a stream are ordered).  ws layout: [0] ticket counter
+// (zero on entry, reset to zero on exit), partials from byte 256.
+struct ReduceWs {
+  unsigned int* counter;
+  float* partials;
+};
+M3L_DEVINL ReduceWs reduce_ws(void* ws) {
+  ReduceWs r;
+  r.counter = reinterpret_cast<unsigned int*>(ws);
+  r.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 256);
+  return r;
+}
+// Call from all threads of every block after the block's partial vector (nv floats) has been
+// written to ws.partials[linear_block * nv ...] by this block.  `sink(col, total)` is invoked by
+// the last block once per column.
+template <typename Sink>
+M3L_DEVINL void last_block_reduce(const ReduceWs& ws, int nv, int num_blocks, Sink sink) {
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(ws.counter, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)num_blocks - 1) return;
+  __threadfence();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthreads = blockDim.x * blockDim.y;
+  for (int col = tid; col < nv; col += nthreads) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int b = 0;
+    for (; b + 3 < num_blocks; b += 4) {
+      t0 += __ldcg(ws.partials + (size_t)b * nv + col);
+      t1 += __ldcg(ws.partials + (size_t)(b + 1) * nv + col);
+      t2 += __ldcg(ws.partials + (size_t)(b + 2) * nv + col);
+      t3 += __ldcg(ws.partials + (size_t)(b + 3) * nv + col);
+    }
+    for (; b < num_blocks; ++b) t0 += __ldcg(ws.partials + (size_t)b * nv + col);
+    sink(col, (t0 + t1) + (t2 + t3));
+  }
+  if (tid == 0) *ws.counter = 0u;
+}
+
 M3L_DEVINL float block_sum(float v, float* red) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -391,6 +435,244 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ sr
     }
   }
   __syncthreads();
+  // grid is capped at two blocks per SM by the host, so each address sees <= ~300 atomics
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) t += spart[(size_t)w * 3 * D + i];
+    const int which = i / D, col = i - which * D;
+    if (which == 0) { if (dgamma) atomicAdd(&dgamma[col], t); }
+    else if (which == 1) { if (dbeta) atomicAdd(&dbeta[col], t); }
+    else if (dx_colsum) atomicAdd(&dx_colsum[col], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 fast paths: warp-private cp.async (LDGSTS) rings keep kStages rows per stream in flight per
+// warp without holding them in registers (these kernels are HBM-latency bound otherwise: the ncu
+// source page showed ~60 % long-scoreboard stalls on the row loads).
+// ------------------------------------------------------------------------------------------
+M3L_DEVINL void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+M3L_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+M3L_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+M3L_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+M3L_DEVINL void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+M3L_DEVINL void cvt8(uint4 u, float (&v)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+template <int NCH, int kStages>
+__global__ void __launch_bounds__(256)
+ln_fwd_pipe_kernel(const bf16* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, bf16* __restrict__ y, float* __restrict__ stats,
+                   const int32_t* __restrict__ dst_row, const float* __restrict__ add0,
+                   const int32_t* __restrict__ add0_row, const float* __restrict__ add1,
+                   const int32_t* __restrict__ add1_row) {
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const float inv_d = 1.0f / D;
+  constexpr int kRowBytes = NCH * 512;
+  const uint32_t ring = smem_u32(ring_raw) + warp * (kStages * kRowBytes);
+  float g[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      load8<float>(gamma + ch * 8, g[c]);
+      load8<float>(beta + ch * 8, bt[c]);
+    }
+  }
+  const int rstride = gridDim.x * warps_per_block;
+  const int r0 = blockIdx.x * warps_per_block + warp;
+  auto issue = [&](int row, int stage) {
+    if (row < M) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunk) cp_async16(ring + stage * kRowBytes + ch * 16, x + (size_t)row * D + ch * 8);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kStages; ++s) issue(r0 + s * rstride, s);
+  int stage = 0;
+  for (int r = r0; r < M; r += rstride) {
+    cp_async_wait<kStages - 1>();
+    float v[NCH][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        cvt8(lds128(ring + stage * kRowBytes + ch * 16), v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += v[c][i];
+      }
+    }
+    issue(r + kStages * rstride, stage);
+    stage = (stage + 1 == kStages) ? 0 : stage + 1;
+    const float mean = warp_sum(sum) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (lane + 32 * c < nchunk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[c][i] -= mean;
+          q += v[c][i] * v[c][i];
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (stats && lane == 0) *reinterpret_cast<float2*>(stats + 2 * r) = make_float2(mean, rstd);
+    const int dr = dst_row ? dst_row[r] : r;
+    if (dr < 0) continue;
+    const float* a0 = add0 ? add0 + (size_t)(add0_row ? add0_row[r] : 0) * D : nullptr;
+    const float* a1 = add1 ? add1 + (size_t)(add1_row ? add1_row[r] : 0) * D : nullptr;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(v[c][i] * rstd, g[c][i], bt[c][i]);
+        if (a0) {
+          float t[8];
+          load8<float>(a0 + ch * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        if (a1) {
+          float t[8];
+          load8<float>(a1 + ch * 8, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += t[i];
+        }
+        store8(y + (size_t)dr * D + ch * 8, o);
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int NCH, int kStages>
+__global__ void __launch_bounds__(256)
+ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_row, const bf16* __restrict__ x,
+                   const float* __restrict__ stats, int M, int D, const float* __restrict__ gamma,
+                   const bf16* __restrict__ skip, bf16* __restrict__ dx, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const float inv_d = 1.0f / D;
+  constexpr int kRowBytes = NCH * 512;
+  constexpr int kStageBytes = 3 * kRowBytes;           // x | dy | skip
+  const uint32_t ring = smem_u32(ring_raw) + warp * (kStages * kStageBytes);
+  float* spart = reinterpret_cast<float*>(ring_raw + (size_t)warps_per_block * kStages * kStageBytes);  // [warps][3][D]
+  float gm[NCH][8], ag[NCH][8], ab[NCH][8], ac[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) load8<float>(gamma + ch * 8, gm[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ac[c][i] = 0.f;
+  }
+  const int rstride = gridDim.x * warps_per_block;
+  const int r0 = blockIdx.x * warps_per_block + warp;
+  auto issue = [&](int row, int stage) {
+    if (row < M) {
+      const int sr = src_row ? src_row[row] : row;
+      const uint32_t base = ring + stage * kStageBytes;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunk) {
+          cp_async16(base + ch * 16, x + (size_t)row * D + ch * 8);
+          if (sr >= 0) cp_async16(base + kRowBytes + ch * 16, dy + (size_t)sr * D + ch * 8);
+          else sts128(base + kRowBytes + ch * 16, make_uint4(0, 0, 0, 0));
+          if (skip) cp_async16(base + 2 * kRowBytes + ch * 16, skip + (size_t)row * D + ch * 8);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kStages; ++s) issue(r0 + s * rstride, s);
+  int stage = 0;
+  for (int r = r0; r < M; r += rstride) {
+    const float2 ms = *reinterpret_cast<const float2*>(stats + 2 * r);
+    cp_async_wait<kStages - 1>();
+    const float mean = ms.x, rstd = ms.y;
+    const uint32_t base = ring + stage * kStageBytes;
+    float xh[NCH][8], g[NCH][8], sk[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float xv[8], dv[8];
+        cvt8(lds128(base + ch * 16), xv);
+        cvt8(lds128(base + kRowBytes + ch * 16), dv);
+        if (skip) cvt8(lds128(base + 2 * kRowBytes + ch * 16), sk[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (xv[i] - mean) * rstd;
+          g[c][i] = dv[i] * gm[c][i];
+          s1 += g[c][i];
+          s2 = fmaf(g[c][i], xh[c][i], s2);
+          ag[c][i] = fmaf(dv[i], xh[c][i], ag[c][i]);
+          ab[c][i] += dv[i];
+        }
+      }
+    }
+    issue(r + kStages * rstride, stage);
+    stage = (stage + 1 == kStages) ? 0 : stage + 1;
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        if (skip) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += sk[c][i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ac[c][i] += o[i];
+        store8(dx + (size_t)r * D + ch * 8, o);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (dgamma == nullptr && dx_colsum == nullptr) return;
+  float* mine = spart + (size_t)warp * 3 * D;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      store8(mine + ch * 8, ag[c]);
+      store8(mine + D + ch * 8, ab[c]);
+      store8(mine + 2 * D + ch * 8, ac[c]);
+    }
+  }
+  __syncthreads();
+  // grid is capped at two blocks per SM by the host, so each address sees <= ~300 atomics
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
     float t = 0.f;
     for (int w = 0; w < warps_per_block; ++w) t += spart[(size_t)w * 3 * D + i];
@@ -437,34 +719,89 @@ __global__ void assemble_fwd_kernel(const bf16* __restrict__ d, int nv, const fl
 }
 
 // backward: dd[b*nv+slot] = dz[b,t] (visible); d mask_token += sum(masked rows);
-// d add0[class] += sum rows of the class; d add1[t] += sum over b (only if dadd1 != null).
-// Block = (token position t, chunk of 32 samples); thread = 2 adjacent columns.
-__global__ void assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slot_of_token,
-                                    int B, int n, int D, int nv, bf16* __restrict__ dd,
-                                    float* __restrict__ dmask_token, float* __restrict__ dadd0,
-                                    const int32_t* __restrict__ tok_class, float* __restrict__ dadd1) {
-  const int t = blockIdx.x;
-  const int b0 = blockIdx.y * 32, b1 = min(b0 + 32, B);
-  for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
-    float2 sum_all = make_float2(0.f, 0.f), sum_masked = make_float2(0.f, 0.f);
-    for (int b = b0; b < b1; ++b) {
-      const size_t r = (size_t)b * n + t;
-      const int slot = slot_of_token[r];
-      const uint32_t raw = *reinterpret_cast<const uint32_t*>(dz + r * D + c);
-      const float2 g = unpack_bf16x2(raw);
-      sum_all.x += g.x; sum_all.y += g.y;
-      if (slot >= 0) *reinterpret_cast<uint32_t*>(dd + ((size_t)b * nv + slot) * D + c) = raw;
-      else { sum_masked.x += g.x; sum_masked.y += g.y; }
+// d add0[class] += sum rows of the class; d add1[t] += sum over b (only if dadd1 != null; that
+// learned-position variant keeps atomics: its sums are per token, not contended).
+// Warp per row (lane = 8 columns), accumulators [masked | class 0..3] in registers, block partials
+// through smem, then one atomic per block and column (grid capped at two blocks per SM).
+constexpr int kAsmClasses = 4;
+template <int NCH>
+__global__ void __launch_bounds__(256)
+assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slot_of_token,
+                    int B, int n, int D, int nv, bf16* __restrict__ dd,
+                    float* __restrict__ dmask_token, float* __restrict__ dadd0,
+                    const int32_t* __restrict__ tok_class, int n_classes, float* __restrict__ dadd1) {
+  extern __shared__ float sred[];   // [warps][(1 + kAsmClasses)][D]
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const int M = B * n;
+  float acc[1 + kAsmClasses][NCH][8];
+#pragma unroll
+  for (int k = 0; k < 1 + kAsmClasses; ++k)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[k][c][i] = 0.f;
+  const int rstride = gridDim.x * warps_per_block;
+  int r = blockIdx.x * warps_per_block + warp;
+  Raw8<bf16> nxt[NCH];
+  int nslot = 0;
+  auto prefetch = [&](int row) {
+    nslot = slot_of_token[row];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (lane + 32 * c < nchunk) raw_load(dz + (size_t)row * D + (lane + 32 * c) * 8, nxt[c]);
+  };
+  if (r < M) prefetch(r);
+  for (; r < M; r += rstride) {
+    const int b = r / n, t = r - b * n;
+    const int slot = nslot;
+    Raw8<bf16> cur[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cur[c] = nxt[c];
+    if (r + rstride < M) prefetch(r + rstride);
+    const int cls = (dadd0 && tok_class) ? tok_class[t] : 0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float v[8];
+        raw_cvt(cur[c], v);
+        if (slot >= 0) {
+          *reinterpret_cast<uint4*>(dd + ((size_t)b * nv + slot) * D + ch * 8) = cur[c].a;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[0][c][i] += v[i];
+        }
+#pragma unroll
+        for (int k = 0; k < kAsmClasses; ++k)
+          if (cls == k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[1 + k][c][i] += v[i];
+          }
+        if (dadd1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(&dadd1[(size_t)t * D + ch * 8 + i], v[i]);
+        }
+      }
     }
-    if (dmask_token) { atomicAdd(&dmask_token[c], sum_masked.x); atomicAdd(&dmask_token[c + 1], sum_masked.y); }
-    if (dadd0) {
-      float* d0 = dadd0 + (size_t)tok_class[t] * D + c;
-      atomicAdd(d0, sum_all.x); atomicAdd(d0 + 1, sum_all.y);
+  }
+  const int nvec = (1 + kAsmClasses) * D;
+  float* mine = sred + (size_t)warp * nvec;
+#pragma unroll
+  for (int k = 0; k < 1 + kAsmClasses; ++k)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) store8(mine + k * D + ch * 8, acc[k][c]);
     }
-    if (dadd1) {
-      float* d1 = dadd1 + (size_t)t * D + c;
-      atomicAdd(d1, sum_all.x); atomicAdd(d1 + 1, sum_all.y);
-    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float tsum = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) tsum += sred[(size_t)w * nvec + i];
+    const int k = i / D, col = i - k * D;
+    if (k == 0) { if (dmask_token) atomicAdd(&dmask_token[col], tsum); }
+    else if (dadd0 && (k - 1) < n_classes) atomicAdd(&dadd0[(size_t)(k - 1) * D + col], tsum);
   }
 }
 
@@ -493,7 +830,7 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
 __global__ void __launch_bounds__(256)
 mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols, int rows,
                 const float* __restrict__ pred, float weight, bf16* __restrict__ dpred,
-                float* __restrict__ loss_acc) {
+                float* __restrict__ loss_acc, void* ws) {
   extern __shared__ float patches[];   // [warps][P] floats, destination order (p1, p2, c)
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -511,7 +848,15 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
       const int c = i / ps.ph, p1 = i - c * ps.ph;
       const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
       float* dst = patch + (p1 * ps.pw) * ps.C + c;
-      for (int p2 = 0; p2 < ps.pw; ++p2) dst[p2 * ps.C] = src[p2];
+      if ((ps.pw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int p2 = 0; p2 < ps.pw; p2 += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + p2));
+          dst[(p2 + 0) * ps.C] = v.x; dst[(p2 + 1) * ps.C] = v.y;
+          dst[(p2 + 2) * ps.C] = v.z; dst[(p2 + 3) * ps.C] = v.w;
+        }
+      } else {
+        for (int p2 = 0; p2 < ps.pw; ++p2) dst[p2 * ps.C] = src[p2];
+      }
     }
     __syncwarp();
     const float* prow = pred + (size_t)r * P;
@@ -527,11 +872,13 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
   acc = warp_sum(acc);
   if (lane == 0) red[warp] = acc;
   __syncthreads();
+  const ReduceWs rws = reduce_ws(ws);
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < nwarps; ++w) t += red[w];
-    atomicAdd(loss_acc, weight * t);
+    rws.partials[blockIdx.x] = weight * t;
   }
+  last_block_reduce(rws, 1, gridDim.x, [&](int, float t) { *loss_acc += t; });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -676,7 +1023,16 @@ extern "C" int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, c
 #define M3L_LN_FWD(T, N)                                                                                   \
   layernorm_fwd_kernel<T, N><<<grid, wpb * 32, 0, st>>>((const T*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, \
                                                         stats, dst_row, add0, add0_row, add1, add1_row)
-  if (x_fp32) {
+  if (!x_fp32 && nch <= 2) {
+    // bf16 fast path: 4-deep warp-private cp.async ring
+    const size_t ring = (size_t)wpb * 4 * nch * 512;
+    if (nch == 1)
+      ln_fwd_pipe_kernel<1, 4><<<grid, wpb * 32, ring, st>>>((const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
+                                                            stats, dst_row, add0, add0_row, add1, add1_row);
+    else
+      ln_fwd_pipe_kernel<2, 4><<<grid, wpb * 32, ring, st>>>((const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
+                                                            stats, dst_row, add0, add0_row, add1, add1_row);
+  } else if (x_fp32) {
     if (nch == 1) M3L_LN_FWD(float, 1); else if (nch == 2) M3L_LN_FWD(float, 2); else M3L_LN_FWD(float, 4);
   } else {
     if (nch == 1) M3L_LN_FWD(bf16, 1); else if (nch == 2) M3L_LN_FWD(bf16, 2); else M3L_LN_FWD(bf16, 4);
@@ -715,8 +1071,8 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
   M3L_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set");
   if (rows == 0) return M3L_OK;
   const int wpb = 8;
-  int grid = (rows + 8 * wpb - 1) / (8 * wpb);   // >= 8 rows per warp so the block-level reduction amortises
-  const int cap = device_sm_count() * 4;
+  int grid = (rows + 2 * wpb - 1) / (2 * wpb);   // small problems: favour parallelism (2 rows per warp)
+  const int cap = device_sm_count() * 2;    // bounds the atomics per gradient address (contended fp32 atomics ~10 ns each)
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   const size_t smem = (size_t)wpb * 3 * dim * sizeof(float);
@@ -724,6 +1080,24 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
   cudaStream_t st = (cudaStream_t)stream;
   const bf16* dy = (const bf16*)dy_bf16;
   const bf16* skip = (const bf16*)skip_bf16;
+  if (!x_fp32 && !dx_fp32 && nch <= 2) {
+    constexpr int kSt = 3;
+
+    const size_t ring = (size_t)wpb * kSt * 3 * nch * 512;
+    const size_t total = ring + smem;
+    static bool configured = false;
+    if (!configured) {
+      M3L_CUDA(cudaFuncSetAttribute(ln_bwd_pipe_kernel<1, kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      M3L_CUDA(cudaFuncSetAttribute(ln_bwd_pipe_kernel<2, kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      configured = true;
+    }
+    if (nch == 1)
+      ln_bwd_pipe_kernel<1, kSt><<<grid, 256, total, st>>>(dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+    else
+      ln_bwd_pipe_kernel<2, kSt><<<grid, 256, total, st>>>(dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+    M3L_CUDA(cudaGetLastError());
+    return M3L_OK;
+  }
   if (x_fp32 && !dx_fp32)
     return launch_ln_bwd<float, bf16>(nch, grid, smem, st, dy, src_row, (const float*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
   if (!x_fp32 && !dx_fp32)
@@ -752,14 +1126,33 @@ extern "C" int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const
 extern "C" int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot_of_token, int batch,
                                         int n_tokens, int dim, int n_visible, void* dd_bf16,
                                         float* dmask_token, float* dadd0, const int32_t* tok_class,
-                                        float* dadd1, void* stream) {
+                                        int n_classes, float* dadd1, void* stream) {
   M3L_REQUIRE(dz_bf16 && slot_of_token && dd_bf16, "decoder_assemble_bwd: null pointer");
   M3L_REQUIRE(dadd0 == nullptr || tok_class != nullptr, "decoder_assemble_bwd: dadd0 needs tok_class");
+  M3L_REQUIRE(dim % 8 == 0 && dim <= 1024, "decoder_assemble_bwd: dim %d unsupported", dim);
+  M3L_REQUIRE(n_classes >= 0 && n_classes <= kAsmClasses, "decoder_assemble_bwd: at most %d token classes", kAsmClasses);
   if (batch * n_tokens == 0) return M3L_OK;
-  M3L_REQUIRE(dim % 2 == 0, "decoder_assemble_bwd: dim must be even");
-  assemble_bwd_kernel<<<dim3(n_tokens, (batch + 31) / 32), 128, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, n_visible, (bf16*)dd_bf16, dmask_token, dadd0,
-      tok_class, dadd1);
+  const int rows = batch * n_tokens;
+  const int wpb = 8;
+  int grid = (rows + 4 * wpb - 1) / (4 * wpb);
+  if (grid > device_sm_count() * 2) grid = device_sm_count() * 2;
+  const int nvec = (1 + kAsmClasses) * dim;
+  const size_t smem = (size_t)wpb * nvec * sizeof(float);
+  const int nch = dim <= 256 ? 1 : (dim <= 512 ? 2 : 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    M3L_CUDA(cudaFuncSetAttribute(assemble_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    M3L_CUDA(cudaFuncSetAttribute(assemble_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    M3L_CUDA(cudaFuncSetAttribute(assemble_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    configured = true;
+  }
+#define M3L_ASM_BWD(N)                                                                                          \
+  assemble_bwd_kernel<N><<<grid, wpb * 32, smem, st>>>((const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, \
+                                                       n_visible, (bf16*)dd_bf16, dmask_token, dadd0, tok_class, \
+                                                       n_classes, dadd1)
+  if (nch == 1) M3L_ASM_BWD(1); else if (nch == 2) M3L_ASM_BWD(2); else M3L_ASM_BWD(4);
+#undef M3L_ASM_BWD
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -777,7 +1170,7 @@ extern "C" int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, i
 
 extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
                             int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
-                            void* stream) {
+                            void* workspace, size_t workspace_bytes, void* stream) {
   M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
   if (batch * ncols == 0) return M3L_OK;
   PatchSrc ps = make_patch_src(src);
@@ -788,10 +1181,12 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
     configured = true;
   }
   const int rows = batch * ncols;
-  int grid = (rows + 7) / 8;
-  if (grid > device_sm_count() * 4) grid = device_sm_count() * 4;
+  int grid = (rows + 15) / 16;                       // two rows per warp: the per-row gather chain is latency bound
+  if (grid > device_sm_count() * 8) grid = device_sm_count() * 8;
+  M3L_REQUIRE(workspace != nullptr && workspace_bytes >= 256 + (size_t)grid * sizeof(float),
+              "mse_loss: workspace too small (%zu bytes)", workspace_bytes);
   mse_loss_kernel<<<grid, 256, ps.P * sizeof(float) * 8, (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, rows, pred, weight,
-                                                                   (bf16*)dpred_bf16, loss_acc);
+                                                                   (bf16*)dpred_bf16, loss_acc, workspace);
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -801,7 +1196,7 @@ extern "C" int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float*
   M3L_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "colsum: cols/ld must be multiples of 8");
   if (rows == 0) return M3L_OK;
   const int gx = (cols / 8 + 31) / 32;
-  int gy = (device_sm_count() * 4 + gx - 1) / gx;
+  int gy = (device_sm_count() * 2 + gx - 1) / gx;   // <= ~2 blocks per SM: few atomics per output address
   if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
   if (gy < 1) gy = 1;
   colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x_bf16, rows, cols, ld, out);

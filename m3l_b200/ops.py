@@ -17,6 +17,20 @@ GELU_FWD = 1
 GELU_BWD = 2
 
 
+_WS = {}
+_WS_BYTES = 1 << 20
+
+
+def workspace(device):
+    """Zero-initialised reduction scratch, one per device (kernels restore the leading counter to 0)."""
+    key = (device.type, device.index)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.zeros(_WS_BYTES, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -174,8 +188,9 @@ def decoder_assemble_bwd(dz, slots, batch, n_tokens, n_visible, *, dmask_token=N
     D = dz.shape[-1]
     if out is None:
         out = torch.empty((batch * n_visible, D), dtype=torch.bfloat16, device=dz.device)
+    n_classes = dadd0.shape[0] if dadd0 is not None else 0
     check(_lib.load().m3l_decoder_assemble_bwd(ptr(dz), ptr(slots), batch, n_tokens, D, n_visible, ptr(out),
-                                               ptr(dmask_token), ptr(dadd0), ptr(tok_class), ptr(dadd1),
+                                               ptr(dmask_token), ptr(dadd0), ptr(tok_class), n_classes, ptr(dadd1),
                                                current_stream()), "m3l_decoder_assemble_bwd")
     return out
 
@@ -191,7 +206,8 @@ def mse_loss(ps, batch, ncols, pred, weight, loss_acc, *, tok_idx=None, col0=0, 
         dpred = torch.empty(pred.shape, dtype=torch.bfloat16, device=pred.device)
     idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
     check(_lib.load().m3l_mse_loss(C.byref(ps), batch, ptr(tok_idx), idx_ld, col0, ncols, ptr(pred),
-                                   C.c_float(weight), ptr(dpred), ptr(loss_acc), current_stream()), "m3l_mse_loss")
+                                   C.c_float(weight), ptr(dpred), ptr(loss_acc), ptr(workspace(pred.device)),
+                                   C.c_size_t(_WS_BYTES), current_stream()), "m3l_mse_loss")
     return dpred
 
 
