@@ -51,7 +51,8 @@ typedef struct m3l_gemm_args {
   void* aux_out;      /* bf16 [m, ld_aux] or NULL */
   const void* aux_in; /* bf16 [m, ld_aux] or NULL */
   int32_t ld_aux;
-  float alpha;
+  float alpha;        /* must be 1 */
+  float* colsum_out;  /* fp32 [n] or NULL: += column sums of the bf16 output (fused bias gradient) */
 } m3l_gemm_args;
 
 int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);

@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int32), ("out_mode", C.c_int32),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p),
-        ("ld_aux", C.c_int32), ("alpha", C.c_float),
+        ("ld_aux", C.c_int32), ("alpha", C.c_float), ("colsum_out", C.c_void_p),
     ]
 
 

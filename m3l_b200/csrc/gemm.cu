@@ -232,11 +232,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool has_bias = (EPI != EPI_GELU_BWD && EPI != EPI_F32_RED) && p.bias != nullptr;
     const bool has_res = (EPI == EPI_BF16) && p.residual != nullptr;
     const int co_row = lane >> 3, co_chunk = lane & 7;
+    // fused column sums of the output (bias gradient): kept in registers while this CTA stays on
+    // the same N tile (the host sizes the grid as a multiple of tiles_n so that it always does)
+    const bool want_colsum = !kF32 && p.colsum_out != nullptr;
+    float csum[kF32 ? 1 : kRounds][8];
+    int csum_n0 = -1;
+    auto flush_colsum = [&]() {
+      if (csum_n0 < 0) return;
+#pragma unroll
+      for (int r = 0; r < (kF32 ? 1 : kRounds); ++r) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = csum[r][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const int gc = csum_n0 + span0 + r * kRoundCols + co_chunk * 8 + e;
+          if (co_row == 0 && gc < p.N) atomicAdd(p.colsum_out + gc, v);
+        }
+      }
+    };
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int t = item / p.splits;
       const int n0 = (t % tiles_n) * BN;
       const int m0 = (t / tiles_n) * BM;
+      if (want_colsum && active && n0 != csum_n0) {
+        flush_colsum();
+        csum_n0 = n0;
+#pragma unroll
+        for (int r = 0; r < (kF32 ? 1 : kRounds); ++r)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) csum[r][e] = 0.f;
+      }
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&bars->tmem_full[buf], acc_phase);
@@ -343,6 +370,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int grow = row_base + 4 * i + co_row;
             if (col_ok && grow < p.M) *reinterpret_cast<uint4*>(outp + (size_t)grow * p.ldo + gcol) = u[i];
           }
+          if (want_colsum) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (row_base + 4 * i + co_row < p.M) {
+                const float2 a = unpack_bf16x2(u[i].x), b = unpack_bf16x2(u[i].y), c = unpack_bf16x2(u[i].z),
+                             d = unpack_bf16x2(u[i].w);
+#pragma unroll
+                for (int rr = 0; rr < kRounds; ++rr)      // static register indexing
+                  if (rr == r) {
+                    csum[rr][0] += a.x; csum[rr][1] += a.y; csum[rr][2] += b.x; csum[rr][3] += b.y;
+                    csum[rr][4] += c.x; csum[rr][5] += c.y; csum[rr][6] += d.x; csum[rr][7] += d.y;
+                  }
+              }
+            }
+          }
           __syncwarp();
         } else {
           // ---------------- fp32 outputs: 32 columns per round ----------------
@@ -391,6 +433,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    if (want_colsum && active) flush_colsum();
   }
 
   tc_fence_before_sync();
@@ -479,8 +522,14 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
     s = make_tmap_2d_bf16(&plan->map_b, p.b, p.K, p.N, p.ldb, BK);
     if (s) return s;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.splits;
+  const int tiles_n = (p.N + bn - 1) / bn;
+  const int tiles = ((p.M + BM - 1) / BM) * tiles_n * p.splits;
   plan->grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  if (p.colsum_out != nullptr) {
+    M3L_REQUIRE(p.out_mode == 0, "gemm: colsum_out needs the bf16 output mode");
+    // keep every CTA on one N tile so the column sums stay in registers across its tiles
+    if (plan->grid > tiles_n) plan->grid = (plan->grid / tiles_n) * tiles_n;
+  }
   return M3L_OK;
 }
 
@@ -508,7 +557,7 @@ extern "C" int m3l_gemm_bf16(const m3l_gemm_args* a, void* stream) {
   g.out = a->out; g.ldo = a->ldo; g.out_mode = a->out_mode;
   g.bias = a->bias; g.residual = (const m3l::bf16*)a->residual; g.ldr = a->ldr;
   g.act = a->act; g.aux_out = (m3l::bf16*)a->aux_out; g.aux_in = (const m3l::bf16*)a->aux_in;
-  g.ld_aux = a->ld_aux; g.alpha = a->alpha;
+  g.ld_aux = a->ld_aux; g.alpha = a->alpha; g.colsum_out = a->colsum_out;
   m3l::GemmPlan plan;
   int s = m3l::gemm_make_plan(&plan, g, a->bn);
   if (s) return s;

@@ -25,6 +25,7 @@ struct GemmArgs {
   const bf16* aux_in = nullptr;
   int ld_aux = 0;
   float alpha = 1.0f;
+  float* colsum_out = nullptr;  // [N] fp32: += column sums of the (bf16) output, e.g. the bias gradient
 };
 
 struct GemmPlan {

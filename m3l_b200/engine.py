@@ -102,8 +102,8 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
         x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h = saved[l]
         # ---- feed-forward branch: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
         wgrad(dx, h, G(pf + ".net.4.weight"))
-        dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre)
-        ops.colsum(dpre, G(pf + ".net.1.bias"))
+        dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre,
+                        colsum_out=G(pf + ".net.1.bias"))
         wgrad(dpre, xn2, G(pf + ".net.1.weight"))
         dxn2 = ops.gemm(dpre, A.bf_t(pf + ".net.1.weight"))
         dx_mid = ops.layernorm_bwd(dxn2, x_mid, st2, A.f32(pf + ".net.0.weight"), dgamma=G(pf + ".net.0.weight"),

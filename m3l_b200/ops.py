@@ -41,7 +41,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
          out_dtype: torch.dtype = torch.bfloat16, accumulate: bool = False, splits: int = 1, bn: int = 0,
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None,
-         alpha: float = 1.0) -> torch.Tensor:
+         alpha: float = 1.0, colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[m, n] = epilogue(alpha * sum_k A[m, k] B[n, k]).
 
     mn_major=False: a is [M, K], b is [N, K] (nn.Linear forward: x @ W.T).
@@ -80,6 +80,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
     aux = aux_out if aux_out is not None else aux_in
     args.ld_aux = aux.stride(0) if aux is not None else 0
     args.alpha = alpha
+    args.colsum_out = ptr(colsum_out)
     check(_lib.load().m3l_gemm_bf16(C.byref(args), current_stream()), "m3l_gemm_bf16")
     return out
 

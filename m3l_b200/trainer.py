@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import engine, ops
+from . import dp, engine, ops
 from ._lib import M3LError
 
 
@@ -67,9 +67,7 @@ class FusedTrainer:
     def _plan(self, geo):
         model, A = self.model, self.model.arena
         live = model.live_param_names(geo, True)
-        dec_names = [k for k in live if k.startswith(("to_pixels", "to_tactiles", "decoder.", "mask_token",
-                                                      "decoder_modality_embedding", "enc_to_dec", "decoder_pos_emb"))]
-        enc_names = [k for k in live if k not in dec_names]
+        dec_names, enc_names = dp.split_buckets(live)
         return live, A.ranges(live), A.ranges(dec_names), A.ranges(enc_names)
 
     def _phase_a(self, xs, noise, geo, box):
@@ -96,8 +94,7 @@ class FusedTrainer:
     def _allreduce(self, ranges, after_event):
         self.comm_stream.wait_event(after_event)
         with torch.cuda.stream(self.comm_stream):
-            for s, e in ranges:
-                torch.distributed.all_reduce(self.gflat[s:e], op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            dp.allreduce_ranges(self.gflat, ranges, group=self.pg)
 
     # ------------------------------------------------------------------------------------
     def step(self, x, noise=None, use_vision=True, use_tactile=True):

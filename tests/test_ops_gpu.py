@@ -59,10 +59,16 @@ def test_gemm_epilogues(ops):
     pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=pre)
     assert rel_err(pre, z + bias) < 1e-2 and rel_err(h, F.gelu(z + bias)) < 1e-2
-    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre)
+    cs = torch.ones(N, device=DEV)
+    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre, colsum_out=cs)
     zz = pre.float().requires_grad_(True)
     F.gelu(zz).sum().backward()
     assert rel_err(g, z * zz.grad) < 1e-2
+    assert rel_err(cs, 1 + g.float().sum(0)) < 1e-4  # fused bias gradient = column sums of the bf16 output
+    big_a = torch.randn(40000, K, device=DEV).bfloat16()
+    cs2 = torch.zeros(N, device=DEV)
+    g2 = ops.gemm(big_a, b, colsum_out=cs2, bn=128)
+    assert rel_err(cs2, g2.float().sum(0)) < 1e-4
     f32 = ops.gemm(a, b, bias=bias, out_dtype=torch.float32)
     assert rel_err(f32, z + bias) < 1e-5
     inplace = res.clone()
