@@ -52,6 +52,45 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, gview: torch.Tensor) -> None:
     ops.gemm(dy, x, mn_major=True, out=gview, accumulate=True, splits=splits, bn=bn)
 
 
+_SIDE_STREAMS: Dict = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """Second stream for the weight-gradient GEMMs: they only feed the gradient arena, so they run
+    beside the dgrad chain (the critical path) instead of inside it.  Forks/joins are event based and
+    are captured as parallel branches of the CUDA graph."""
+    key = (device.type, device.index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
+class WgradFork:
+    """Runs wgrad GEMMs on the side stream; join() before their operands may be freed or reused."""
+
+    def __init__(self, device, enabled: bool = True):
+        self.enabled = enabled
+        self.main = torch.cuda.current_stream(device)
+        self.side = side_stream(device) if enabled else None
+        self.dirty = False
+
+    def wgrad(self, dy, x, gview):
+        if not self.enabled:
+            wgrad(dy, x, gview)
+            return
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            wgrad(dy, x, gview)
+        self.dirty = True
+
+    def join(self):
+        if self.enabled and self.dirty:
+            self.main.wait_stream(self.side)
+            self.dirty = False
+
+
 class GradView:
     """Accessor of per-parameter views into a flat fp32 gradient buffer laid out like the arena."""
 
@@ -97,26 +136,29 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
     The producer of dx (the final-LayerNorm backward) must already have accumulated its column sums
     into G(last_ff_bias(spec)) (dx_colsum= of ops.layernorm_bwd)."""
     scale = spec.dim_head ** -0.5
+    fork = WgradFork(A.device)
     for l in reversed(range(spec.depth)):
         pa, pf = f"{spec.prefix}.layers.{l}.0", f"{spec.prefix}.layers.{l}.1"
         x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h = saved[l]
         # ---- feed-forward branch: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
-        wgrad(dx, h, G(pf + ".net.4.weight"))
+        fork.wgrad(dx, h, G(pf + ".net.4.weight"))
         dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre,
                         colsum_out=G(pf + ".net.1.bias"))
-        wgrad(dpre, xn2, G(pf + ".net.1.weight"))
+        fork.wgrad(dpre, xn2, G(pf + ".net.1.weight"))
         dxn2 = ops.gemm(dpre, A.bf_t(pf + ".net.1.weight"))
         dx_mid = ops.layernorm_bwd(dxn2, x_mid, st2, A.f32(pf + ".net.0.weight"), dgamma=G(pf + ".net.0.weight"),
                                    dbeta=G(pf + ".net.0.bias"), skip=dx, dx_colsum=G(pa + ".to_out.0.bias"))
         # ---- attention branch: x_mid = x + Wo attn(Wqkv LN1(x)) + bo
-        wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
+        fork.wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
         do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"))
         dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale)
-        wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
+        fork.wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
         dxn1 = ops.gemm(dqkv, A.bf_t(pa + ".to_qkv.weight"))
         prev_bias = G(f"{spec.prefix}.layers.{l - 1}.1.net.4.bias") if l > 0 else None
-        dx = ops.layernorm_bwd(dxn1, x, st1, A.f32(pa + ".norm.weight"), dgamma=G(pa + ".norm.weight"),
-                               dbeta=G(pa + ".norm.bias"), skip=dx_mid, dx_colsum=prev_bias)
+        dx_in = ops.layernorm_bwd(dxn1, x, st1, A.f32(pa + ".norm.weight"), dgamma=G(pa + ".norm.weight"),
+                                  dbeta=G(pa + ".norm.bias"), skip=dx_mid, dx_colsum=prev_bias)
+        fork.join()          # this layer's wgrad operands (dx, dpre, dx_mid, dqkv) die below
+        dx = dx_in
     return dx
 
 
