@@ -46,8 +46,8 @@ typedef struct m3l_gemm_args {
   const float* bias;  /* [n] fp32 or NULL */
   const void* residual; /* bf16 [m, ldr] or NULL; added after the activation (may alias out) */
   int32_t ldr;
-  int32_t act;        /* 0 none; 1 exact-erf GELU (pre-activation stored to aux_out if non-NULL);
-                         2 multiply by GELU'(aux_in[m, n]) (backward of 1) */
+  int32_t act;        /* 0 none; 1 exact-erf GELU (its derivative GELU'(pre-activation) stored to
+                         aux_out if non-NULL); 2 multiply by aux_in[m, n] (backward of 1) */
   void* aux_out;      /* bf16 [m, ld_aux] or NULL */
   const void* aux_in; /* bf16 [m, ld_aux] or NULL */
   int32_t ld_aux;

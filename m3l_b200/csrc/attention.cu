@@ -618,9 +618,15 @@ attn_small_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, floa
       for (int j = 0; j < kSmallMaxN; ++j) {
         float acc = 0.f;
         if (j < n) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-          for (int d = 0; d < kDh; ++d) acc = fmaf(q[d], sK[j * kSmallPad + d], acc);
-          acc *= scale;
+          for (int d = 0; d < kDh; d += 4) {
+            a0 = fmaf(q[d], sK[j * kSmallPad + d], a0);
+            a1 = fmaf(q[d + 1], sK[j * kSmallPad + d + 1], a1);
+            a2 = fmaf(q[d + 2], sK[j * kSmallPad + d + 2], a2);
+            a3 = fmaf(q[d + 3], sK[j * kSmallPad + d + 3], a3);
+          }
+          acc = ((a0 + a1) + (a2 + a3)) * scale;
           mx = fmaxf(mx, acc);
         }
         sc[j] = acc;
@@ -688,11 +694,15 @@ attn_small_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
       for (int j = 0; j < kSmallMaxN; ++j) {
         float s = 0.f, t = 0.f;
         if (j < n) {
+          float s1 = 0.f, t1 = 0.f;
 #pragma unroll
-          for (int d = 0; d < kDh; ++d) {
+          for (int d = 0; d < kDh; d += 2) {
             s = fmaf(sQ[i * kSmallPad + d], sK[j * kSmallPad + d], s);
             t = fmaf(sDO[i * kSmallPad + d], sV[j * kSmallPad + d], t);
+            s1 = fmaf(sQ[i * kSmallPad + d + 1], sK[j * kSmallPad + d + 1], s1);
+            t1 = fmaf(sDO[i * kSmallPad + d + 1], sV[j * kSmallPad + d + 1], t1);
           }
+          s += s1; t += t1;
           p[j] = __expf(s * scale - li);
           dp[j] = t;
           delta = fmaf(p[j], t, delta);

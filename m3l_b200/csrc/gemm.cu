@@ -60,8 +60,8 @@ M3L_DEVINL void red_add_v4(float* addr, float4 v) {
 // Epilogue flavours (compile time, so the inner loops carry no mode branches):
 enum : int {
   EPI_BF16 = 0,      // out bf16 = acc (+ bias) (+ residual)
-  EPI_GELU_FWD = 1,  // aux_out bf16 = acc + bias ; out bf16 = GELU(acc + bias)
-  EPI_GELU_BWD = 2,  // out bf16 = acc * GELU'(aux_in)
+  EPI_GELU_FWD = 1,  // out bf16 = GELU(acc + bias) ; aux_out bf16 = GELU'(acc + bias)
+  EPI_GELU_BWD = 2,  // out bf16 = acc * aux_in   (aux_in = the stored GELU')
   EPI_F32 = 3,       // out fp32 = acc (+ bias)
   EPI_F32_RED = 4,   // out fp32 += acc  (red.global.add, split-K)
 };
@@ -318,10 +318,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           uint32_t w[32];
           if constexpr (EPI == EPI_GELU_FWD) {
+            // out = GELU(v); aux_out = GELU'(v) (bf16) so that the backward pass is a plain multiply
+            // and never evaluates erf again (the exp(-v^2/2) is shared between the two here)
             if (p.aux_out != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              for (int j = 0; j < 32; ++j) {
+                const float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+                const GeluParts g0 = gelu_parts(x0), g1 = gelu_parts(x1);
+                w[j] = pack_bf16x2(fmaf(x0, g0.pdf, g0.cdf), fmaf(x1, g1.pdf, g1.cdf));
+                v[2 * j] = __float_as_uint(x0 * g0.cdf);
+                v[2 * j + 1] = __float_as_uint(x1 * g1.cdf);
+              }
               stg_store_row(stg, lane, w);
               __syncwarp();
               uint4 u[8];
@@ -334,9 +341,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   *reinterpret_cast<uint4*>(p.aux_out + (size_t)grow * p.ld_aux + gcol) = u[i];
               }
               __syncwarp();
-            }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+              for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+            }
           }
           if (EPI == EPI_GELU_BWD || has_res) {
 #pragma unroll
@@ -347,9 +355,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float2 s2 = unpack_bf16x2(w[j]);
-              if constexpr (EPI == EPI_GELU_BWD) {
-                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) * gelu_erf_grad(s2.x));
-                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) * gelu_erf_grad(s2.y));
+              if constexpr (EPI == EPI_GELU_BWD) {   // aux_in holds GELU'(pre-activation)
+                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) * s2.x);
+                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) * s2.y);
               } else {
                 v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + s2.x);
                 v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + s2.y);

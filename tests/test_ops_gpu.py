@@ -56,14 +56,16 @@ def test_gemm_epilogues(ops):
     z = a.float() @ b.float().T
     out = ops.gemm(a, b, bias=bias, residual=res)
     assert rel_err(out, z + bias + res.float()) < 1e-2
-    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
-    h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=pre)
-    assert rel_err(pre, z + bias) < 1e-2 and rel_err(h, F.gelu(z + bias)) < 1e-2
-    cs = torch.ones(N, device=DEV)
-    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=pre, colsum_out=cs)
-    zz = pre.float().requires_grad_(True)
+    dgelu = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=dgelu)
+    zz = (z + bias).requires_grad_(True)
     F.gelu(zz).sum().backward()
-    assert rel_err(g, z * zz.grad) < 1e-2
+    assert rel_err(dgelu, zz.grad) < 1e-2 and rel_err(h, F.gelu(z + bias)) < 1e-2   # aux = GELU'(pre-activation)
+    h2 = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD)
+    assert torch.equal(h2, h)
+    cs = torch.ones(N, device=DEV)
+    g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=dgelu, colsum_out=cs)
+    assert rel_err(g, z * dgelu.float()) < 1e-2
     assert rel_err(cs, 1 + g.float().sum(0)) < 1e-4  # fused bias gradient = column sums of the bf16 output
     big_a = torch.randn(40000, K, device=DEV).bfloat16()
     cs2 = torch.zeros(N, device=DEV)
