@@ -110,6 +110,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();      // prologue above overlapped the predecessor kernel; global memory from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
@@ -365,6 +367,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();      // prologue above overlapped the predecessor kernel; global memory from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
@@ -590,6 +594,8 @@ M3L_DEVINL void small_load_rows(const bf16* g, int ld, int n, float* dst, int la
 __global__ void __launch_bounds__(256)
 attn_small_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int n,
                       int heads, int inner, int num_items, float scale) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm_small[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float* sK = sm_small + (size_t)warp * 2 * kSmallMaxN * kSmallPad;
@@ -665,6 +671,8 @@ attn_small_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, floa
 __global__ void __launch_bounds__(128)
 attn_small_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
                       bf16* __restrict__ dqkv, int n, int heads, int inner, int num_items, float scale) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm_small[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   constexpr int kTile = kSmallMaxN * kSmallPad;
@@ -790,8 +798,8 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
       configured = true;
     }
     const int grid = std::min((items + wpb - 1) / wpb, device_sm_count() * 4);
-    attn_small_fwd_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>((const bf16*)qkv_bf16, (bf16*)out_bf16, lse, n,
-                                                                         heads, inner, items, scale);
+    M3L_CUDA(launch_kernel(attn_small_fwd_kernel, dim3(grid), dim3(wpb * 32), smem, (cudaStream_t)stream, (const bf16*)qkv_bf16, (bf16*)out_bf16, lse, n,
+                                                                         heads, inner, items, scale));
     M3L_CUDA(cudaGetLastError());
     return M3L_OK;
   }
@@ -821,7 +829,7 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
     configured = true;
   }
   const int grid = std::min(p.num_items, device_sm_count());
-  attn_fwd_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(map_q, map_kv, p);
+  M3L_CUDA(launch_kernel(attn_fwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_q, map_kv, p));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -843,8 +851,8 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
       configured = true;
     }
     const int grid = std::min((items + wpb - 1) / wpb, device_sm_count() * 8);
-    attn_small_bwd_kernel<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>((const bf16*)qkv_bf16, (const bf16*)dout_bf16, lse,
-                                                                         (bf16*)dqkv_bf16, n, heads, inner, items, scale);
+    M3L_CUDA(launch_kernel(attn_small_bwd_kernel, dim3(grid), dim3(wpb * 32), smem, (cudaStream_t)stream, (const bf16*)qkv_bf16, (const bf16*)dout_bf16, lse,
+                                                                         (bf16*)dqkv_bf16, n, heads, inner, items, scale));
     M3L_CUDA(cudaGetLastError());
     return M3L_OK;
   }
@@ -873,7 +881,7 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
     configured = true;
   }
   const int grid = std::min(p.num_items, device_sm_count());
-  attn_bwd_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(map_q, map_kv, map_do, p);
+  M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_q, map_kv, map_do, p));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -42,31 +43,41 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                      uint64_t ld, uint32_t box_rows) {
+static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize,
+                        uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return M3L_ERR_CUDA;
   }
   M3L_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map base %p not 16-byte aligned", base);
-  M3L_REQUIRE((ld * 2) % 16 == 0, "tensor map leading dimension %llu not a multiple of 8 elements",
+  M3L_REQUIRE((ld * esize) % 16 == 0, "tensor map leading dimension %llu not a multiple of 16 bytes",
               (unsigned long long)ld);
   M3L_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows %u out of range", box_rows);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t gstr[1] = {ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box_rows=%u) failed: %d",
+    set_last_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box_rows=%u esize=%d) failed: %d",
                    (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
-                   box_rows, (int)r);
+                   box_rows, esize, (int)r);
     return M3L_ERR_CUDA;
   }
   return M3L_OK;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, ld, box_rows);
+}
+
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, ld, box_rows);
 }
 
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
@@ -92,6 +103,15 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
     return M3L_ERR_CUDA;
   }
   return M3L_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3L_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int device_sm_count() {

@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 namespace m3l {
 
 typedef __nv_bfloat16 bf16;
@@ -46,6 +48,39 @@ int check_cuda(cudaError_t e, const char* what);
       return ::m3l::M3L_ERR_INVALID;                    \
     }                                                   \
   } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the step is launched with the
+// programmatic-stream-serialisation attribute (launch_kernel below) and starts with
+//     <prologue that touches no global memory: barrier init, TMEM alloc, descriptor prefetch>
+//     pdl_wait();      // predecessor grid complete, its writes visible
+//     pdl_trigger();   // successor grid may start ITS prologue as SM resources free up
+// so launch latency and prologues of consecutive kernels overlap the predecessor's tail, also
+// inside a captured CUDA graph (programmatic edges).  Every kernel launched this way must
+// execute pdl_wait() before its first global-memory access (reads AND writes): completion of
+// grid N then implies completion of grid N-1, which keeps the stream order transitive.
+// M3L_PDL=0 in the environment launches everything fully serialised.
+// ---------------------------------------------------------------------------------------
+M3L_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+M3L_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 // ---------------------------------------------------------------------------------------
 // small utilities
@@ -149,15 +184,24 @@ M3L_DEVINL uint64_t global_timer_ns() {
   return t;
 }
 // Parity wait with a watchdog: a pipeline bug must trap (-> CUDA error on the host) instead of
-// hanging the GPU box.  The watchdog only runs on the slow path.
+// hanging the GPU box.  The watchdog reads %globaltimer only once every 4096 failed polls: a
+// timer read per poll (the first version) put a slow special-register access on the wake-up path
+// of EVERY barrier hand-off and cost ~2 us per GEMM tile (measured with all memory traffic and
+// 15/16 of the MMAs removed, tools/gemm_probe.py).
 M3L_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) {  // 4 s
-      printf("m3l: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
-             (int)threadIdx.x);
-      __trap();
+    if ((++polls & 4095u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 4000000000ull) {  // 4 s
+        printf("m3l: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
+               (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -190,6 +234,41 @@ M3L_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
         "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// TMA stores (smem -> global, bulk async-group completion).  The smem tile must have been made
+// visible to the async proxy (fence_proxy_async_smem) before the issuing thread calls these.
+M3L_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src_u32, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src_u32), "r"(c0), "r"(c1)
+               : "memory");
+}
+// global[tile] += smem tile (element type taken from the tensor map; fp32 here)
+M3L_DEVINL void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src_u32, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src_u32), "r"(c0), "r"(c1)
+               : "memory");
+}
+M3L_DEVINL void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their smem source
+template <int N>
+M3L_DEVINL void tma_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// at most N of this thread's bulk groups may still be incomplete (writes not yet performed)
+template <int N>
+M3L_DEVINL void tma_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+M3L_DEVINL void tma_load_2d_u32(uint32_t smem_dst_u32, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst_u32), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
@@ -298,6 +377,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
 // (128 B, SWIZZLE_128B) x box_rows rows.  Out-of-bounds elements are zero-filled.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows);
+// same for fp32: box = 32 columns (128 B, SWIZZLE_128B) x box_rows rows
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_rows);
 // 3-D bf16 tensor [d2, d1, d0 (contiguous)] with strides (elements) s2, s1; box = 64 x box1 x 1.
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t s1, uint64_t s2, uint32_t box1);

@@ -22,6 +22,8 @@ __global__ void mask_indices_kernel(const float* __restrict__ noise, int n_total
                                     int64_t* __restrict__ unmasked, int n_unmasked_total,
                                     int32_t* __restrict__ slot_of_token, int32_t* __restrict__ unmasked_i32,
                                     int32_t* __restrict__ masked_row_of_token, int n_masked_first, int batch) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float keys[];
   const int b = blockIdx.x;
   const int s = blockIdx.y;
@@ -172,6 +174,8 @@ M3L_DEVINL float block_sum(float v, float* red) {
 __global__ void patch_ln_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0,
                                 int ncols, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 bf16* __restrict__ out, bf16* __restrict__ xhat_out, float eps) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float patch[];   // P floats
   __shared__ float red[32];
   const int r = blockIdx.x;
@@ -255,6 +259,8 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, int M, int D, const float* __res
                      float* __restrict__ stats, const int32_t* __restrict__ dst_row,
                      const float* __restrict__ add0, const int32_t* __restrict__ add0_row,
                      const float* __restrict__ add1, const int32_t* __restrict__ add1_row) {
+  pdl_wait();
+  pdl_trigger();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
@@ -348,6 +354,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ sr
                      const float* __restrict__ gamma, const bf16* __restrict__ skip,
                      TOut* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float spart[];  // [warps][3][D]
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -477,6 +485,8 @@ ln_fwd_pipe_kernel(const bf16* __restrict__ x, int M, int D, const float* __rest
                    const int32_t* __restrict__ dst_row, const float* __restrict__ add0,
                    const int32_t* __restrict__ add0_row, const float* __restrict__ add1,
                    const int32_t* __restrict__ add1_row) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t ring_raw[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -573,6 +583,8 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_
                    const float* __restrict__ stats, int M, int D, const float* __restrict__ gamma,
                    const bf16* __restrict__ skip, bf16* __restrict__ dx, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t ring_raw[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -690,6 +702,8 @@ __global__ void assemble_fwd_kernel(const bf16* __restrict__ d, int nv, const fl
                                     const int32_t* __restrict__ slot_of_token, int B, int n, int D,
                                     const float* __restrict__ add0, const int32_t* __restrict__ tok_class,
                                     const float* __restrict__ add1, bf16* __restrict__ z) {
+  pdl_wait();
+  pdl_trigger();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;
@@ -730,6 +744,8 @@ assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slo
                     int B, int n, int D, int nv, bf16* __restrict__ dd,
                     float* __restrict__ dmask_token, float* __restrict__ dadd0,
                     const int32_t* __restrict__ tok_class, int n_classes, float* __restrict__ dadd1) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sred[];   // [warps][(1 + kAsmClasses)][D]
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -809,6 +825,8 @@ assemble_bwd_kernel(const bf16* __restrict__ dz, const int32_t* __restrict__ slo
 __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, int D,
                                     const int32_t* __restrict__ row_class, float* __restrict__ dclass,
                                     const int32_t* __restrict__ row_pos, float* __restrict__ dpos) {
+  pdl_wait();
+  pdl_trigger();
   // one block per visible slot j (class is a function of j only; position varies per sample)
   const int j = blockIdx.x;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
@@ -831,6 +849,8 @@ __global__ void __launch_bounds__(256)
 mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols, int rows,
                 const float* __restrict__ pred, float weight, bf16* __restrict__ dpred,
                 float* __restrict__ loss_acc, void* ws) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float patches[];   // [warps][P] floats, destination order (p1, p2, c)
   __shared__ float red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -885,6 +905,8 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
 // 7. column sums of a bf16 matrix: out[n] += sum_m x[m, n]   (bias gradients)
 // ------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   // block: 32 x 8 threads; each thread owns 8 consecutive columns, 4 rows in flight
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   __shared__ float part[8][32][8];
@@ -931,6 +953,8 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, 
 // LayerNorm(P) parameter gradients of the patch embedding: dgamma[p] += sum_r dA[r,p]*xhat[r,p]; dbeta[p] += sum_r dA[r,p]
 __global__ void ln_param_grad_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ xhat, int M, int P,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
+  pdl_trigger();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
@@ -986,9 +1010,9 @@ extern "C" int m3l_mask_indices(const float* noise, int batch, int n_total, cons
   M3L_REQUIRE(maxlen <= 8192, "mask_indices: segment longer than 8192");
   dim3 grid(batch, segs->count);
   const int threads = maxlen <= 64 ? 64 : (maxlen <= 128 ? 128 : 256);
-  mask_indices_kernel<<<grid, threads, maxlen * sizeof(float), (cudaStream_t)stream>>>(
+  M3L_CUDA(launch_kernel(mask_indices_kernel, dim3(grid), dim3(threads), maxlen * sizeof(float), (cudaStream_t)stream, 
       noise, n_total, *segs, masked, nm, unmasked, nu, slot_of_token, unmasked_i32, masked_row_of_token,
-      n_masked_first, batch);
+      n_masked_first, batch));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1000,8 +1024,8 @@ extern "C" int m3l_patch_layernorm(const m3l_patch_source* src, int batch, const
   if (batch * ncols == 0) return M3L_OK;
   PatchSrc ps = make_patch_src(src);
   M3L_REQUIRE(ps.P * sizeof(float) <= 48 * 1024, "patch_layernorm: patch dim %d too large", ps.P);
-  patch_ln_kernel<<<batch * ncols, 128, ps.P * sizeof(float), (cudaStream_t)stream>>>(
-      ps, tok_idx, idx_ld, col0, ncols, gamma, beta, (bf16*)out_bf16, (bf16*)xhat_bf16, eps);
+  M3L_CUDA(launch_kernel(patch_ln_kernel, dim3(batch * ncols), dim3(128), ps.P * sizeof(float), (cudaStream_t)stream, 
+      ps, tok_idx, idx_ld, col0, ncols, gamma, beta, (bf16*)out_bf16, (bf16*)xhat_bf16, eps));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1021,17 +1045,17 @@ extern "C" int m3l_layernorm_fwd(const void* x, int x_fp32, int rows, int dim, c
   const int nch = dim <= 256 ? 1 : (dim <= 512 ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define M3L_LN_FWD(T, N)                                                                                   \
-  layernorm_fwd_kernel<T, N><<<grid, wpb * 32, 0, st>>>((const T*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, \
-                                                        stats, dst_row, add0, add0_row, add1, add1_row)
+  M3L_CUDA(launch_kernel(layernorm_fwd_kernel<T, N>, dim3(grid), dim3(wpb * 32), 0, st, (const T*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16, \
+                                                        stats, dst_row, add0, add0_row, add1, add1_row))
   if (!x_fp32 && nch <= 2) {
     // bf16 fast path: 4-deep warp-private cp.async ring
     const size_t ring = (size_t)wpb * 4 * nch * 512;
     if (nch == 1)
-      ln_fwd_pipe_kernel<1, 4><<<grid, wpb * 32, ring, st>>>((const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
-                                                            stats, dst_row, add0, add0_row, add1, add1_row);
+      M3L_CUDA(launch_kernel(ln_fwd_pipe_kernel<1, 4>, dim3(grid), dim3(wpb * 32), ring, st, (const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
+                                                            stats, dst_row, add0, add0_row, add1, add1_row));
     else
-      ln_fwd_pipe_kernel<2, 4><<<grid, wpb * 32, ring, st>>>((const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
-                                                            stats, dst_row, add0, add0_row, add1, add1_row);
+      M3L_CUDA(launch_kernel(ln_fwd_pipe_kernel<2, 4>, dim3(grid), dim3(wpb * 32), ring, st, (const bf16*)x, rows, dim, gamma, beta, eps, (bf16*)y_bf16,
+                                                            stats, dst_row, add0, add0_row, add1, add1_row));
   } else if (x_fp32) {
     if (nch == 1) M3L_LN_FWD(float, 1); else if (nch == 2) M3L_LN_FWD(float, 2); else M3L_LN_FWD(float, 4);
   } else {
@@ -1053,11 +1077,11 @@ static int launch_ln_bwd(int nch, int grid, size_t smem, cudaStream_t st, const 
     configured = true;
   }
   if (nch == 1)
-    layernorm_bwd_kernel<TIn, TOut, 1><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+    M3L_CUDA(launch_kernel(layernorm_bwd_kernel<TIn, TOut, 1>, dim3(grid), dim3(256), smem, st, dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum));
   else if (nch == 2)
-    layernorm_bwd_kernel<TIn, TOut, 2><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+    M3L_CUDA(launch_kernel(layernorm_bwd_kernel<TIn, TOut, 2>, dim3(grid), dim3(256), smem, st, dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum));
   else
-    layernorm_bwd_kernel<TIn, TOut, 4><<<grid, 256, smem, st>>>(dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum);
+    M3L_CUDA(launch_kernel(layernorm_bwd_kernel<TIn, TOut, 4>, dim3(grid), dim3(256), smem, st, dy, src_row, x, stats, rows, dim, gamma, skip, dx, dgamma, dbeta, dx_colsum));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1092,9 +1116,9 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
       configured = true;
     }
     if (nch == 1)
-      ln_bwd_pipe_kernel<1, kSt><<<grid, 256, total, st>>>(dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+      M3L_CUDA(launch_kernel(ln_bwd_pipe_kernel<1, kSt>, dim3(grid), dim3(256), total, st, dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum));
     else
-      ln_bwd_pipe_kernel<2, kSt><<<grid, 256, total, st>>>(dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum);
+      M3L_CUDA(launch_kernel(ln_bwd_pipe_kernel<2, kSt>, dim3(grid), dim3(256), total, st, dy, src_row, (const bf16*)x, stats, rows, dim, gamma, skip, (bf16*)dx, dgamma, dbeta, dx_colsum));
     M3L_CUDA(cudaGetLastError());
     return M3L_OK;
   }
@@ -1116,9 +1140,9 @@ extern "C" int m3l_decoder_assemble_fwd(const void* d_bf16, int n_visible, const
   M3L_REQUIRE(add0 == nullptr || tok_class != nullptr, "decoder_assemble_fwd: add0 needs tok_class");
   if (batch * n_tokens == 0) return M3L_OK;
   const int wpb = 8;
-  assemble_fwd_kernel<<<ln_grid(batch * n_tokens, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+  M3L_CUDA(launch_kernel(assemble_fwd_kernel, dim3(ln_grid(batch * n_tokens, wpb)), dim3(wpb * 32), 0, (cudaStream_t)stream, 
       (const bf16*)d_bf16, n_visible, mask_token, slot_of_token, batch, n_tokens, dim, add0, tok_class, add1,
-      (bf16*)z_bf16);
+      (bf16*)z_bf16));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1148,9 +1172,9 @@ extern "C" int m3l_decoder_assemble_bwd(const void* dz_bf16, const int32_t* slot
     configured = true;
   }
 #define M3L_ASM_BWD(N)                                                                                          \
-  assemble_bwd_kernel<N><<<grid, wpb * 32, smem, st>>>((const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, \
+  M3L_CUDA(launch_kernel(assemble_bwd_kernel<N>, dim3(grid), dim3(wpb * 32), smem, st, (const bf16*)dz_bf16, slot_of_token, batch, n_tokens, dim, \
                                                        n_visible, (bf16*)dd_bf16, dmask_token, dadd0, tok_class, \
-                                                       n_classes, dadd1)
+                                                       n_classes, dadd1))
   if (nch == 1) M3L_ASM_BWD(1); else if (nch == 2) M3L_ASM_BWD(2); else M3L_ASM_BWD(4);
 #undef M3L_ASM_BWD
   M3L_CUDA(cudaGetLastError());
@@ -1162,8 +1186,8 @@ extern "C" int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, i
                                 void* stream) {
   M3L_REQUIRE(dx_bf16, "rowclass_sum: null pointer");
   if (batch * n_visible == 0) return M3L_OK;
-  rowclass_sum_kernel<<<n_visible, 256, 0, (cudaStream_t)stream>>>((const bf16*)dx_bf16, batch, n_visible, dim,
-                                                                   slot_class, dclass, row_pos, dpos);
+  M3L_CUDA(launch_kernel(rowclass_sum_kernel, dim3(n_visible), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dx_bf16, batch, n_visible, dim,
+                                                                   slot_class, dclass, row_pos, dpos));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1185,8 +1209,8 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
   if (grid > device_sm_count() * 8) grid = device_sm_count() * 8;
   M3L_REQUIRE(workspace != nullptr && workspace_bytes >= 256 + (size_t)grid * sizeof(float),
               "mse_loss: workspace too small (%zu bytes)", workspace_bytes);
-  mse_loss_kernel<<<grid, 256, ps.P * sizeof(float) * 8, (cudaStream_t)stream>>>(ps, tok_idx, idx_ld, col0, ncols, rows, pred, weight,
-                                                                   (bf16*)dpred_bf16, loss_acc, workspace);
+  M3L_CUDA(launch_kernel(mse_loss_kernel, dim3(grid), dim3(256), ps.P * sizeof(float) * 8, (cudaStream_t)stream, ps, tok_idx, idx_ld, col0, ncols, rows, pred, weight,
+                                                                   (bf16*)dpred_bf16, loss_acc, workspace));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1199,7 +1223,7 @@ extern "C" int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float*
   int gy = (device_sm_count() * 2 + gx - 1) / gx;   // <= ~2 blocks per SM: few atomics per output address
   if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)x_bf16, rows, cols, ld, out);
+  M3L_CUDA(launch_kernel(colsum_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, (const bf16*)x_bf16, rows, cols, ld, out));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1211,8 +1235,8 @@ extern "C" int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int
   const int gx = (dim + 127) / 128;
   int gy = (rows + 127) / 128;
   if (gy > 64) gy = 64;
-  ln_param_grad_kernel<<<dim3(gx, gy), 128, 0, (cudaStream_t)stream>>>((const bf16*)da_bf16, (const bf16*)xhat_bf16,
-                                                                       rows, dim, dgamma, dbeta);
+  M3L_CUDA(launch_kernel(ln_param_grad_kernel, dim3(dim3(gx, gy)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)da_bf16, (const bf16*)xhat_bf16,
+                                                                       rows, dim, dgamma, dbeta));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

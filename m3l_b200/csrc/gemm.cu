@@ -1,6 +1,6 @@
 // m3l_b200 — persistent warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA (sm_100a).
 //
-//   C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] )
 //
 // This one kernel serves every dense contraction of the VTMAE step that the reference hands to
 // cuBLAS through nn.Linear (vit_pytorch Attention.to_qkv / to_out / FeedForward.net, the patch
@@ -9,16 +9,28 @@
 //   * forward and dgrad: both operands K-major (activations [M,K]; weights [N,K], or the bf16
 //     transposed shadow copy of the weight for dgrad);
 //   * wgrad dW[n,k] = sum_m dY[m,n] X[m,k]: both operands MN-major (the contraction runs over
-//     the token rows), split-K over the token dimension, fp32 vector red.add into the grad arena.
+//     the token rows), split-K over the token dimension, fp32 TMA reduce-add into the grad arena.
 //
-// Structure (one CTA per SM, persistent over a static round-robin tile schedule):
+// Structure (one CTA per SM, persistent over a static tile schedule):
 //   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (mbarrier tx)
 //   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BN x 16), fp32 accum in TMEM,
 //                              tcgen05.commit frees smem stages / publishes the accumulator
-//   warps 2..9  epilogue       tcgen05.ld TMEM -> regs -> swizzled smem transpose -> coalesced
-//                              16-byte global accesses; bias / GELU / GELU' / residual fused
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> registers (thread = tile row) -> math -> the
+//                              thread's row of a 128B-swizzled [32 x 128 B] smem tile -> ONE TMA
+//                              store (or fp32 reduce-add) per 32 x 64 sub-tile.  Residual / GELU'
+//                              operands come in the same way (TMA load, prefetched one round
+//                              ahead) and the result is written in place over them.
 // TMEM holds two accumulators (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1 (K is only 256 for most of these GEMMs: SURVEY.md §7.3 hard part 2).
+//
+// Why the epilogue looks like this (measured, profiles/r01_gemm_epilogue.md): with K = 256 a tile
+// is 16 MMAs = 2048 clk of tensor work, and the previous epilogue (registers -> smem transpose ->
+// ld.shared -> per-thread 16-byte global stores, residual through per-thread global loads) took
+// ~3900 clk per tile per warp as one long dependent chain (LDTM -> F2FP -> STS -> LDS -> address
+// math -> STG; 24 % issue utilisation), i.e. the GEMMs ran at < 50 % of the MMA rate with every
+// memory pipe below 40 %.  TMA does the address generation, coalescing and bounds handling.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "m3l_internal.h"
 
@@ -30,17 +42,24 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
-constexpr int kStagingBytesPerWarp = 32 * 128;
+constexpr int kStgTileBytes = 32 * 128;   // one staging tile: 32 rows x 128 B
 
-template <int BN>
+// WS ("weight stationary", K <= 256): the whole [BN x K] slice of the B operand (the weight) stays
+// resident in shared memory for the life of the CTA and only A tiles stream through the ring,
+// which removes 2/3 of the operand traffic through the L2 -> SM path for the K = 256 GEMMs.
+constexpr int kWsMaxKb = 4;
+template <int BN, bool WS>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStgBufs = WS ? 1 : 2;                     // staging tiles per epilogue warp
+  static constexpr int kStages = WS ? (BN == 256 ? 4 : 8) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
+  static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
+  static constexpr int kResidentBytes = WS ? kWsMaxKb * kBBytes : 0;
+  static constexpr int kStagingBytes = kNumEpiWarps * kStgBufs * kStgTileBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + kNumEpiWarps * kStagingBytesPerWarp + 256;
+      1024 /*align slack*/ + kStages * kStageBytes + kResidentBytes + kStagingBytes + 512;
 };
 
 struct alignas(8) GemmBarriers {
@@ -48,14 +67,11 @@ struct alignas(8) GemmBarriers {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t b_full;                      // WS: resident weight slice landed
+  uint64_t side_full[kNumEpiWarps][2];  // per epilogue warp: residual / aux tile landed
   uint32_t tmem_base;
 };
-
-M3L_DEVINL void red_add_v4(float* addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w)
-               : "memory");
-}
+static_assert(sizeof(GemmBarriers) <= 512, "barrier block");
 
 // Epilogue flavours (compile time, so the inner loops carry no mode branches):
 enum : int {
@@ -63,13 +79,11 @@ enum : int {
   EPI_GELU_FWD = 1,  // out bf16 = GELU(acc + bias) ; aux_out bf16 = GELU'(acc + bias)
   EPI_GELU_BWD = 2,  // out bf16 = acc * aux_in   (aux_in = the stored GELU')
   EPI_F32 = 3,       // out fp32 = acc (+ bias)
-  EPI_F32_RED = 4,   // out fp32 += acc  (red.global.add, split-K)
+  EPI_F32_RED = 4,   // out fp32 += acc  (TMA reduce-add, split-K)
 };
 
-// ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) ------------
-// "row" mapping: thread `lane` owns row `lane` (this is how tcgen05.ld hands out the accumulator);
-// "co" mapping : iteration i, row 4*i + (lane >> 3), chunk lane & 7 (8 lanes cover one 128 B row,
-//                so global accesses are full-line coalesced).  Both mappings are bank-conflict free.
+// ---- staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) == SWIZZLE_128B ------
+// thread `lane` owns row `lane` (this is how tcgen05.ld hands out the accumulator); bank-conflict free.
 M3L_DEVINL void stg_store_row(uint32_t stg, int lane, const uint32_t* w) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -89,34 +103,46 @@ M3L_DEVINL void stg_load_row(uint32_t stg, int lane, uint32_t* w) {
                  : "memory");
   }
 }
-M3L_DEVINL uint4 stg_load_co(uint32_t stg, int lane, int i) {
-  const int r = 4 * i + (lane >> 3);
-  const uint32_t addr = stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"(addr)
-               : "memory");
+// 32-bit word `lane` (= bf16 columns 2*lane, 2*lane+1) of row r: one conflict-free column read
+M3L_DEVINL uint32_t stg_load_word(uint32_t stg, int lane, int r) {
+  const uint32_t addr = stg + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2);
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-M3L_DEVINL void stg_store_co(uint32_t stg, int lane, int i, uint4 v) {
-  const int r = 4 * i + (lane >> 3);
-  const uint32_t addr = stg + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// Static tile schedule of one CTA (identical in the producer, MMA and epilogue roles).
+//   streaming : items blockIdx.x, +gridDim.x, ... over (m tile, n tile, split), n fastest
+//   WS        : the CTA owns n tile (blockIdx.x % tiles_n) and walks m tiles q, q + G, ...
+struct TileSched {
+  int tiles_n, splits, count, first, step, n_fixed;
+  bool ws;
+  M3L_DEVINL void get(int i, int BN_, int* m0, int* n0, int* split) const {
+    const int item = first + i * step;
+    if (ws) {
+      *m0 = item * BM; *n0 = n_fixed * BN_; *split = 0;
+    } else {
+      *split = item % splits;
+      const int t = item / splits;
+      *n0 = (t % tiles_n) * BN_;
+      *m0 = (t / tiles_n) * BM;
+    }
+  }
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool WS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmArgs p) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_aux,
+                 const __grid_constant__ CUtensorMap map_side, const GemmArgs p) {
+  static_assert(!WS || (!A_MN && !B_MN), "weight-stationary mode is for K-major operands");
+  using Cfg = GemmCfg<BN, WS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-  GemmBarriers* bars =
-      reinterpret_cast<GemmBarriers*>(staging + kNumEpiWarps * kStagingBytesPerWarp);
+  uint8_t* resident = smem + Cfg::kStages * Cfg::kStageBytes;      // WS: [kb][BN x 64] weight slice
+  uint8_t* staging = resident + Cfg::kResidentBytes;
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(staging + Cfg::kStagingBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,11 +151,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int tiles_m = (p.M + BM - 1) / BM;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
-  const int num_items = tiles_m * tiles_n * p.splits;
+  TileSched sched;
+  sched.tiles_n = tiles_n; sched.splits = p.splits; sched.ws = WS;
+  if (WS) {
+    const int n_idx = blockIdx.x % tiles_n, q = blockIdx.x / tiles_n;
+    const int group = ((int)gridDim.x - n_idx + tiles_n - 1) / tiles_n;   // CTAs that own this n tile
+    sched.n_fixed = n_idx; sched.first = q; sched.step = group;
+    sched.count = q < tiles_m ? (tiles_m - q + group - 1) / group : 0;
+  } else {
+    const int num_items = tiles_m * tiles_n * p.splits;
+    sched.n_fixed = 0; sched.first = blockIdx.x; sched.step = gridDim.x;
+    sched.count = (int)blockIdx.x < num_items
+                      ? (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+    if (EPI == EPI_GELU_FWD) tma_prefetch_desc(&map_aux);
+    if (EPI == EPI_GELU_BWD || EPI == EPI_BF16) tma_prefetch_desc(&map_side);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -138,6 +179,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&bars->tmem_full[b], 1);
       mbar_init(&bars->tmem_empty[b], kNumEpiWarps);
     }
+    mbar_init(&bars->b_full, 1);
+    for (int w = 0; w < kNumEpiWarps; ++w) {
+      mbar_init(&bars->side_full[w][0], 1);
+      mbar_init(&bars->side_full[w][1], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, Cfg::kTmemCols);
@@ -145,17 +191,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();      // prologue above overlapped the predecessor kernel; global memory from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item % p.splits;
-        const int t = item / p.splits;
-        const int n0 = (t % tiles_n) * BN;
-        const int m0 = (t / tiles_n) * BM;
+      if (WS && sched.count > 0) {
+        mbar_arrive_expect_tx(&bars->b_full, kb_total * Cfg::kBBytes);
+        for (int kb = 0; kb < kb_total; ++kb)
+          tma_load_2d(resident + kb * Cfg::kBBytes, &map_b, &bars->b_full, kb * BK, sched.n_fixed * BN);
+      }
+      for (int i = 0; i < sched.count; ++i) {
+        int m0, n0, split;
+        sched.get(i, BN, &m0, &n0, &split);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -170,7 +221,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(sa + j * 8192, &map_a, &bars->full[stage], m0 + 64 * j, kb * BK);
           }
-          if (!B_MN) {
+          if (WS) {
+            // weight slice already resident
+          } else if (!B_MN) {
             tma_load_2d(sb, &map_b, &bars->full[stage], kb * BK, n0);
           } else {
 #pragma unroll
@@ -187,9 +240,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int split = item % p.splits;
+      if (WS && sched.count > 0) mbar_wait(&bars->b_full, 0);
+      for (int it = 0; it < sched.count; ++it) {
+        int m0, n0, split;
+        sched.get(it, BN, &m0, &n0, &split);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, kb_total);
         const int buf = it & 1;
@@ -201,7 +255,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + Cfg::kABytes;
+          const uint32_t b_addr = WS ? smem_u32(resident + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
@@ -226,41 +280,89 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool active = BN >= 128 || col_half == 0;
     const int span0 = BN >= 128 ? col_half * kSpan : 0;
     constexpr bool kF32 = (EPI == EPI_F32 || EPI == EPI_F32_RED);
-    constexpr int kRoundCols = kF32 ? 32 : 64;
+    constexpr int kRoundCols = kF32 ? 32 : 64;   // one staging tile (128 B per row) per round
     constexpr int kRounds = kSpan / kRoundCols;
-    const uint32_t stg = smem_u32(staging + ew * kStagingBytesPerWarp);
+    constexpr int kBufs = Cfg::kStgBufs;
+    const uint32_t stg = smem_u32(staging + ew * kBufs * kStgTileBytes);
     const bool has_bias = (EPI != EPI_GELU_BWD && EPI != EPI_F32_RED) && p.bias != nullptr;
-    const bool has_res = (EPI == EPI_BF16) && p.residual != nullptr;
-    const int co_row = lane >> 3, co_chunk = lane & 7;
-    // fused column sums of the output (bias gradient): kept in registers while this CTA stays on
-    // the same N tile (the host sizes the grid as a multiple of tiles_n so that it always does)
+    // side operand (TMA-loaded, result written in place): residual (EPI_BF16) or aux_in (GELU')
+    const bool has_side = kBufs == 2 && ((EPI == EPI_BF16 && p.residual != nullptr) || EPI == EPI_GELU_BWD);
     const bool want_colsum = !kF32 && p.colsum_out != nullptr;
-    float csum[kF32 ? 1 : kRounds][8];
+    // fused column sums of the bf16 output (bias gradient): lane accumulates 8 columns (16-byte chunk
+    // lane & 7) over the rows = (lane >> 3) mod 4 of every staged tile, in registers while this CTA
+    // stays on the same n tile (the host sizes the grid as a multiple of tiles_n so that it always does)
+    float csum[kRounds][8];
     int csum_n0 = -1;
+    const int cs_row = lane >> 3, cs_chunk = lane & 7;
     auto flush_colsum = [&]() {
       if (csum_n0 < 0) return;
 #pragma unroll
-      for (int r = 0; r < (kF32 ? 1 : kRounds); ++r) {
+      for (int r = 0; r < kRounds; ++r) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float v = csum[r][e];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          const int gc = csum_n0 + span0 + r * kRoundCols + co_chunk * 8 + e;
-          if (co_row == 0 && gc < p.N) atomicAdd(p.colsum_out + gc, v);
+          float t = csum[r][e];
+          t += __shfl_xor_sync(0xffffffffu, t, 8);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          const int gc = csum_n0 + span0 + r * kRoundCols + cs_chunk * 8 + e;
+          if (cs_row == 0 && gc < p.N) atomicAdd(p.colsum_out + gc, t);
         }
       }
     };
-    int it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int t = item / p.splits;
-      const int n0 = (t % tiles_n) * BN;
-      const int m0 = (t / tiles_n) * BM;
+    // column sums of the tile just staged at `sb` (bf16), rows beyond M excluded
+    auto add_colsum = [&](uint32_t sb, int row0, int r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + cs_row;
+        const uint32_t addr = sb + rr * 128 + ((cs_chunk ^ (rr & 7)) << 4);
+        uint4 u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+        if (row0 + rr < p.M) {
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+#pragma unroll
+          for (int q = 0; q < kRounds; ++q)      // static register indexing
+            if (q == r) {
+              csum[q][0] += a.x; csum[q][1] += a.y; csum[q][2] += b.x; csum[q][3] += b.y;
+              csum[q][4] += c.x; csum[q][5] += c.y; csum[q][6] += d.x; csum[q][7] += d.y;
+            }
+        }
+      }
+    };
+    const int total_rounds = active ? sched.count * kRounds : 0;
+    auto issue_side = [&](int gi) {   // lane 0: prefetch the side tile of global round gi
+      int m0, n0, split;
+      sched.get(gi / kRounds, BN, &m0, &n0, &split);
+      const int b = gi & 1;
+      mbar_arrive_expect_tx(&bars->side_full[ew][b], kStgTileBytes);
+      tma_load_2d_u32(stg + b * kStgTileBytes, &map_side, &bars->side_full[ew][b],
+                      n0 + span0 + (gi % kRounds) * kRoundCols, m0 + quad * 32);
+    };
+    if (has_side && lane == 0 && total_rounds > 0) issue_side(0);
+    int g = 0;      // global round counter of this warp
+    int ob = 0;     // staging buffer of the next output tile (modes without a side operand)
+    // stage one 32 x 128 B tile (row-mapped registers) and hand it to TMA; returns the smem tile
+    auto stage_and_store = [&](const CUtensorMap* map, const uint32_t* w, int col, int row, bool reduce) {
+      const uint32_t dst = stg + ob * kStgTileBytes;
+      if (lane == 0) tma_wait_group_read<kBufs - 1>();   // the tile last stored from this buffer was read
+      __syncwarp();
+      stg_store_row(dst, lane, w);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (reduce) tma_reduce_add_2d(map, dst, col, row); else tma_store_2d(map, dst, col, row);
+        tma_commit_group();
+      }
+      ob = (ob + 1 == kBufs) ? 0 : ob + 1;
+      return dst;
+    };
+    for (int it = 0; it < sched.count; ++it) {
+      int m0, n0, split;
+      sched.get(it, BN, &m0, &n0, &split);
       if (want_colsum && active && n0 != csum_n0) {
         flush_colsum();
         csum_n0 = n0;
 #pragma unroll
-        for (int r = 0; r < (kF32 ? 1 : kRounds); ++r)
+        for (int r = 0; r < kRounds; ++r)
 #pragma unroll
           for (int e = 0; e < 8; ++e) csum[r][e] = 0.f;
       }
@@ -268,7 +370,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&bars->tmem_full[buf], acc_phase);
       tc_fence_after_sync();
-      const int row_base = m0 + quad * 32;
+      const int row0 = m0 + quad * 32;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN;
       if (!active) {
         tc_fence_before_sync();
@@ -277,27 +379,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         continue;
       }
 #pragma unroll 1
-      for (int r = 0; r < kRounds; ++r) {
+      for (int r = 0; r < kRounds; ++r, ++g) {
         const int c0 = span0 + r * kRoundCols;        // first tile column of this round
+        const int gcol = n0 + c0;
         if constexpr (!kF32) {
           // ---------------- bf16 outputs: 64 columns per round ----------------
-          const int gcol = n0 + c0 + co_chunk * 8;      // this lane's 8 columns in the co mapping
-          const bool col_ok = gcol < p.N;
-          uint4 side[8];
-          if (EPI == EPI_GELU_BWD || has_res) {
-            const bf16* sp = (EPI == EPI_GELU_BWD) ? p.aux_in : p.residual;
-            const int ld = (EPI == EPI_GELU_BWD) ? p.ld_aux : p.ldr;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int grow = row_base + 4 * i + co_row;
-              side[i] = (col_ok && grow < p.M)
-                            ? *reinterpret_cast<const uint4*>(sp + (size_t)grow * ld + gcol)
-                            : make_uint4(0, 0, 0, 0);
-            }
-          }
           uint32_t v[64];
           tmem_ld_32x32(t_acc + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           tmem_ld_32x32(t_acc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          if (has_side && g + 1 < total_rounds) {
+            __syncwarp();    // every lane is done with buffer (g+1)&1 (round g-1: row + column-sum reads)
+            if (lane == 0) {
+              tma_wait_group_read<0>();     // ... and so is the TMA store that was issued from it
+              fence_proxy_async_smem();
+              issue_side(g + 1);
+            }
+          }
           tmem_ld_wait();
           if (r == kRounds - 1) {
             tc_fence_before_sync();
@@ -307,7 +404,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
-              const int c = n0 + c0 + j;
+              const int c = gcol + j;
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
               v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
@@ -329,75 +426,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 v[2 * j] = __float_as_uint(x0 * g0.cdf);
                 v[2 * j + 1] = __float_as_uint(x1 * g1.cdf);
               }
-              stg_store_row(stg, lane, w);
-              __syncwarp();
-              uint4 u[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int grow = row_base + 4 * i + co_row;
-                if (col_ok && grow < p.M)
-                  *reinterpret_cast<uint4*>(p.aux_out + (size_t)grow * p.ld_aux + gcol) = u[i];
-              }
-              __syncwarp();
+              stage_and_store(&map_aux, w, gcol, row0, false);
             } else {
 #pragma unroll
               for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
             }
           }
-          if (EPI == EPI_GELU_BWD || has_res) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) stg_store_co(stg, lane, i, side[i]);
-            __syncwarp();
-            stg_load_row(stg, lane, w);
-            __syncwarp();
+          if (has_side) {
+            const uint32_t sb = stg + (g & 1) * kStgTileBytes;
+            mbar_wait(&bars->side_full[ew][g & 1], (g >> 1) & 1);
+            stg_load_row(sb, lane, w);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float2 s2 = unpack_bf16x2(w[j]);
               if constexpr (EPI == EPI_GELU_BWD) {   // aux_in holds GELU'(pre-activation)
-                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) * s2.x);
-                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) * s2.y);
+                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * s2.x, __uint_as_float(v[2 * j + 1]) * s2.y);
               } else {
-                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + s2.x);
-                v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + s2.y);
+                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + s2.x, __uint_as_float(v[2 * j + 1]) + s2.y);
               }
             }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          stg_store_row(stg, lane, w);
-          __syncwarp();
-          uint4 u[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
-          bf16* outp = reinterpret_cast<bf16*>(p.out);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = row_base + 4 * i + co_row;
-            if (col_ok && grow < p.M) *reinterpret_cast<uint4*>(outp + (size_t)grow * p.ldo + gcol) = u[i];
-          }
-          if (want_colsum) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (row_base + 4 * i + co_row < p.M) {
-                const float2 a = unpack_bf16x2(u[i].x), b = unpack_bf16x2(u[i].y), c = unpack_bf16x2(u[i].z),
-                             d = unpack_bf16x2(u[i].w);
-#pragma unroll
-                for (int rr = 0; rr < kRounds; ++rr)      // static register indexing
-                  if (rr == r) {
-                    csum[rr][0] += a.x; csum[rr][1] += a.y; csum[rr][2] += b.x; csum[rr][3] += b.y;
-                    csum[rr][4] += c.x; csum[rr][5] += c.y; csum[rr][6] += d.x; csum[rr][7] += d.y;
-                  }
-              }
+            stg_store_row(sb, lane, w);      // in place: every thread only touches its own row
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_out, sb, gcol, row0);
+              tma_commit_group();
             }
+            if (want_colsum) add_colsum(sb, row0, r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            const uint32_t sb = stage_and_store(&map_out, w, gcol, row0, false);
+            if (want_colsum) add_colsum(sb, row0, r);
           }
-          __syncwarp();
         } else {
           // ---------------- fp32 outputs: 32 columns per round ----------------
-          const int gcol = n0 + c0 + co_chunk * 4;
-          const bool col_ok = gcol < p.N;
           uint32_t v[32];
           tmem_ld_32x32(t_acc + c0, v);
           tmem_ld_wait();
@@ -409,7 +473,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const int c = n0 + c0 + j;
+              const int c = gcol + j;
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
               v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
@@ -418,30 +482,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
             }
           }
-          stg_store_row(stg, lane, v);
-          __syncwarp();
-          uint4 u[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) u[i] = stg_load_co(stg, lane, i);
-          float* outp = reinterpret_cast<float*>(p.out);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = row_base + 4 * i + co_row;
-            if (col_ok && grow < p.M) {
-              float* dst = outp + (size_t)grow * p.ldo + gcol;
-              if constexpr (EPI == EPI_F32_RED) {
-                red_add_v4(dst, make_float4(__uint_as_float(u[i].x), __uint_as_float(u[i].y),
-                                            __uint_as_float(u[i].z), __uint_as_float(u[i].w)));
-              } else {
-                *reinterpret_cast<uint4*>(dst) = u[i];
-              }
-            }
-          }
-          __syncwarp();
+          stage_and_store(&map_out, v, gcol, row0, EPI == EPI_F32_RED);
         }
       }
     }
     if (want_colsum && active) flush_colsum();
+    if (lane == 0) tma_wait_group<0>();   // every store / reduce of this warp has been performed
   }
 
   tc_fence_before_sync();
@@ -452,16 +498,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool WS = false>
 int launch_variant(const GemmPlan& plan, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
+  using Cfg = GemmCfg<BN, WS>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, WS>;
   static bool configured = false;
   if (!configured) {
     M3L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  kern<<<plan.grid, kNumThreads, Cfg::kSmemBytes, stream>>>(plan.map_a, plan.map_b, plan.args);
+  M3L_CUDA(launch_kernel(kern, dim3(plan.grid), dim3(kNumThreads), Cfg::kSmemBytes, stream, plan.map_a,
+                         plan.map_b, plan.map_out, plan.map_aux, plan.map_side, plan.args));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -470,6 +518,13 @@ template <int BN>
 int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
   const GemmArgs& p = plan.args;
   if (p.a_mn_major) return launch_variant<BN, true, true, EPI_F32_RED>(plan, stream);
+  if constexpr (BN >= 128) {
+    if (plan.ws) {
+      if (p.out_mode == 1) return launch_variant<BN, false, false, EPI_F32, true>(plan, stream);
+      if (p.act == 1) return launch_variant<BN, false, false, EPI_GELU_FWD, true>(plan, stream);
+      return launch_variant<BN, false, false, EPI_BF16, true>(plan, stream);
+    }
+  }
   if (p.out_mode == 1) return launch_variant<BN, false, false, EPI_F32>(plan, stream);
   if (p.act == 1) return launch_variant<BN, false, false, EPI_GELU_FWD>(plan, stream);
   if (p.act == 2) return launch_variant<BN, false, false, EPI_GELU_BWD>(plan, stream);
@@ -518,21 +573,38 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   M3L_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
   plan->bn = bn;
   plan->args = p;
+  int s;
   if (!p.a_mn_major) {
-    int s = make_tmap_2d_bf16(&plan->map_a, p.a, p.M, p.K, p.lda, BM);
-    if (s) return s;
-    s = make_tmap_2d_bf16(&plan->map_b, p.b, p.N, p.K, p.ldb, bn);
-    if (s) return s;
+    if ((s = make_tmap_2d_bf16(&plan->map_a, p.a, p.M, p.K, p.lda, BM))) return s;
+    if ((s = make_tmap_2d_bf16(&plan->map_b, p.b, p.N, p.K, p.ldb, bn))) return s;
   } else {
     // operands stored [K rows, M or N columns]
-    int s = make_tmap_2d_bf16(&plan->map_a, p.a, p.K, p.M, p.lda, BK);
-    if (s) return s;
-    s = make_tmap_2d_bf16(&plan->map_b, p.b, p.K, p.N, p.ldb, BK);
-    if (s) return s;
+    if ((s = make_tmap_2d_bf16(&plan->map_a, p.a, p.K, p.M, p.lda, BK))) return s;
+    if ((s = make_tmap_2d_bf16(&plan->map_b, p.b, p.K, p.N, p.ldb, BK))) return s;
+  }
+  // epilogue tiles: 32 rows x 128 B (64 bf16 / 32 fp32 columns)
+  if (p.out_mode == 0) {
+    if ((s = make_tmap_2d_bf16(&plan->map_out, p.out, p.M, p.N, p.ldo, 32))) return s;
+  } else {
+    if ((s = make_tmap_2d_f32(&plan->map_out, p.out, p.M, p.N, p.ldo, 32))) return s;
+  }
+  plan->map_aux = plan->map_out;
+  plan->map_side = plan->map_out;
+  if (p.aux_out != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.aux_out, p.M, p.N, p.ld_aux, 32))) return s;
+  if (p.act == 2) {
+    if ((s = make_tmap_2d_bf16(&plan->map_side, p.aux_in, p.M, p.N, p.ld_aux, 32))) return s;
+  } else if (p.residual != nullptr) {
+    if ((s = make_tmap_2d_bf16(&plan->map_side, p.residual, p.M, p.N, p.ldr, 32))) return s;
   }
   const int tiles_n = (p.N + bn - 1) / bn;
   const int tiles = ((p.M + BM - 1) / BM) * tiles_n * p.splits;
   plan->grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  // weight-stationary mode: K fits the resident slice, no side operand (its staging is single
+  // buffered) and every CTA gets several m tiles to amortise the one-off weight load over
+  // (M3L_GEMM_WS=0 disables it, for A/B measurements)
+  static const bool ws_allowed = [] { const char* e = getenv("M3L_GEMM_WS"); return !(e && e[0] == '0'); }();
+  plan->ws = ws_allowed && !p.a_mn_major && kb_total <= kWsMaxKb && p.splits == 1 && bn >= 128 &&
+             p.residual == nullptr && p.act != 2 && tiles >= 2 * device_sm_count() && tiles_n <= plan->grid;
   if (p.colsum_out != nullptr) {
     M3L_REQUIRE(p.out_mode == 0, "gemm: colsum_out needs the bf16 output mode");
     // keep every CTA on one N tile so the column sums stay in registers across its tiles

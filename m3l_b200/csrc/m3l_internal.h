@@ -30,9 +30,11 @@ struct GemmArgs {
 
 struct GemmPlan {
   CUtensorMap map_a, map_b;
+  CUtensorMap map_out, map_aux, map_side;   // epilogue tiles: output, second output (GELU'), side operand
   GemmArgs args;
   int bn = 0;
   int grid = 0;
+  bool ws = false;          // weight-stationary schedule (gemm.cu)
 };
 
 int gemm_pick_bn(int M, int N);

@@ -14,6 +14,8 @@ namespace m3l {
 namespace {
 
 __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double red[32];
   double acc = 0.0;
   const size_t n4 = n >> 2;
@@ -39,6 +41,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __re
 
 // state[0] = step counter (as double), state[1] = sum of squares of all grads, state[2] = total norm (out)
 __global__ void step_begin_kernel(double* state) {
+  pdl_wait();
+  pdl_trigger();
   state[0] += 1.0;
   state[2] = sqrt(state[1]);
 }
@@ -47,6 +51,8 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
                              float* __restrict__ v, size_t n, const double* __restrict__ state, float lr,
                              float beta1, float beta2, float eps, float weight_decay, float max_norm,
                              int write_clipped_grad) {
+  pdl_wait();
+  pdl_trigger();
   const float step = (float)state[0];
   const float total = (float)state[2];
   float coef = 1.0f;
@@ -89,6 +95,8 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  pdl_wait();
+  pdl_trigger();
   const size_t n8 = n >> 3;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
@@ -105,6 +113,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 // transposed bf16 copies of a table of fp32 matrices: dst[c, r] = src[r, c]
 __global__ void transpose_cast_kernel(const float* __restrict__ src_base, bf16* __restrict__ dst_base,
                                       const m3l_matrix_desc* __restrict__ descs) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const m3l_matrix_desc d = descs[blockIdx.y];
   const int tiles_c = (d.cols + 31) / 32, tiles_r = (d.rows + 31) / 32;
@@ -142,14 +152,14 @@ extern "C" int m3l_grad_sumsq(const float* grads, size_t count, double* state, v
   M3L_REQUIRE(grads && state, "grad_sumsq: null pointer");
   M3L_REQUIRE(((uintptr_t)grads & 15) == 0, "grad_sumsq: grads not 16-byte aligned");
   if (count == 0) return M3L_OK;
-  sumsq_kernel<<<stream_grid(count, 4), 256, 0, (cudaStream_t)stream>>>(grads, count, state + 1);
+  M3L_CUDA(launch_kernel(sumsq_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, grads, count, state + 1));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
 
 extern "C" int m3l_optimizer_step_begin(double* state, void* stream) {
   M3L_REQUIRE(state, "optimizer_step_begin: null pointer");
-  step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  M3L_CUDA(launch_kernel(step_begin_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -161,9 +171,9 @@ extern "C" int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float
   M3L_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
               "clip_adamw: arenas must be 16-byte aligned");
   if (count == 0) return M3L_OK;
-  adamw_kernel<<<stream_grid(count, 4), 256, 0, (cudaStream_t)stream>>>(
+  M3L_CUDA(launch_kernel(adamw_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, 
       params, grads, exp_avg, exp_avg_sq, count, state, lr, beta1, beta2, eps, weight_decay, max_norm,
-      write_clipped_grad);
+      write_clipped_grad));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -172,7 +182,7 @@ extern "C" int m3l_cast_bf16(const float* src, void* dst_bf16, size_t count, voi
   M3L_REQUIRE(src && dst_bf16, "cast_bf16: null pointer");
   M3L_REQUIRE((((uintptr_t)src | (uintptr_t)dst_bf16) & 15) == 0, "cast_bf16: pointers must be 16-byte aligned");
   if (count == 0) return M3L_OK;
-  cast_bf16_kernel<<<stream_grid(count, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst_bf16, count);
+  M3L_CUDA(launch_kernel(cast_bf16_kernel, dim3(stream_grid(count, 8)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, count));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -181,8 +191,8 @@ extern "C" int m3l_transpose_cast_bf16(const float* src_base, void* dst_base_bf1
                                        int count, void* stream) {
   M3L_REQUIRE(src_base && dst_base_bf16 && descs_dev, "transpose_cast_bf16: null pointer");
   if (count == 0) return M3L_OK;
-  transpose_cast_kernel<<<dim3(64, count), dim3(32, 8), 0, (cudaStream_t)stream>>>(src_base, (bf16*)dst_base_bf16,
-                                                                                  descs_dev);
+  M3L_CUDA(launch_kernel(transpose_cast_kernel, dim3(dim3(64, count)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, src_base, (bf16*)dst_base_bf16,
+                                                                                  descs_dev));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
