@@ -143,13 +143,15 @@ int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, int dim,
                      void* stream);
 
 /* Masked-patch MSE (pretrain_models.py:327-340): target rows are gathered from the raw maps;
- * *loss_acc += weight * sum((pred - target)^2); dpred = 2 * weight * (pred - target) (bf16).
+ * *loss_acc += weight * sum((pred - target)^2); dpred = 2 * weight * (pred - target) (bf16);
+ * dpred_colsum (optional, patch dim <= 1024): [P] fp32 += column sums of dpred, i.e. the bias
+ * gradient of the head Linear (nn.Linear backward through to_pixels / to_tactiles).
  * workspace: device scratch (>= 256 + 4 * blocks bytes; 1 MiB is always enough) whose first 4 bytes
  * are zero on entry and zero again on exit; per-block partial losses are summed by the last block
  * to finish, which makes the loss bit-reproducible run to run. */
 int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
                  int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 float* dpred_colsum, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[n] += sum_m x[m, n] (bias gradients). */
 int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);

@@ -827,11 +827,12 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
                                     const int32_t* __restrict__ row_pos, float* __restrict__ dpos) {
   pdl_wait();
   pdl_trigger();
-  // one block per visible slot j (class is a function of j only; position varies per sample)
+  // block (j, y): visible slot j (class is a function of j only; position varies per sample),
+  // samples y, y + gridDim.y, ...
   const int j = blockIdx.x;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
       const size_t r = (size_t)b * nv + j;
       const float g = __bfloat162float(dx[r * D + c]);
       s += g;
@@ -844,30 +845,47 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
 // ------------------------------------------------------------------------------------------
 // 6. masked-patch MSE: pred fp32 [rows, P]; target gathered from the raw maps.
 //    loss_acc[slot] += weight * sum((pred - tgt)^2) ; dpred = 2 * weight * (pred - tgt)  (bf16)
+//    dcolsum[p] += sum_rows dpred[row, p]  (optional: the bias gradient of the head Linear)
+//    Warp per row.  The patch is transposed through smem from the source order (c, p1, p2) to the
+//    destination order (p1, p2, c): lanes walk (p1, c) with c fastest and every p1 row of the patch
+//    has pitch pw*C + pad floats with pitch % 32 == C % 32, which keeps the scattered stores
+//    conflict free (the first version put all 8 p1 rows of a lane group on one bank).  The final
+//    loss reduction over the block partials is done by ALL threads of the last block in a fixed
+//    order (deterministic, and not a 1184-long chain of L2 round trips on one thread).
 // ------------------------------------------------------------------------------------------
+constexpr int kMseMaxT = 8;   // column sums kept in registers: P <= 128 * 4 * ... = 1024
 __global__ void __launch_bounds__(256)
 mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols, int rows,
                 const float* __restrict__ pred, float weight, bf16* __restrict__ dpred,
-                float* __restrict__ loss_acc, void* ws) {
+                float* __restrict__ loss_acc, float* __restrict__ dcolsum, int pitch, void* ws) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float patches[];   // [warps][P] floats, destination order (p1, p2, c)
+  extern __shared__ __align__(16) float patches[];   // [warps][ph * pitch] floats, then [P] column sums
   __shared__ float red[8];
+  __shared__ unsigned int s_ticket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int P = ps.P;
-  float* patch = patches + (size_t)warp * P;
+  const int rowlen = ps.pw * ps.C;                   // floats per patch row p1 (destination order)
+  float* patch = patches + (size_t)warp * ps.ph * pitch;
+  float* s_cs = patches + (size_t)nwarps * ps.ph * pitch;
   const int src_rows = ps.C * ps.ph;
   const float w2 = 2.f * weight;
   float acc = 0.f;
+  float cs[kMseMaxT][4];
+#pragma unroll
+  for (int t = 0; t < kMseMaxT; ++t) cs[t][0] = cs[t][1] = cs[t][2] = cs[t][3] = 0.f;
+  if (dcolsum) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_cs[i] = 0.f;
+  }
   for (int r = blockIdx.x * nwarps + warp; r < rows; r += gridDim.x * nwarps) {
     const int b = r / ncols, jj = r - b * ncols;
     const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
     int sensor;
     const float* origin = patch_origin(ps, b, tok, &sensor);
-    for (int i = lane; i < src_rows; i += 32) {      // one (channel, patch row) per lane: pw contiguous floats
-      const int c = i / ps.ph, p1 = i - c * ps.ph;
+    for (int i = lane; i < src_rows; i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
+      const int p1 = i / ps.C, c = i - p1 * ps.C;
       const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
-      float* dst = patch + (p1 * ps.pw) * ps.C + c;
+      float* dst = patch + p1 * pitch + c;
       if ((ps.pw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         for (int p2 = 0; p2 < ps.pw; p2 += 4) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(src + p2));
@@ -881,13 +899,42 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
     __syncwarp();
     const float* prow = pred + (size_t)r * P;
     bf16* drow = dpred + (size_t)r * P;
-    for (int e = lane * 4; e < P; e += 128) {
+#pragma unroll
+    for (int t = 0; t < kMseMaxT; ++t) {
+      const int e = t * 128 + lane * 4;
+      if (e < P) {
+        const int p1 = e / rowlen;
+        const float4 tv = *reinterpret_cast<const float4*>(patch + p1 * pitch + (e - p1 * rowlen));
+        const float4 pv = *reinterpret_cast<const float4*>(prow + e);
+        const float d0 = pv.x - tv.x, d1 = pv.y - tv.y, d2 = pv.z - tv.z, d3 = pv.w - tv.w;
+        acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        const float g0 = w2 * d0, g1 = w2 * d1, g2 = w2 * d2, g3 = w2 * d3;
+        *reinterpret_cast<uint2*>(drow + e) = make_uint2(pack_bf16x2(g0, g1), pack_bf16x2(g2, g3));
+        cs[t][0] += g0; cs[t][1] += g1; cs[t][2] += g2; cs[t][3] += g3;
+      }
+    }
+    for (int e = kMseMaxT * 128 + lane * 4; e < P; e += 128) {      // P > 1024: no column sums
+      const int p1 = e / rowlen;
+      const float4 tv = *reinterpret_cast<const float4*>(patch + p1 * pitch + (e - p1 * rowlen));
       const float4 pv = *reinterpret_cast<const float4*>(prow + e);
-      const float d0 = pv.x - patch[e], d1 = pv.y - patch[e + 1], d2 = pv.z - patch[e + 2], d3 = pv.w - patch[e + 3];
+      const float d0 = pv.x - tv.x, d1 = pv.y - tv.y, d2 = pv.z - tv.z, d3 = pv.w - tv.w;
       acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
       *reinterpret_cast<uint2*>(drow + e) = make_uint2(pack_bf16x2(w2 * d0, w2 * d1), pack_bf16x2(w2 * d2, w2 * d3));
     }
     __syncwarp();
+  }
+  if (dcolsum) {
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kMseMaxT; ++t) {
+      const int e = t * 128 + lane * 4;
+      if (e < P) {
+        atomicAdd(&s_cs[e], cs[t][0]); atomicAdd(&s_cs[e + 1], cs[t][1]);
+        atomicAdd(&s_cs[e + 2], cs[t][2]); atomicAdd(&s_cs[e + 3], cs[t][3]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&dcolsum[i], s_cs[i]);
   }
   acc = warp_sum(acc);
   if (lane == 0) red[warp] = acc;
@@ -897,8 +944,24 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
     float t = 0.f;
     for (int w = 0; w < nwarps; ++w) t += red[w];
     rws.partials[blockIdx.x] = weight * t;
+    __threadfence();
+    s_ticket = atomicAdd(rws.counter, 1u);
   }
-  last_block_reduce(rws, 1, gridDim.x, [&](int, float t) { *loss_acc += t; });
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  float t = 0.f;                                        // fixed assignment of partials to threads
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(rws.partials + i);
+  t = warp_sum(t);
+  __syncthreads();
+  if (lane == 0) red[warp] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; ++w) tot += red[w];
+    *loss_acc += tot;
+    *rws.counter = 0u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -951,22 +1014,40 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int M, int N, int ld, 
 }
 
 // LayerNorm(P) parameter gradients of the patch embedding: dgamma[p] += sum_r dA[r,p]*xhat[r,p]; dbeta[p] += sum_r dA[r,p]
+// block 32 x 8 threads; thread owns 8 consecutive columns (16-byte loads), rows strided by 8
 __global__ void ln_param_grad_kernel(const bf16* __restrict__ dA, const bf16* __restrict__ xhat, int M, int P,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_wait();
   pdl_trigger();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-  const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, M);
-  float g = 0.f, bsum = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const float d = __bfloat162float(dA[(size_t)r * P + p]);
-    g += d * __bfloat162float(xhat[(size_t)r * P + p]);
-    bsum += d;
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  __shared__ float part[2][8][32][8];
+  float g[8], bs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = bs[i] = 0.f;
+  if (col < P) {
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, M);
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float d[8], x[8];
+      load8<bf16>(dA + (size_t)r * P + col, d);
+      load8<bf16>(xhat + (size_t)r * P + col, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { g[i] = fmaf(d[i], x[i], g[i]); bs[i] += d[i]; }
+    }
   }
-  atomicAdd(&dgamma[p], g);
-  atomicAdd(&dbeta[p], bsum);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { part[0][threadIdx.y][threadIdx.x][i] = g[i]; part[1][threadIdx.y][threadIdx.x][i] = bs[i]; }
+  __syncthreads();
+  if (threadIdx.y < 2 && col < P) {
+    float* out = threadIdx.y == 0 ? dgamma : dbeta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+      for (int y = 0; y < 8; ++y) t += part[threadIdx.y][y][threadIdx.x][i];
+      atomicAdd(&out[col + i], t);
+    }
+  }
 }
 
 PatchSrc make_patch_src(const m3l_patch_source* s) {
@@ -1186,7 +1267,7 @@ extern "C" int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, i
                                 void* stream) {
   M3L_REQUIRE(dx_bf16, "rowclass_sum: null pointer");
   if (batch * n_visible == 0) return M3L_OK;
-  M3L_CUDA(launch_kernel(rowclass_sum_kernel, dim3(n_visible), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dx_bf16, batch, n_visible, dim,
+  M3L_CUDA(launch_kernel(rowclass_sum_kernel, dim3(n_visible, batch >= 64 ? 16 : 1), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dx_bf16, batch, n_visible, dim,
                                                                    slot_class, dclass, row_pos, dpos));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
@@ -1194,23 +1275,33 @@ extern "C" int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, i
 
 extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
                             int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+                            float* dpred_colsum, void* workspace, size_t workspace_bytes, void* stream) {
   M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
   if (batch * ncols == 0) return M3L_OK;
   PatchSrc ps = make_patch_src(src);
-  M3L_REQUIRE(ps.P % 4 == 0 && ps.P * sizeof(float) * 8 <= 96 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
+  const int rowlen = ps.pw * ps.C;
+  M3L_REQUIRE(ps.P % 4 == 0 && rowlen % 4 == 0, "mse_loss: patch dim %d / row %d must be multiples of 4", ps.P, rowlen);
+  M3L_REQUIRE(dpred_colsum == nullptr || ps.P <= kMseMaxT * 128, "mse_loss: fused column sums need patch dim <= %d", kMseMaxT * 128);
+  // pitch = rowlen + pad with pitch % 32 == round_up(C, 4) % 32 (rowlen % 4 == 0, so pitch % 4 == 0 for
+  // the float4 reads): the lane groups of consecutive p1 rows land on disjoint banks
+  const int want = ((ps.C + 3) & ~3) % 32;
+  const int pad = ((want - rowlen) % 32 + 32) % 32;
+  const int pitch = rowlen + pad;
+  const size_t smem = ((size_t)8 * ps.ph * pitch + ps.P) * sizeof(float);
+  M3L_REQUIRE(smem <= 160 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
   static bool configured = false;
   if (!configured) {
-    M3L_CUDA(cudaFuncSetAttribute(mse_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    M3L_CUDA(cudaFuncSetAttribute(mse_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
   const int rows = batch * ncols;
   int grid = (rows + 15) / 16;                       // two rows per warp: the per-row gather chain is latency bound
-  if (grid > device_sm_count() * 8) grid = device_sm_count() * 8;
+  const int cap = device_sm_count() * (dpred_colsum ? 4 : 8);   // bounds the atomics per bias-gradient address
+  if (grid > cap) grid = cap;
   M3L_REQUIRE(workspace != nullptr && workspace_bytes >= 256 + (size_t)grid * sizeof(float),
               "mse_loss: workspace too small (%zu bytes)", workspace_bytes);
-  M3L_CUDA(launch_kernel(mse_loss_kernel, dim3(grid), dim3(256), ps.P * sizeof(float) * 8, (cudaStream_t)stream, ps, tok_idx, idx_ld, col0, ncols, rows, pred, weight,
-                                                                   (bf16*)dpred_bf16, loss_acc, workspace));
+  M3L_CUDA(launch_kernel(mse_loss_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, ps, tok_idx, idx_ld, col0,
+                         ncols, rows, pred, weight, (bf16*)dpred_bf16, loss_acc, dpred_colsum, pitch, workspace));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -1231,12 +1322,14 @@ extern "C" int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float*
 extern "C" int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int dim, float* dgamma,
                                  float* dbeta, void* stream) {
   M3L_REQUIRE(da_bf16 && xhat_bf16 && dgamma && dbeta, "ln_param_grad: null pointer");
+  M3L_REQUIRE(dim % 8 == 0, "ln_param_grad: dim %d must be a multiple of 8", dim);
   if (rows == 0) return M3L_OK;
-  const int gx = (dim + 127) / 128;
-  int gy = (rows + 127) / 128;
-  if (gy > 64) gy = 64;
-  M3L_CUDA(launch_kernel(ln_param_grad_kernel, dim3(dim3(gx, gy)), dim3(128), 0, (cudaStream_t)stream, (const bf16*)da_bf16, (const bf16*)xhat_bf16,
-                                                                       rows, dim, dgamma, dbeta));
+  const int gx = (dim / 8 + 31) / 32;
+  int gy = (device_sm_count() * 2 + gx - 1) / gx;
+  if (gy > (rows + 31) / 32) gy = (rows + 31) / 32;
+  if (gy < 1) gy = 1;
+  M3L_CUDA(launch_kernel(ln_param_grad_kernel, dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream,
+                         (const bf16*)da_bf16, (const bf16*)xhat_bf16, rows, dim, dgamma, dbeta));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

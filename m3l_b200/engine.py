@@ -329,8 +329,11 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
 # --------------------------------------------------------------------------------------------
 # masked-autoencoder forward / backward
 # --------------------------------------------------------------------------------------------
-def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geometry, training: bool):
-    """Returns (loss_acc fp32[1], ctx).  ctx holds what mae_backward needs (None if not training)."""
+def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geometry, training: bool,
+                gflat: Optional[torch.Tensor] = None):
+    """Returns (loss_acc fp32[1], ctx).  ctx holds what mae_backward needs (None if not training).
+    gflat: the (zeroed) flat gradient buffer the backward pass will use; when given, the MSE kernel
+    already accumulates the head bias gradients (column sums of dpred) into it."""
     cfg, A = model.cfg, model.arena
     dev = A.device
     B = noise.shape[0]
@@ -362,22 +365,26 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
                                          out_rows=B * geo.nm, dst_row=mrow, want_stats=training)
     loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
     heads = []
+    G = GradView(A, gflat) if (training and gflat is not None) else None
     r_img = B * geo.nm_img
     if geo.nt:
         g_tac = gathered[r_img:]
         pred = ops.gemm(g_tac, A.bf("to_tactiles.weight"), bias=A.f32("to_tactiles.bias"), out_dtype=torch.float32)
         ps = ops.make_patch_source([x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac, geo.n_img)
-        dpred = ops.mse_loss(ps, B, geo.nm_tac_total, pred, 10.0 / pred.numel(), loss_acc, tok_idx=masked, col0=geo.nm_img)
+        dpred = ops.mse_loss(ps, B, geo.nm_tac_total, pred, 10.0 / pred.numel(), loss_acc, tok_idx=masked, col0=geo.nm_img,
+                             dpred_colsum=G("to_tactiles.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_tactiles", g_tac, dpred, r_img))
     if geo.use_vision:
         g_img = gathered[:r_img]
         pred = ops.gemm(g_img, A.bf("to_pixels.weight"), bias=A.f32("to_pixels.bias"), out_dtype=torch.float32)
         ps = ops.make_patch_source([x["image"]], model.ph_img, model.pw_img, 0)
-        dpred = ops.mse_loss(ps, B, geo.nm_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=masked, col0=0)
+        dpred = ops.mse_loss(ps, B, geo.nm_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=masked, col0=0,
+                             dpred_colsum=G("to_pixels.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_pixels", g_img, dpred, 0))
     if training:
         ctx.update(tabs=tabs, slots=slots, mrow=mrow, emb=emb_saved, enc=enc_saved, xe=xe, st_enc=st_enc,
-                   enc_out=enc_out, dec=dec_saved, xd=xd, st_dec=st_dec, heads=heads, n_gathered=gathered.shape[0])
+                   enc_out=enc_out, dec=dec_saved, xd=xd, st_dec=st_dec, heads=heads, n_gathered=gathered.shape[0],
+                   gflat_fwd=gflat)
     return loss_acc, ctx
 
 
@@ -388,8 +395,10 @@ def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
     geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
     Dd = cfg.decoder_dim
     dgath = torch.empty((ctx["n_gathered"], Dd), dtype=torch.bfloat16, device=A.device)
+    bias_done = ctx.get("gflat_fwd") is gflat and gflat is not None   # fused into the MSE kernel
     for name, g_in, dpred, row0 in ctx["heads"]:
-        ops.colsum(dpred, G(name + ".bias"))
+        if not (bias_done and dpred.shape[1] <= 1024):
+            ops.colsum(dpred, G(name + ".bias"))
         wgrad(dpred, g_in, G(name + ".weight"))
         ops.gemm(dpred, A.bf_t(name + ".weight"), out=dgath[row0:row0 + g_in.shape[0]])
     dxd = ops.layernorm_bwd(dgath, ctx["xd"], ctx["st_dec"], A.f32("decoder.norm.weight"),

@@ -73,7 +73,7 @@ class FusedTrainer:
     def _phase_a(self, xs, noise, geo, box):
         self.gflat.zero_()
         self.state[1:2].zero_()
-        loss_acc, ctx = engine.mae_forward(self.model, xs, noise, geo, training=True)
+        loss_acc, ctx = engine.mae_forward(self.model, xs, noise, geo, training=True, gflat=self.gflat)
         engine.mae_backward_decoder(self.model, ctx, self.gflat)
         box["loss"], box["ctx"] = loss_acc, ctx
 

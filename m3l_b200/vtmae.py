@@ -408,14 +408,19 @@ class _MAEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, xs, noise, geo, live, *params):
         need = any(ctx.needs_input_grad)
-        loss_acc, c = engine.mae_forward(model, xs, noise, geo, training=need)
+        gflat = model.arena.new_grad_buffer() if need else None
+        loss_acc, c = engine.mae_forward(model, xs, noise, geo, training=need, gflat=gflat)
         ctx.model, ctx.c, ctx.live = model, c, live
         return loss_acc.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
         model, A = ctx.model, ctx.model.arena
-        gflat = A.new_grad_buffer()
+        # the buffer the forward pass put the head bias gradients into (first backward only)
+        gflat = ctx.c.get("gflat_fwd")
+        if gflat is None or ctx.c.get("gflat_used"):
+            gflat = A.new_grad_buffer()
+        ctx.c["gflat_used"] = True
         engine.mae_backward_decoder(model, ctx.c, gflat)
         engine.mae_backward_encoder(model, ctx.c, gflat)
         gflat.mul_(gout)

@@ -276,6 +276,26 @@ def test_mse_loss_and_grad(ops):
     l.backward()
     assert abs(acc.item() - l.item()) < 1e-5 * abs(l.item())
     assert rel_err(dpred, pr.grad) < 1e-2
+    # fused bias gradient (column sums of dpred) + tactile geometry (two sensors, 4x4 patches, ragged grid)
+    cs = torch.ones(768, device=DEV)
+    acc2 = torch.zeros(1, device=DEV)
+    dpred2 = ops.mse_loss(ps, B, nm, pred, w, acc2, tok_idx=idx, dpred_colsum=cs)
+    assert torch.equal(dpred2, dpred) and acc2.item() == acc.item()       # deterministic
+    assert rel_err(cs, 1 + pr.grad.sum(0)) < 1e-4
+    t1, t2 = torch.rand(B, 12, 32, 32, device=DEV), torch.rand(B, 12, 32, 32, device=DEV)
+    pst = ops.make_patch_source([t1, t2], 4, 4, token_base=64)
+    nmt = 122
+    idt = torch.stack([torch.randperm(128)[:nmt] + 64 for _ in range(B)]).to(DEV)
+    predt = torch.randn(B * nmt, 192, device=DEV)
+    acct, cst = torch.zeros(1, device=DEV), torch.zeros(192, device=DEV)
+    wt = 10.0 / predt.numel()
+    dpt = ops.mse_loss(pst, B, nmt, predt, wt, acct, tok_idx=idt, dpred_colsum=cst)
+    tg = torch.cat([_patchify(t1, 4, 4), _patchify(t2, 4, 4)], 1)[torch.arange(B, device=DEV)[:, None], idt - 64].reshape(B * nmt, 192)
+    prt = predt.clone().requires_grad_(True)
+    lt = 10 * F.mse_loss(prt, tg)
+    lt.backward()
+    assert abs(acct.item() - lt.item()) < 1e-5 * abs(lt.item())
+    assert rel_err(dpt, prt.grad) < 1e-2 and rel_err(cst, prt.grad.sum(0)) < 1e-4
 
 
 # ------------------------------------------------------------------------------------ optimizer
