@@ -53,6 +53,9 @@ typedef struct m3l_gemm_args {
   int32_t ld_aux;
   float alpha;        /* must be 1 */
   float* colsum_out;  /* fp32 [n] or NULL: += column sums of the bf16 output (fused bias gradient) */
+  const void* dot_side; /* bf16 [m, ld_dot] or NULL (bf16 output, no residual / act; n % 64 == 0): */
+  int32_t ld_dot;       /*   dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]        */
+  float* dot_out;       /* fp32 [m, n/64]: with out = dO and dot_side = O this is FlashAttention's delta */
 } m3l_gemm_args;
 
 int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);
@@ -171,9 +174,11 @@ int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int 
  * ---------------------------------------------------------------------------------------- */
 int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int heads, int dim_head, float scale,
                       void* out_bf16, float* lse, void* stream);
+/* delta: fp32 [batch*n, heads] = rowsum(dO * O) per head, or NULL (computed in the kernel from out/dout);
+ * m3l_gemm_bf16 produces it for free in the epilogue of the GEMM that computes dO (dot_side / dot_out). */
 int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                      const float* lse, int batch, int n, int heads, int dim_head, float scale,
-                      void* dqkv_bf16, void* stream);
+                      const float* lse, const float* delta, int batch, int n, int heads, int dim_head,
+                      float scale, void* dqkv_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer over flat fp32 arenas: clip_grad_norm_(params, max_norm) + AdamW.step()

@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p),
         ("ld_aux", C.c_int32), ("alpha", C.c_float), ("colsum_out", C.c_void_p),
+        ("dot_side", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
     ]
 
 

@@ -16,6 +16,8 @@
 //   backward, CTA = (sample, head), loops over the 128-query tiles:
 //     S = Q K^T -> P = exp(S*scale - LSE) -> smem ; dP = dO V^T -> dS = P (dP - delta) scale -> smem
 //     dQ_t = dS K ; dV += P^T dO ; dK += dS^T Q   (P / dS slabs double as MN-major A operands)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "m3l_internal.h"
 
@@ -69,6 +71,7 @@ struct AttnFwdParams {
   float* lse;
   int n, heads, inner, q_tiles, tile_rows, num_items, kv_bufs, slot_cols;
   float scale;
+  long long* prof;   // M3L_ATTN_PROF: cycle counters of CTA 0 (measurement only)
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -192,6 +195,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const float sl2 = p.scale * kLog2e;
     const int nchunks = (NK + 31) / 32;
     int it = 0, jt = 0;
+    long long pf_ws = 0, pf_p1 = 0, pf_p2 = 0, pf_wo = 0, pf_ep = 0, pf_n = 0;
+    const long long pf_t0 = clock64();
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int h = item % p.heads, b = item / p.heads;
       for (int t = 0; t < p.q_tiles; ++t, ++jt) {
@@ -200,8 +205,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int grow = t * p.tile_rows + row;
         const bool warp_active = (quad * 32 < p.tile_rows) && (t * p.tile_rows + quad * 32 < n);
         const bool valid = row < p.tile_rows && grow < n;
+        long long c0 = clock64();
         mbar_wait(&bars->s_full[wg], ph);
         tc_fence_after_sync();
+        long long c1 = clock64(); pf_ws += c1 - c0;
         float mx = -INFINITY, sum = 0.f;
         if (warp_active) {
           for (int c = 0; c < nchunks; ++c) {
@@ -213,6 +220,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
           const float mxs = mx * sl2;
+          { long long c2 = clock64(); pf_p1 += c2 - c1; c1 = c2; }
           for (int c = 0; c < nchunks; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(t_row + c * 32, v);
@@ -240,9 +248,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[wg]);
+        { long long c2 = clock64(); pf_p2 += c2 - c1; c1 = c2; }
         // ---- epilogue
         mbar_wait(&bars->o_full[wg], ph);
         tc_fence_after_sync();
+        { long long c2 = clock64(); pf_wo += c2 - c1; c1 = c2; }
         if (warp_active) {
           const float inv = 1.0f / sum;
           uint32_t o0[32], o1[32];
@@ -270,7 +280,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         tc_fence_before_sync();
         mbar_arrive(&bars->slot_free[wg]);
+        { long long c2 = clock64(); pf_ep += c2 - c1; pf_n += 1; }
       }
+    }
+    if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
+      p.prof[0] = pf_ws; p.prof[1] = pf_p1; p.prof[2] = pf_p2; p.prof[3] = pf_wo; p.prof[4] = pf_ep;
+      p.prof[5] = pf_n; p.prof[6] = clock64() - pf_t0;
     }
   }
   tc_fence_before_sync();
@@ -294,7 +309,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 //               K-major (dQ) and MN-major (dV, dK) operands.  Group 0 drains dV_j / dQ_0, group 1 dK_j / dQ_1.
 // ------------------------------------------------------------------------------------------
 struct AttnBwdBars {
-  uint64_t kv_full[2], kv_empty[2], qdo_full, qdo_empty, sdp_full, pds_full, dkv_full, dkv_free, item_done;
+  uint64_t kv_full[2], kv_empty[2], qdo_full, qdo_empty, sdp_full, sdp_free, pds_full, pds_free, dkv_full, dkv_free,
+      item_done;
   uint32_t tmem_base;
 };
 
@@ -302,9 +318,11 @@ struct AttnBwdParams {
   const bf16* o;
   const bf16* dout;
   const float* lse;
+  const float* delta;   // [batch*n, heads] precomputed rowsum(dO * O), or nullptr
   bf16* dqkv;
   int n, heads, inner, q_tiles, key_tiles, num_items, kv_bufs;
   float scale;
+  long long* prof;   // M3L_ATTN_PROF: cycle counters of CTA 0 (measurement only)
 };
 
 M3L_DEVINL void store_row64(bf16* dst, const uint32_t (&a0)[32], const uint32_t (&a1)[32]) {
@@ -356,7 +374,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(&bars->qdo_full, 1);
     mbar_init(&bars->qdo_empty, 1);
     mbar_init(&bars->sdp_full, 1);
+    mbar_init(&bars->sdp_free, 256);
     mbar_init(&bars->pds_full, 256);
+    mbar_init(&bars->pds_free, 1);
     mbar_init(&bars->dkv_full, 1);
     mbar_init(&bars->dkv_free, 256);
     mbar_init(&bars->item_done, 256);
@@ -403,34 +423,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t idesc_dkv = umma_idesc_bf16(128, kDh, 1, 1);    // both MN-major
       const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       int it = 0, st = 0, dk = 0;
+      long long m_wload = 0, m_wfree = 0, m_isdp = 0, m_wpds = 0, m_wacc = 0, m_imma = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
         const uint32_t kph = (it / p.kv_bufs) & 1;
+        long long mc = clock64();
         mbar_wait(&bars->kv_full[kb], kph);
         mbar_wait(&bars->qdo_full, it & 1);
         tc_fence_after_sync();
+        { long long c2 = clock64(); m_wload += c2 - mc; mc = c2; }
         const uint32_t k_base = smem_u32(sKV + kb * 2 * kv_region), v_base = k_base + kv_region;
-        for (int j = 0; j < p.key_tiles; ++j) {
+        // S / dP of step (j, i):  S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T
+        auto issue_sdp = [&](int j, int i) {
           const int nkj = min(128, NK - j * 128);                    // valid (padded) keys of this tile
           const uint32_t idesc_s = umma_idesc_bf16(128, nkj, 0, 0);
           const uint32_t kj = k_base + j * 128 * 128, vj = v_base + j * 128 * 128;
+          const uint32_t qi = q_base + i * 16384, doi = do_base + i * 16384;
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColS, umma_smem_desc(qi + k * 32, 16, 1024),
+                      umma_smem_desc(kj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < kDh / 16; ++k)
+            umma_bf16(tmem_base + kColDP, umma_smem_desc(doi + k * 32, 16, 1024),
+                      umma_smem_desc(vj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&bars->sdp_full);
+        };
+        // the S / dP columns are free once the producers hold the previous step's values in registers
+        if (st > 0) mbar_wait(&bars->sdp_free, (st - 1) & 1);
+        tc_fence_after_sync();
+        { long long c2 = clock64(); m_wfree += c2 - mc; mc = c2; }
+        issue_sdp(0, 0);
+        { long long c2 = clock64(); m_isdp += c2 - mc; mc = c2; }
+        for (int j = 0; j < p.key_tiles; ++j) {
+          const int nkj = min(128, NK - j * 128);
+          const uint32_t kj = k_base + j * 128 * 128;
           for (int i = 0; i < p.q_tiles; ++i, ++st) {
             const uint32_t qi = q_base + i * 16384, doi = do_base + i * 16384;
-            // ---- S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T
-#pragma unroll
-            for (int k = 0; k < kDh / 16; ++k)
-              umma_bf16(tmem_base + kColS, umma_smem_desc(qi + k * 32, 16, 1024),
-                        umma_smem_desc(kj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < kDh / 16; ++k)
-              umma_bf16(tmem_base + kColDP, umma_smem_desc(doi + k * 32, 16, 1024),
-                        umma_smem_desc(vj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(&bars->sdp_full);
+            // ---- software pipeline: S / dP of the NEXT step go to the tensor core before the three
+            //      accumulating products of this one, so they are ready when the producers come back
+            const int i2 = (i + 1 == p.q_tiles) ? 0 : i + 1, j2 = (i + 1 == p.q_tiles) ? j + 1 : j;
+            if (j2 < p.key_tiles) {
+              mbar_wait(&bars->sdp_free, st & 1);
+              tc_fence_after_sync();
+              { long long c2 = clock64(); m_wfree += c2 - mc; mc = c2; }
+              issue_sdp(j2, i2);
+              { long long c2 = clock64(); m_isdp += c2 - mc; mc = c2; }
+            }
             // ---- wait for P_ij / dS_ij, then the three accumulating products
             mbar_wait(&bars->pds_full, st & 1);
+            { long long c2 = clock64(); m_wpds += c2 - mc; mc = c2; }
             if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);   // dV/dK accumulators drained
             if (j == 0 && i == 0 && it > 0) mbar_wait(&bars->item_done, (it - 1) & 1);   // dQ accumulators drained
             tc_fence_after_sync();
+            { long long c2 = clock64(); m_wacc += c2 - mc; mc = c2; }
             for (int kk = 0; kk < 128 / 16; ++kk) {                  // contraction over the 128 query rows
               const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
               umma_bf16(tmem_base + kColDV, umma_smem_desc(p_addr + kk * 2048, 16384, 1024),
@@ -442,14 +488,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               umma_bf16(tmem_base + kColDQ + i * 64,
                         umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                         umma_smem_desc(kj + kk * 2048, 8192, 1024), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&bars->pds_free);                            // P / dS slabs may be rewritten
             if (i == p.q_tiles - 1) {
               umma_commit(&bars->dkv_full);
               ++dk;
             }
+            { long long c2 = clock64(); m_imma += c2 - mc; mc = c2; }
           }
         }
         umma_commit(&bars->kv_empty[kb]);
         umma_commit(&bars->qdo_empty);
+      }
+      if (p.prof && blockIdx.x == 0) {
+        p.prof[10] = m_wload; p.prof[11] = m_wfree; p.prof[12] = m_isdp; p.prof[13] = m_wpds; p.prof[14] = m_wacc; p.prof[15] = m_imma;
       }
     }
   } else {
@@ -461,13 +512,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t p_slab = smem_u32(sP + wg * 16384), ds_slab = smem_u32(sDS + wg * 16384);
     const float sl2 = p.scale * kLog2e;
     int it = 0, st = 0, dk = 0;
+    long long pf_delta = 0, pf_wsdp = 0, pf_work = 0, pf_wdkv = 0, pf_epi = 0, pf_dq = 0, pf_n = 0, pf_wfree = 0, pf_sts = 0;
+    const long long pf_t0 = clock64();
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int h = item % p.heads, b = item / p.heads;
+      long long c1 = clock64();
       // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile
       float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
       for (int i = 0; i < p.q_tiles; ++i) {
         const int grow = i * 128 + row;
-        if (grow < n) {
+        if (grow < n && p.delta != nullptr) {
+          delta[i] = p.delta[((size_t)b * n + grow) * p.heads + h];
+          l2[i] = p.lse[((size_t)b * p.heads + h) * n + grow] * kLog2e;
+        } else if (grow < n) {
           const bf16* po = p.o + ((size_t)b * n + grow) * p.inner + h * kDh;
           const bf16* pd = p.dout + ((size_t)b * n + grow) * p.inner + h * kDh;
           float acc = 0.f;
@@ -484,6 +541,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           l2[i] = p.lse[((size_t)b * p.heads + h) * n + grow] * kLog2e;
         }
       }
+      { long long c2 = clock64(); pf_delta += c2 - c1; c1 = c2; }
       for (int j = 0; j < p.key_tiles; ++j) {
         for (int i = 0; i < p.q_tiles; ++i, ++st) {
           const int grow = i * 128 + row;
@@ -494,6 +552,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const float dl = delta[i], lg = l2[i];
           mbar_wait(&bars->sdp_full, st & 1);
           tc_fence_after_sync();
+          { long long c2 = clock64(); pf_wsdp += c2 - c1; c1 = c2; }
+          // P / dS of this thread's (row, 64-key half): TMEM -> registers first, so that the S / dP
+          // columns can be handed back to the tensor core (next step's products) before the math
+          uint32_t pw[32], dw[32];
           if (warp_rows && cols_any) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -501,40 +563,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               tmem_ld_32x32(t_row + kColS + wg * 64 + c * 32, sv);
               tmem_ld_32x32(t_row + kColDP + wg * 64 + c * 32, dv);
               tmem_ld_wait();
+              if (c == 1) {
+                tc_fence_before_sync();
+                mbar_arrive(&bars->sdp_free);
+              }
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float pv[8], ds[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int key = key0 + c * 32 + g * 8 + e;
-                  const float pe = exp2f(fmaf(__uint_as_float(sv[g * 8 + e]), sl2, -lg));
-                  const bool ok = valid && key < n;
-                  pv[e] = ok ? pe : 0.f;
-                  ds[e] = ok ? pe * (__uint_as_float(dv[g * 8 + e]) - dl) * p.scale : 0.f;
-                }
-                uint4 u, w;
-                u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-                u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-                w.x = pack_bf16x2(ds[0], ds[1]); w.y = pack_bf16x2(ds[2], ds[3]);
-                w.z = pack_bf16x2(ds[4], ds[5]); w.w = pack_bf16x2(ds[6], ds[7]);
-                st_swz_chunk(p_slab, row, c * 4 + g, u);
-                st_swz_chunk(ds_slab, row, c * 4 + g, w);
+              for (int e = 0; e < 32; e += 2) {
+                const int key = key0 + c * 32 + e;
+                const float p0 = exp2f(fmaf(__uint_as_float(sv[e]), sl2, -lg));
+                const float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lg));
+                const bool ok0 = valid && key < n, ok1 = valid && key + 1 < n;
+                const float q0 = ok0 ? p0 : 0.f, q1 = ok1 ? p1 : 0.f;
+                pw[c * 16 + (e >> 1)] = pack_bf16x2(q0, q1);
+                dw[c * 16 + (e >> 1)] = pack_bf16x2(q0 * (__uint_as_float(dv[e]) - dl) * p.scale,
+                                                    q1 * (__uint_as_float(dv[e + 1]) - dl) * p.scale);
               }
             }
           } else {
+            tc_fence_before_sync();
+            mbar_arrive(&bars->sdp_free);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              st_swz_chunk(p_slab, row, ch, make_uint4(0, 0, 0, 0));
-              st_swz_chunk(ds_slab, row, ch, make_uint4(0, 0, 0, 0));
-            }
+            for (int e = 0; e < 32; ++e) pw[e] = dw[e] = 0u;
+          }
+          { long long c2 = clock64(); pf_work += c2 - c1; c1 = c2; }
+          // the slabs are still being read by the previous step's dV / dK / dQ products
+          if (st > 0) mbar_wait(&bars->pds_free, (st - 1) & 1);
+          { long long c2 = clock64(); pf_wfree += c2 - c1; c1 = c2; }
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            st_swz_chunk(p_slab, row, ch, make_uint4(pw[4 * ch], pw[4 * ch + 1], pw[4 * ch + 2], pw[4 * ch + 3]));
+            st_swz_chunk(ds_slab, row, ch, make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]));
           }
           fence_proxy_async_smem();
           tc_fence_before_sync();
           mbar_arrive(&bars->pds_full);
+          { long long c2 = clock64(); pf_sts += c2 - c1; c1 = c2; pf_n += 1; }
           if (i == p.q_tiles - 1) {
             // ---- dV_j (group 0) / dK_j (group 1) epilogue
             mbar_wait(&bars->dkv_full, dk & 1);
             tc_fence_after_sync();
+            { long long c2 = clock64(); pf_wdkv += c2 - c1; c1 = c2; }
             const int key = j * 128 + row;
             if (j * 128 + quad * 32 < n) {
               uint32_t a0[32], a1[32];
@@ -549,6 +617,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_before_sync();
             mbar_arrive(&bars->dkv_free);
             ++dk;
+            { long long c2 = clock64(); pf_epi += c2 - c1; c1 = c2; }
           }
         }
       }
@@ -563,6 +632,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       tc_fence_before_sync();
       mbar_arrive(&bars->item_done);
+      { long long c2 = clock64(); pf_dq += c2 - c1; }
+    }
+    if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
+      p.prof[0] = pf_delta; p.prof[1] = pf_wsdp; p.prof[2] = pf_work; p.prof[3] = pf_wdkv; p.prof[4] = pf_epi;
+      p.prof[5] = pf_dq; p.prof[6] = pf_n; p.prof[7] = clock64() - pf_t0; p.prof[8] = pf_wfree; p.prof[9] = pf_sts;
     }
   }
   tc_fence_before_sync();
@@ -770,6 +844,15 @@ attn_small_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
   }
 }
 
+long long* attn_prof_buf() {
+  static long long* buf = [] {
+    long long* b = nullptr;
+    if (getenv("M3L_ATTN_PROF")) { cudaMalloc(&b, 64 * sizeof(long long)); cudaMemset(b, 0, 64 * sizeof(long long)); }
+    return b;
+  }();
+  return buf;
+}
+
 int attn_check(int n, int heads, int dim_head, int batch) {
   M3L_REQUIRE(dim_head == kDh, "attention: dim_head=%d unsupported (only 64)", dim_head);
   M3L_REQUIRE(n >= 1 && n <= 256, "attention: sequence length %d unsupported (1..256)", n);
@@ -811,6 +894,7 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
   if (s) return s;
   AttnFwdParams p;
   p.out = (bf16*)out_bf16; p.lse = lse; p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
+  p.prof = attn_prof_buf();
   p.q_tiles = (n + 127) / 128;
   const int per_tile = (n + p.q_tiles - 1) / p.q_tiles;
   p.tile_rows = std::min(128, (per_tile + 31) & ~31);
@@ -835,8 +919,8 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
 }
 
 extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                                 const float* lse, int batch, int n, int heads, int dim_head, float scale,
-                                 void* dqkv_bf16, void* stream) {
+                                 const float* lse, const float* delta, int batch, int n, int heads, int dim_head,
+                                 float scale, void* dqkv_bf16, void* stream) {
   M3L_REQUIRE(qkv_bf16 && out_bf16 && dout_bf16 && lse && dqkv_bf16, "attention_bwd: null pointer");
   int s = attn_check(n, heads, dim_head, batch);
   if (s) return s;
@@ -865,8 +949,9 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
   s = make_tmap_3d_bf16(&map_do, dout_bf16, inner, n, batch, inner, (uint64_t)n * inner, 128);
   if (s) return s;
   AttnBwdParams p;
-  p.o = (const bf16*)out_bf16; p.dout = (const bf16*)dout_bf16; p.lse = lse; p.dqkv = (bf16*)dqkv_bf16;
+  p.o = (const bf16*)out_bf16; p.dout = (const bf16*)dout_bf16; p.lse = lse; p.delta = delta; p.dqkv = (bf16*)dqkv_bf16;
   p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
+  p.prof = attn_prof_buf();
   p.q_tiles = (n + 127) / 128;
   p.key_tiles = (NK + 127) / 128;
   p.num_items = batch * heads;
@@ -883,5 +968,15 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
   const int grid = std::min(p.num_items, device_sm_count());
   M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_q, map_kv, map_do, p));
   M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+// measurement only (M3L_ATTN_PROF=1): read and reset the in-kernel cycle counters of CTA 0
+extern "C" int m3l_debug_attn_prof(long long* host_out, int n) {
+  long long* b = m3l::attn_prof_buf();
+  if (b == nullptr || n > 64) return M3L_ERR_INVALID;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, b, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(b, 0, 64 * sizeof(long long));
   return M3L_OK;
 }

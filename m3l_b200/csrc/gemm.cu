@@ -286,7 +286,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t stg = smem_u32(staging + ew * kBufs * kStgTileBytes);
     const bool has_bias = (EPI != EPI_GELU_BWD && EPI != EPI_F32_RED) && p.bias != nullptr;
     // side operand (TMA-loaded, result written in place): residual (EPI_BF16) or aux_in (GELU')
-    const bool has_side = kBufs == 2 && ((EPI == EPI_BF16 && p.residual != nullptr) || EPI == EPI_GELU_BWD);
+    const bool has_dot = EPI == EPI_BF16 && p.dot_out != nullptr;    // side = dot operand, output = acc
+    const bool has_side = kBufs == 2 && ((EPI == EPI_BF16 && (p.residual != nullptr || has_dot)) || EPI == EPI_GELU_BWD);
     const bool want_colsum = !kF32 && p.colsum_out != nullptr;
     // fused column sums of the bf16 output (bias gradient): lane accumulates 8 columns (16-byte chunk
     // lane & 7) over the rows = (lane >> 3) mod 4 of every staged tile, in registers while this CTA
@@ -436,13 +437,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t sb = stg + (g & 1) * kStgTileBytes;
             mbar_wait(&bars->side_full[ew][g & 1], (g >> 1) & 1);
             stg_load_row(sb, lane, w);
+            if (has_dot) {
+              // out = acc (rounded to bf16 first: the consumer sees exactly these values); dot over this
+              // round's 64 columns with the side operand (dO . O per head = FlashAttention's delta)
+              float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 s2 = unpack_bf16x2(w[j]);
-              if constexpr (EPI == EPI_GELU_BWD) {   // aux_in holds GELU'(pre-activation)
-                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * s2.x, __uint_as_float(v[2 * j + 1]) * s2.y);
-              } else {
-                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + s2.x, __uint_as_float(v[2 * j + 1]) + s2.y);
+              for (int j = 0; j < 32; ++j) {
+                const float2 s2 = unpack_bf16x2(w[j]);
+                w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                const float2 o2 = unpack_bf16x2(w[j]);
+                dot = fmaf(o2.x, s2.x, dot);
+                dot = fmaf(o2.y, s2.y, dot);
+              }
+              if (row0 + lane < p.M && gcol < p.N) p.dot_out[(size_t)(row0 + lane) * (p.N >> 6) + (gcol >> 6)] = dot;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float2 s2 = unpack_bf16x2(w[j]);
+                if constexpr (EPI == EPI_GELU_BWD) {   // aux_in holds GELU'(pre-activation)
+                  w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * s2.x, __uint_as_float(v[2 * j + 1]) * s2.y);
+                } else {
+                  w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + s2.x, __uint_as_float(v[2 * j + 1]) + s2.y);
+                }
               }
             }
             stg_store_row(sb, lane, w);      // in place: every thread only touches its own row
@@ -569,6 +585,10 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   M3L_REQUIRE(p.ldo % 8 == 0 && (p.residual == nullptr || p.ldr % 8 == 0) &&
                   ((p.aux_in == nullptr && p.aux_out == nullptr) || p.ld_aux % 8 == 0),
               "gemm: output / residual / aux leading dimensions must be multiples of 8");
+  M3L_REQUIRE((p.dot_out == nullptr) == (p.dot_side == nullptr), "gemm: dot_side and dot_out go together");
+  M3L_REQUIRE(p.dot_out == nullptr || (p.out_mode == 0 && p.act == 0 && p.residual == nullptr && p.N % 64 == 0 &&
+                                       p.ld_dot % 8 == 0 && !p.a_mn_major),
+              "gemm: the fused row-dot needs a plain bf16 output with N %% 64 == 0");
   if (bn == 0) bn = gemm_pick_bn(p.M, p.N);
   M3L_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
   plan->bn = bn;
@@ -595,6 +615,8 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
     if ((s = make_tmap_2d_bf16(&plan->map_side, p.aux_in, p.M, p.N, p.ld_aux, 32))) return s;
   } else if (p.residual != nullptr) {
     if ((s = make_tmap_2d_bf16(&plan->map_side, p.residual, p.M, p.N, p.ldr, 32))) return s;
+  } else if (p.dot_out != nullptr) {
+    if ((s = make_tmap_2d_bf16(&plan->map_side, p.dot_side, p.M, p.N, p.ld_dot, 32))) return s;
   }
   const int tiles_n = (p.N + bn - 1) / bn;
   const int tiles = ((p.M + BM - 1) / BM) * tiles_n * p.splits;
@@ -604,7 +626,8 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   // (M3L_GEMM_WS=0 disables it, for A/B measurements)
   static const bool ws_allowed = [] { const char* e = getenv("M3L_GEMM_WS"); return !(e && e[0] == '0'); }();
   plan->ws = ws_allowed && !p.a_mn_major && kb_total <= kWsMaxKb && p.splits == 1 && bn >= 128 &&
-             p.residual == nullptr && p.act != 2 && tiles >= 2 * device_sm_count() && tiles_n <= plan->grid;
+             p.residual == nullptr && p.dot_out == nullptr && p.act != 2 && tiles >= 2 * device_sm_count() &&
+             tiles_n <= plan->grid;
   if (p.colsum_out != nullptr) {
     M3L_REQUIRE(p.out_mode == 0, "gemm: colsum_out needs the bf16 output mode");
     // keep every CTA on one N tile so the column sums stay in registers across its tiles
@@ -638,6 +661,7 @@ extern "C" int m3l_gemm_bf16(const m3l_gemm_args* a, void* stream) {
   g.bias = a->bias; g.residual = (const m3l::bf16*)a->residual; g.ldr = a->ldr;
   g.act = a->act; g.aux_out = (m3l::bf16*)a->aux_out; g.aux_in = (const m3l::bf16*)a->aux_in;
   g.ld_aux = a->ld_aux; g.alpha = a->alpha; g.colsum_out = a->colsum_out;
+  g.dot_side = (const m3l::bf16*)a->dot_side; g.ld_dot = a->ld_dot; g.dot_out = a->dot_out;
   m3l::GemmPlan plan;
   int s = m3l::gemm_make_plan(&plan, g, a->bn);
   if (s) return s;

@@ -26,6 +26,9 @@ struct GemmArgs {
   int ld_aux = 0;
   float alpha = 1.0f;
   float* colsum_out = nullptr;  // [N] fp32: += column sums of the (bf16) output, e.g. the bias gradient
+  const bf16* dot_side = nullptr;   // [M, ld_dot] bf16: dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]
+  int ld_dot = 0;
+  float* dot_out = nullptr;         // [M, N/64] fp32
 };
 
 struct GemmPlan {

@@ -136,6 +136,7 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
     The producer of dx (the final-LayerNorm backward) must already have accumulated its column sums
     into G(last_ff_bias(spec)) (dx_colsum= of ops.layernorm_bwd)."""
     scale = spec.dim_head ** -0.5
+    M = dx.shape[0]
     fork = WgradFork(A.device)
     for l in reversed(range(spec.depth)):
         pa, pf = f"{spec.prefix}.layers.{l}.0", f"{spec.prefix}.layers.{l}.1"
@@ -150,8 +151,10 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
                                    dbeta=G(pf + ".net.0.bias"), skip=dx, dx_colsum=G(pa + ".to_out.0.bias"))
         # ---- attention branch: x_mid = x + Wo attn(Wqkv LN1(x)) + bo
         fork.wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
-        do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"))
-        dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale)
+        # dO, and in the same epilogue delta = rowsum(dO * O) per head (dim_head == 64 == one epilogue round)
+        delta = torch.empty((M, spec.heads), dtype=torch.float32, device=dx.device) if spec.dim_head == 64 else None
+        do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"), dot_side=o if delta is not None else None, dot_out=delta)
+        dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale, delta=delta)
         fork.wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
         dxn1 = ops.gemm(dqkv, A.bf_t(pa + ".to_qkv.weight"))
         prev_bias = G(f"{spec.prefix}.layers.{l - 1}.1.net.4.bias") if l > 0 else None

@@ -41,7 +41,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
          out_dtype: torch.dtype = torch.bfloat16, accumulate: bool = False, splits: int = 1, bn: int = 0,
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None,
-         alpha: float = 1.0, colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         alpha: float = 1.0, colsum_out: Optional[torch.Tensor] = None,
+         dot_side: Optional[torch.Tensor] = None, dot_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[m, n] = epilogue(alpha * sum_k A[m, k] B[n, k]).
 
     mn_major=False: a is [M, K], b is [N, K] (nn.Linear forward: x @ W.T).
@@ -81,6 +82,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
     args.ld_aux = aux.stride(0) if aux is not None else 0
     args.alpha = alpha
     args.colsum_out = ptr(colsum_out)
+    if dot_side is not None:
+        assert dot_side.dtype == torch.bfloat16 and dot_side.stride(1) == 1 and dot_side.shape == (M, N)
+        assert dot_out is not None and dot_out.dtype == torch.float32 and dot_out.is_contiguous() and dot_out.shape == (M, N // 64)
+        args.dot_side, args.ld_dot, args.dot_out = ptr(dot_side), dot_side.stride(0), ptr(dot_out)
     check(_lib.load().m3l_gemm_bf16(C.byref(args), current_stream()), "m3l_gemm_bf16")
     return out
 
@@ -241,11 +246,13 @@ def attention_fwd(qkv, batch, n, heads, dim_head, scale, *, out=None, lse=None):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, batch, n, heads, dim_head, scale, *, dqkv=None):
+def attention_bwd(qkv, out, dout, lse, batch, n, heads, dim_head, scale, *, dqkv=None, delta=None):
+    """delta: optional fp32 [batch*n, heads] = rowsum(dout * out) per head (gemm(dot_side=, dot_out=))."""
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     assert dout.is_contiguous() and out.is_contiguous()
-    check(_lib.load().m3l_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), batch, n, heads, dim_head,
+    assert delta is None or (delta.dtype == torch.float32 and delta.is_contiguous() and delta.shape == (batch * n, heads))
+    check(_lib.load().m3l_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta), batch, n, heads, dim_head,
                                         C.c_float(scale), ptr(dqkv), current_stream()), "m3l_attention_bwd")
     return dqkv
 

@@ -67,6 +67,12 @@ def test_gemm_epilogues(ops):
     g = ops.gemm(a, b, act=ops.GELU_BWD, aux_in=dgelu, colsum_out=cs)
     assert rel_err(g, z * dgelu.float()) < 1e-2
     assert rel_err(cs, 1 + g.float().sum(0)) < 1e-4  # fused bias gradient = column sums of the bf16 output
+    # fused row-dot: out = a @ b.T (bf16), dot[row, c] = sum_j out[row, 64c + j] * side[row, 64c + j]
+    side = torch.randn(M, N, device=DEV).bfloat16()
+    dot = torch.full((M, N // 64), 7.0, device=DEV)
+    o2 = ops.gemm(a, b, dot_side=side, dot_out=dot)
+    assert torch.equal(o2, ops.gemm(a, b))
+    assert rel_err(dot, (o2.float() * side.float()).reshape(M, N // 64, 64).sum(-1)) < 1e-5
     big_a = torch.randn(40000, K, device=DEV).bfloat16()
     cs2 = torch.zeros(N, device=DEV)
     g2 = ops.gemm(big_a, b, colsum_out=cs2, bn=128)
@@ -207,6 +213,10 @@ def test_attention_fwd_bwd(ops, B, n, H):
     for name, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
         assert cos(dqkv[:, sl], qr.grad[:, sl]) > 0.999, name
         assert rel_err(dqkv[:, sl], qr.grad[:, sl]) < 5e-2, name
+    # same with delta = rowsum(dO * O) supplied (the product path: fused into the GEMM that makes dO)
+    delta = (dout.float() * out.float()).reshape(B * n, H, 64).sum(-1).contiguous()
+    dqkv2 = ops.attention_bwd(qkv, out, dout, lse, B, n, H, 64, scale, delta=delta)
+    assert rel_err(dqkv2, dqkv) < 1e-2
 
 
 # ------------------------------------------------------------------- decoder assembly / sums

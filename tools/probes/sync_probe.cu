@@ -36,7 +36,7 @@ __global__ void pingpong(int mode, int iters, long long* out) {
 }
 
 // MMA issue -> commit -> wait, by one thread.  nmma MMAs (128 x N x 16) per iteration.
-__global__ void mma_commit(int nmma, int n, int iters, int use_test_wait, long long* out) {
+__global__ void mma_commit(int nmma, int n, int iters, int use_test_wait, long long* out, int a_mn = 0, int b_mn = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   __shared__ Bars bars;
@@ -49,12 +49,15 @@ __global__ void mma_commit(int nmma, int n, int iters, int use_test_wait, long l
   tc_fence_after_sync();
   const uint32_t tm = bars.tmem;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, n, a_mn, b_mn);
     const uint32_t a = smem_u32(smem), b = a + 16384;
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
-      for (int k = 0; k < nmma; ++k)
-        umma_bf16(tm, umma_smem_desc(a + (k & 3) * 32, 16, 1024), umma_smem_desc(b + (k & 3) * 32, 16, 1024), idesc, k > 0);
+      for (int k = 0; k < nmma; ++k) {
+        const uint64_t ad = a_mn ? umma_smem_desc(a + (k & 3) * 2048, 8192, 1024) : umma_smem_desc(a + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = b_mn ? umma_smem_desc(b + (k & 3) * 2048, 8192, 1024) : umma_smem_desc(b + (k & 3) * 32, 16, 1024);
+        umma_bf16(tm, ad, bd, idesc, k > 0);
+      }
       umma_commit(&bars.a);
       if (use_test_wait) { while (!mbar_test_wait(&bars.a, i & 1)) {} } else { while (!mbar_try_wait(&bars.a, i & 1)) {} }
       tc_fence_after_sync();
@@ -110,6 +113,12 @@ int main() {
       mma_commit<<<1, 128, 64 * 1024>>>(nm, 256, it, tw, d); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       printf("mma x%-2d (128x256x16) + commit + %-9s : %.1f clk per iteration\n", nm, tw ? "test_wait" : "try_wait", (double)h[0] / it);
     }
+  for (int amn = 0; amn < 2; ++amn)
+    for (int bmn = 0; bmn < 2; ++bmn)
+      for (int n : {64, 128, 256}) {
+        mma_commit<<<1, 128, 64 * 1024>>>(16, n, it, 0, d, amn, bmn); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("mma x16 128x%dx16 A %s B %s : %.1f clk per MMA\n", n, amn ? "MN" : "K ", bmn ? "MN" : "K ", ((double)h[0] / it - 319) / 16);
+      }
   for (int warps : {1, 4, 8})
     for (int we = 0; we < 2; ++we) {
       tmem_drain<<<1, warps * 32>>>(256, it, we, d); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
