@@ -301,16 +301,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 //   P_ij = exp(S_ij * scale - LSE_i) and dS_ij = P_ij (dP_ij - delta_i) scale are element-wise given
 //   LSE / delta, so no row-wide pass is needed and S_ij, dP_ij sit in TMEM side by side:
 //     TMEM columns: [0,128) S_ij  [128,256) dP_ij  [256,320) dQ_0  [320,384) dQ_1  [384,448) dV_j  [448,512) dK_j
-//   warp 0      TMA loader (K,V double-buffered across items when they fit; Q / dO tiles per item)
-//   warp 1      MMA issuer: [S, dP](step) ; wait P/dS ; [dV += P^T dO, dK += dS^T Q, dQ += dS K](step)
-//               followed immediately by [S, dP](step+1), so the tensor core never waits for the epilogues
+//   warp 0      TMA loader, running ahead of the tensor core: Q / dO double-buffered across items, the
+//               last key tile's K / V double-buffered, the earlier key tiles single-buffered but released
+//               as soon as their last product is issued (half way through the item)
+//   warp 1      MMA issuer, ONE flat software pipeline over all steps of all items of this CTA:
+//                 [S, dP](step g+1)  is issued as soon as the producers hold step g's values in registers,
+//                 [dV += P^T dO, dK += dS^T Q, dQ += dS K](step g)  once the P / dS slabs are written,
+//               so neither item boundaries nor the producers' math leave the tensor core idle
 //   warps 2..9  two groups of 128 threads; thread = (query row, 64-key half): both read their half of
 //               S and dP from TMEM and write the P and dS slabs (bf16, swizzled) the MMAs consume as
 //               K-major (dQ) and MN-major (dV, dK) operands.  Group 0 drains dV_j / dQ_0, group 1 dK_j / dQ_1.
+//   Measured before this structure (cycle counters, tools/attn_probe.py): 9.3 k clk per step of which the
+//   tensor core was busy 2.7 k; the rest were exposed Q/dO load latency at item starts (4.3 k clk per
+//   item), the delta prologue (4.8 k per item) and hand-offs that serialised math and MMAs.
 // ------------------------------------------------------------------------------------------
 struct AttnBwdBars {
-  uint64_t kv_full[2], kv_empty[2], qdo_full, qdo_empty, sdp_full, sdp_free, pds_full, pds_free, dkv_full, dkv_free,
-      item_done;
+  uint64_t qdo_full[2], qdo_empty[2], kva_full, kva_empty, kvl_full[2], kvl_empty[2];
+  uint64_t sdp_full, sdp_free, pds_full, pds_free, dkv_full, dkv_free, item_done;
   uint32_t tmem_base;
 };
 
@@ -320,7 +327,12 @@ struct AttnBwdParams {
   const float* lse;
   const float* delta;   // [batch*n, heads] precomputed rowsum(dO * O), or nullptr
   bf16* dqkv;
-  int n, heads, inner, q_tiles, key_tiles, num_items, kv_bufs;
+  int n, heads, inner, q_tiles, key_tiles, num_items;
+  int qdo_bufs, kvl_bufs;       // 1 or 2
+  int q_rows[2], q_off[2];      // per query tile: rows loaded (multiple of 64), byte offset in a Q / dO region
+  int k_rows[2];                // per key tile: rows loaded (multiple of 64)
+  int q_region;                 // bytes of one Q (= one dO) region
+  int kva_region, kvl_region;   // bytes of K (= V) of the early key tiles / of the last key tile
   float scale;
   long long* prof;   // M3L_ATTN_PROF: cycle counters of CTA 0 (measurement only)
 };
@@ -343,36 +355,39 @@ M3L_DEVINL void store_row64(bf16* dst, const uint32_t (&a0)[32], const uint32_t 
 }
 
 __global__ void __launch_bounds__(320, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                const __grid_constant__ CUtensorMap map_do, const AttnBwdParams p) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int n = p.n;
   const int NK = (n + 15) & ~15;
-  const int kv_bytes = NK * 128;
-  const int kv_region = (kv_bytes + 1023) & ~1023;
-  uint8_t* sQ = smem;                                 // [2][128 q][64 d]
-  uint8_t* sDO = sQ + 2 * 16384;                      // [2][128 q][64 d]
-  uint8_t* sP = sDO + 2 * 16384;                      // [2 slabs][128 q][64 keys]
-  uint8_t* sDS = sP + 2 * 16384;                      // [2 slabs][128 q][64 keys]
-  uint8_t* sKV = sDS + 2 * 16384;                     // [kv_bufs][K | V]
-  AttnBwdBars* bars = reinterpret_cast<AttnBwdBars*>(sKV + p.kv_bufs * 2 * kv_region);
+  uint8_t* sQ = smem;                                     // [qdo_bufs][q_region]
+  uint8_t* sDO = sQ + p.qdo_bufs * p.q_region;            // [qdo_bufs][q_region]
+  uint8_t* sP = sDO + p.qdo_bufs * p.q_region;            // [2 slabs][128 q][64 keys]
+  uint8_t* sDS = sP + 2 * 16384;                          // [2 slabs][128 q][64 keys]
+  uint8_t* sKA = sDS + 2 * 16384;                         // early key tiles: [K | V], kva_region each
+  uint8_t* sKL = sKA + 2 * p.kva_region;                  // last key tile: [kvl_bufs][K | V]
+  AttnBwdBars* bars = reinterpret_cast<AttnBwdBars*>(sKL + p.kvl_bufs * 2 * p.kvl_region);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 512;
   constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDV = 384, kColDK = 448;
+  const int steps_per_item = p.key_tiles * p.q_tiles;
+  const int my_items = (int)blockIdx.x < p.num_items ? (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int jl = p.key_tiles - 1;                         // the last key tile
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_kv);
+    tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->kv_full[i], 1);
-      mbar_init(&bars->kv_empty[i], 1);
+      mbar_init(&bars->qdo_full[i], 1);
+      mbar_init(&bars->qdo_empty[i], 1);
+      mbar_init(&bars->kvl_full[i], 1);
+      mbar_init(&bars->kvl_empty[i], 1);
     }
-    mbar_init(&bars->qdo_full, 1);
-    mbar_init(&bars->qdo_empty, 1);
+    mbar_init(&bars->kva_full, 1);
+    mbar_init(&bars->kva_empty, 1);
     mbar_init(&bars->sdp_full, 1);
     mbar_init(&bars->sdp_free, 256);
     mbar_init(&bars->pds_full, 256);
@@ -390,94 +405,128 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   pdl_wait();      // prologue above overlapped the predecessor kernel; global memory from here on
   pdl_trigger();
 
+  // buffer selection helpers (identical in all roles)
+  auto qdo_buf = [&](int it) { return p.qdo_bufs == 2 ? (it & 1) : 0; };
+  auto qdo_par = [&](int it) { return (uint32_t)((it / p.qdo_bufs) & 1); };
+  auto kvl_buf = [&](int it) { return p.kvl_bufs == 2 ? (it & 1) : 0; };
+  auto kvl_par = [&](int it) { return (uint32_t)((it / p.kvl_bufs) & 1); };
+
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
     if (lane == 0) {
-      auto load_kv = [&](int it, int item) {
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
         const int h = item % p.heads, b = item / p.heads;
-        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
-        const uint32_t kph = (it / p.kv_bufs) & 1;
-        mbar_wait(&bars->kv_empty[kb], kph ^ 1);
-        uint8_t* k_dst = sKV + kb * 2 * kv_region;
-        mbar_arrive_expect_tx(&bars->kv_full[kb], 2 * kv_bytes);
-        tma_load_3d(k_dst, &map_kv, &bars->kv_full[kb], p.inner + h * kDh, 0, b);
-        tma_load_3d(k_dst + kv_region, &map_kv, &bars->kv_full[kb], 2 * p.inner + h * kDh, 0, b);
-      };
-      int it = 0;
-      if ((int)blockIdx.x < p.num_items) load_kv(0, blockIdx.x);
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int h = item % p.heads, b = item / p.heads;
-        mbar_wait(&bars->qdo_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->qdo_full, p.q_tiles * 2 * 16384);
-        for (int i = 0; i < p.q_tiles; ++i) {
-          tma_load_3d(sQ + i * 16384, &map_q, &bars->qdo_full, h * kDh, i * 128, b);
-          tma_load_3d(sDO + i * 16384, &map_do, &bars->qdo_full, h * kDh, i * 128, b);
+        // Q / dO of the item
+        {
+          const int s = qdo_buf(it);
+          mbar_wait(&bars->qdo_empty[s], qdo_par(it) ^ 1);
+          int bytes = 0;
+          for (int i = 0; i < p.q_tiles; ++i) bytes += 2 * p.q_rows[i] * 128;
+          mbar_arrive_expect_tx(&bars->qdo_full[s], bytes);
+          for (int i = 0; i < p.q_tiles; ++i)
+            for (int r = 0; r < p.q_rows[i]; r += 64) {
+              tma_load_3d(sQ + s * p.q_region + p.q_off[i] + r * 128, &map_qkv, &bars->qdo_full[s], h * kDh, i * 128 + r, b);
+              tma_load_3d(sDO + s * p.q_region + p.q_off[i] + r * 128, &map_do, &bars->qdo_full[s], h * kDh, i * 128 + r, b);
+            }
         }
-        if (item + (int)gridDim.x < p.num_items) load_kv(it + 1, item + gridDim.x);
+        // K / V of the last key tile
+        {
+          const int kb = kvl_buf(it);
+          mbar_wait(&bars->kvl_empty[kb], kvl_par(it) ^ 1);
+          mbar_arrive_expect_tx(&bars->kvl_full[kb], 2 * p.k_rows[jl] * 128);
+          uint8_t* kd = sKL + kb * 2 * p.kvl_region;
+          for (int r = 0; r < p.k_rows[jl]; r += 64) {
+            tma_load_3d(kd + r * 128, &map_qkv, &bars->kvl_full[kb], p.inner + h * kDh, jl * 128 + r, b);
+            tma_load_3d(kd + p.kvl_region + r * 128, &map_qkv, &bars->kvl_full[kb], 2 * p.inner + h * kDh, jl * 128 + r, b);
+          }
+        }
+        // K / V of the early key tiles (single buffer, released half way through the previous item)
+        if (p.key_tiles > 1) {
+          mbar_wait(&bars->kva_empty, (uint32_t)(it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars->kva_full, 2 * jl * 128 * 128);
+          for (int r = 0; r < jl * 128; r += 64) {
+            tma_load_3d(sKA + r * 128, &map_qkv, &bars->kva_full, p.inner + h * kDh, r, b);
+            tma_load_3d(sKA + p.kva_region + r * 128, &map_qkv, &bars->kva_full, 2 * p.inner + h * kDh, r, b);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------
-    if (lane == 0) {
+    if (lane == 0 && my_items > 0) {
       const uint32_t idesc_dq = umma_idesc_bf16(128, kDh, 0, 1);     // A K-major (dS), B MN-major (K)
       const uint32_t idesc_dkv = umma_idesc_bf16(128, kDh, 1, 1);    // both MN-major
-      const uint32_t q_base = smem_u32(sQ), do_base = smem_u32(sDO), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-      int it = 0, st = 0, dk = 0;
-      long long m_wload = 0, m_wfree = 0, m_isdp = 0, m_wpds = 0, m_wacc = 0, m_imma = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int kb = p.kv_bufs == 2 ? (it & 1) : 0;
-        const uint32_t kph = (it / p.kv_bufs) & 1;
-        long long mc = clock64();
-        mbar_wait(&bars->kv_full[kb], kph);
-        mbar_wait(&bars->qdo_full, it & 1);
-        tc_fence_after_sync();
-        { long long c2 = clock64(); m_wload += c2 - mc; mc = c2; }
-        const uint32_t k_base = smem_u32(sKV + kb * 2 * kv_region), v_base = k_base + kv_region;
-        // S / dP of step (j, i):  S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T
-        auto issue_sdp = [&](int j, int i) {
-          const int nkj = min(128, NK - j * 128);                    // valid (padded) keys of this tile
-          const uint32_t idesc_s = umma_idesc_bf16(128, nkj, 0, 0);
-          const uint32_t kj = k_base + j * 128 * 128, vj = v_base + j * 128 * 128;
-          const uint32_t qi = q_base + i * 16384, doi = do_base + i * 16384;
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      auto q_addr = [&](int it, int i) { return smem_u32(sQ + qdo_buf(it) * p.q_region + p.q_off[i]); };
+      auto do_addr = [&](int it, int i) { return smem_u32(sDO + qdo_buf(it) * p.q_region + p.q_off[i]); };
+      auto k_addr = [&](int it, int j) {
+        return j < jl ? smem_u32(sKA + j * 16384) : smem_u32(sKL + kvl_buf(it) * 2 * p.kvl_region);
+      };
+      auto v_addr = [&](int it, int j) {
+        return j < jl ? smem_u32(sKA + p.kva_region + j * 16384)
+                      : smem_u32(sKL + kvl_buf(it) * 2 * p.kvl_region + p.kvl_region);
+      };
+      auto wait_loads = [&](int it) {
+        mbar_wait(&bars->qdo_full[qdo_buf(it)], qdo_par(it));
+        mbar_wait(&bars->kvl_full[kvl_buf(it)], kvl_par(it));
+        if (p.key_tiles > 1) mbar_wait(&bars->kva_full, (uint32_t)(it & 1));
+      };
+      // S / dP of step (it, j, i):  S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T
+      auto issue_sdp = [&](int it, int j, int i) {
+        const int nkj = min(128, NK - j * 128);                      // valid (padded) keys of this tile
+        const uint32_t idesc_s = umma_idesc_bf16(128, nkj, 0, 0);
+        const uint32_t kj = k_addr(it, j), vj = v_addr(it, j), qi = q_addr(it, i), doi = do_addr(it, i);
 #pragma unroll
-          for (int k = 0; k < kDh / 16; ++k)
-            umma_bf16(tmem_base + kColS, umma_smem_desc(qi + k * 32, 16, 1024),
-                      umma_smem_desc(kj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + kColS, umma_smem_desc(qi + k * 32, 16, 1024),
+                    umma_smem_desc(kj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kDh / 16; ++k)
-            umma_bf16(tmem_base + kColDP, umma_smem_desc(doi + k * 32, 16, 1024),
-                      umma_smem_desc(vj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&bars->sdp_full);
-        };
-        // the S / dP columns are free once the producers hold the previous step's values in registers
-        if (st > 0) mbar_wait(&bars->sdp_free, (st - 1) & 1);
-        tc_fence_after_sync();
-        { long long c2 = clock64(); m_wfree += c2 - mc; mc = c2; }
-        issue_sdp(0, 0);
-        { long long c2 = clock64(); m_isdp += c2 - mc; mc = c2; }
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_bf16(tmem_base + kColDP, umma_smem_desc(doi + k * 32, 16, 1024),
+                    umma_smem_desc(vj + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&bars->sdp_full);
+      };
+      // S / dP of the next item's first step can only be issued ahead when that item's operands have
+      // their own buffers
+      const bool cross = p.qdo_bufs == 2 && p.kvl_bufs == 2;
+      int g = 0, dk = 0;                                             // global step / key-tile counters
+      long long m_sdp = 0, m_acc = 0, m_w1 = 0, m_w2 = 0;
+      const bool serial = p.prof != nullptr && p.prof[32] != 0;      // measurement: wait for every batch
+      for (int it = 0; it < my_items; ++it) {
+        if (it == 0 || !cross) {
+          wait_loads(it);
+          if (g > 0) mbar_wait(&bars->sdp_free, (g - 1) & 1);
+          tc_fence_after_sync();
+          issue_sdp(it, 0, 0);
+        }
         for (int j = 0; j < p.key_tiles; ++j) {
           const int nkj = min(128, NK - j * 128);
-          const uint32_t kj = k_base + j * 128 * 128;
-          for (int i = 0; i < p.q_tiles; ++i, ++st) {
-            const uint32_t qi = q_base + i * 16384, doi = do_base + i * 16384;
-            // ---- software pipeline: S / dP of the NEXT step go to the tensor core before the three
-            //      accumulating products of this one, so they are ready when the producers come back
-            const int i2 = (i + 1 == p.q_tiles) ? 0 : i + 1, j2 = (i + 1 == p.q_tiles) ? j + 1 : j;
-            if (j2 < p.key_tiles) {
-              mbar_wait(&bars->sdp_free, st & 1);
+          const uint32_t kj = k_addr(it, j);
+          for (int i = 0; i < p.q_tiles; ++i, ++g) {
+            // ---- S / dP of the next step (possibly the next item's first) go to the tensor core first
+            int it2 = it, j2 = j, i2 = i + 1;
+            if (i2 == p.q_tiles) { i2 = 0; ++j2; }
+            if (j2 == p.key_tiles) { j2 = 0; ++it2; }
+            if (it2 < my_items && (it2 == it || cross)) {
+              if (it2 != it) wait_loads(it2);
+              long long c0 = clock64();
+              mbar_wait(&bars->sdp_free, g & 1);       // the producers hold step g's S / dP in registers
               tc_fence_after_sync();
-              { long long c2 = clock64(); m_wfree += c2 - mc; mc = c2; }
-              issue_sdp(j2, i2);
-              { long long c2 = clock64(); m_isdp += c2 - mc; mc = c2; }
+              long long c1 = clock64(); m_w1 += c1 - c0;
+              issue_sdp(it2, j2, i2);
+              if (serial) { mbar_wait(&bars->sdp_full, (g + 1) & 1); m_sdp += clock64() - c1; }
             }
             // ---- wait for P_ij / dS_ij, then the three accumulating products
-            mbar_wait(&bars->pds_full, st & 1);
-            { long long c2 = clock64(); m_wpds += c2 - mc; mc = c2; }
-            if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);   // dV/dK accumulators drained
+            long long c2 = clock64();
+            mbar_wait(&bars->pds_full, g & 1);
+            long long c3 = clock64(); m_w2 += c3 - c2;
+            if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);               // dV/dK accumulators drained
             if (j == 0 && i == 0 && it > 0) mbar_wait(&bars->item_done, (it - 1) & 1);   // dQ accumulators drained
             tc_fence_after_sync();
-            { long long c2 = clock64(); m_wacc += c2 - mc; mc = c2; }
-            for (int kk = 0; kk < 128 / 16; ++kk) {                  // contraction over the 128 query rows
+            const uint32_t qi = q_addr(it, i), doi = do_addr(it, i);
+            const int qk = p.q_rows[i] / 16;                         // contraction over the loaded query rows
+            for (int kk = 0; kk < qk; ++kk) {
               const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
               umma_bf16(tmem_base + kColDV, umma_smem_desc(p_addr + kk * 2048, 16384, 1024),
                         umma_smem_desc(doi + kk * 2048, 8192, 1024), idesc_dkv, acc);
@@ -492,16 +541,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             if (i == p.q_tiles - 1) {
               umma_commit(&bars->dkv_full);
               ++dk;
+              if (j == jl - 1) umma_commit(&bars->kva_empty);        // last product on the early key tiles
             }
-            { long long c2 = clock64(); m_imma += c2 - mc; mc = c2; }
+            if (serial) { long long c4 = clock64(); mbar_wait(&bars->pds_free, g & 1); m_acc += clock64() - c4; }
           }
         }
-        umma_commit(&bars->kv_empty[kb]);
-        umma_commit(&bars->qdo_empty);
+        umma_commit(&bars->qdo_empty[qdo_buf(it)]);
+        umma_commit(&bars->kvl_empty[kvl_buf(it)]);
       }
-      if (p.prof && blockIdx.x == 0) {
-        p.prof[10] = m_wload; p.prof[11] = m_wfree; p.prof[12] = m_isdp; p.prof[13] = m_wpds; p.prof[14] = m_wacc; p.prof[15] = m_imma;
-      }
+      if (p.prof && blockIdx.x == 0) { p.prof[26] = m_w1; p.prof[27] = m_sdp; p.prof[28] = m_w2; p.prof[29] = m_acc; }
     }
   } else {
     // ------------------------------- P / dS producers + epilogues ------------------------
@@ -511,48 +559,87 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t p_slab = smem_u32(sP + wg * 16384), ds_slab = smem_u32(sDS + wg * 16384);
     const float sl2 = p.scale * kLog2e;
-    int it = 0, st = 0, dk = 0;
-    long long pf_delta = 0, pf_wsdp = 0, pf_work = 0, pf_wdkv = 0, pf_epi = 0, pf_dq = 0, pf_n = 0, pf_wfree = 0, pf_sts = 0;
+    int g = 0, dk = 0;
     const long long pf_t0 = clock64();
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc = pf_t0;
+#define PF(k) { const long long c_ = clock64(); pf[k] += c_ - pc; pc = c_; }
+    // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile; with a
+    // precomputed delta the next item's values are fetched one item ahead
+    float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f}, delta_n[2] = {0.f, 0.f}, l2_n[2] = {0.f, 0.f};
+    auto fetch_stats = [&](int it, float (&d)[2], float (&l)[2]) {
+      const int item = blockIdx.x + it * gridDim.x;
       const int h = item % p.heads, b = item / p.heads;
-      long long c1 = clock64();
-      // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile
-      float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f};
       for (int i = 0; i < p.q_tiles; ++i) {
         const int grow = i * 128 + row;
-        if (grow < n && p.delta != nullptr) {
-          delta[i] = p.delta[((size_t)b * n + grow) * p.heads + h];
-          l2[i] = p.lse[((size_t)b * p.heads + h) * n + grow] * kLog2e;
-        } else if (grow < n) {
-          const bf16* po = p.o + ((size_t)b * n + grow) * p.inner + h * kDh;
-          const bf16* pd = p.dout + ((size_t)b * n + grow) * p.inner + h * kDh;
-          float acc = 0.f;
+        d[i] = 0.f; l[i] = 0.f;
+        if (grow < n) {
+          l[i] = p.lse[((size_t)b * p.heads + h) * n + grow];     // raw: scaled at use, so the load stays in flight
+          if (p.delta != nullptr) {
+            d[i] = p.delta[((size_t)b * n + grow) * p.heads + h];
+          } else {
+            const bf16* po = p.o + ((size_t)b * n + grow) * p.inner + h * kDh;
+            const bf16* pd = p.dout + ((size_t)b * n + grow) * p.inner + h * kDh;
+            float acc = 0.f;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint4 a = *reinterpret_cast<const uint4*>(po + g * 8);
-            const uint4 d = *reinterpret_cast<const uint4*>(pd + g * 8);
-            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-            const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-            acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y +
-                   a3.x * d3.x + a3.y * d3.y;
+            for (int q = 0; q < 8; ++q) {
+              const uint4 a = *reinterpret_cast<const uint4*>(po + q * 8);
+              const uint4 dd = *reinterpret_cast<const uint4*>(pd + q * 8);
+              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+              const float2 d0 = unpack_bf16x2(dd.x), d1 = unpack_bf16x2(dd.y), d2 = unpack_bf16x2(dd.z), d3 = unpack_bf16x2(dd.w);
+              acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y +
+                     a3.x * d3.x + a3.y * d3.y;
+            }
+            d[i] = acc;
           }
-          delta[i] = acc;
-          l2[i] = p.lse[((size_t)b * p.heads + h) * n + grow] * kLog2e;
         }
       }
-      { long long c2 = clock64(); pf_delta += c2 - c1; c1 = c2; }
+    };
+    // dV_j (group 0) / dK_j (group 1) epilogue of a finished key tile.  It is deferred until this thread
+    // has issued the next step's TMEM reads and math: waiting for the tile's last products right after
+    // handing over P / dS left the producers idle for a whole MMA batch every second step.
+    int pend_j = -1, pend_b = 0, pend_h = 0;
+    auto drain_dkv = [&]() {
+      if (pend_j < 0) return;
+      mbar_wait(&bars->dkv_full, dk & 1);
+      tc_fence_after_sync();
+      const int key = pend_j * 128 + row;
+      if (pend_j * 128 + quad * 32 < n) {
+        uint32_t a0[32], a1[32];
+        const uint32_t col = wg == 0 ? kColDV : kColDK;
+        tmem_ld_32x32(t_row + col, a0);
+        tmem_ld_32x32(t_row + col + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->dkv_free);
+        if (key < n)
+          store_row64(p.dqkv + ((size_t)pend_b * n + key) * (3 * p.inner) + (wg == 0 ? 2 : 1) * p.inner + pend_h * kDh,
+                      a0, a1);
+      } else {
+        tc_fence_before_sync();
+        mbar_arrive(&bars->dkv_free);
+      }
+      ++dk;
+      pend_j = -1;
+    };
+    if (my_items > 0) fetch_stats(0, delta_n, l2_n);
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int h = item % p.heads, b = item / p.heads;
+      delta[0] = delta_n[0]; delta[1] = delta_n[1]; l2[0] = l2_n[0]; l2[1] = l2_n[1];
+      if (it + 1 < my_items) fetch_stats(it + 1, delta_n, l2_n);
+      PF(0)
       for (int j = 0; j < p.key_tiles; ++j) {
-        for (int i = 0; i < p.q_tiles; ++i, ++st) {
+        for (int i = 0; i < p.q_tiles; ++i, ++g) {
           const int grow = i * 128 + row;
           const bool valid = grow < n;
           const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
           const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
           const bool cols_any = key0 < n;
-          const float dl = delta[i], lg = l2[i];
-          mbar_wait(&bars->sdp_full, st & 1);
+          mbar_wait(&bars->sdp_full, g & 1);
           tc_fence_after_sync();
-          { long long c2 = clock64(); pf_wsdp += c2 - c1; c1 = c2; }
+          PF(1)
+          const float dl = delta[i], lg = l2[i] * kLog2e;
           // P / dS of this thread's (row, 64-key half): TMEM -> registers first, so that the S / dP
           // columns can be handed back to the tensor core (next step's products) before the math
           uint32_t pw[32], dw[32];
@@ -585,10 +672,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 32; ++e) pw[e] = dw[e] = 0u;
           }
-          { long long c2 = clock64(); pf_work += c2 - c1; c1 = c2; }
+          PF(2)
+          drain_dkv();
+          PF(5)
           // the slabs are still being read by the previous step's dV / dK / dQ products
-          if (st > 0) mbar_wait(&bars->pds_free, (st - 1) & 1);
-          { long long c2 = clock64(); pf_wfree += c2 - c1; c1 = c2; }
+          if (g > 0) mbar_wait(&bars->pds_free, (g - 1) & 1);
+          PF(3)
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             st_swz_chunk(p_slab, row, ch, make_uint4(pw[4 * ch], pw[4 * ch + 1], pw[4 * ch + 2], pw[4 * ch + 3]));
@@ -597,46 +686,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           fence_proxy_async_smem();
           tc_fence_before_sync();
           mbar_arrive(&bars->pds_full);
-          { long long c2 = clock64(); pf_sts += c2 - c1; c1 = c2; pf_n += 1; }
-          if (i == p.q_tiles - 1) {
-            // ---- dV_j (group 0) / dK_j (group 1) epilogue
-            mbar_wait(&bars->dkv_full, dk & 1);
-            tc_fence_after_sync();
-            { long long c2 = clock64(); pf_wdkv += c2 - c1; c1 = c2; }
-            const int key = j * 128 + row;
-            if (j * 128 + quad * 32 < n) {
-              uint32_t a0[32], a1[32];
-              const uint32_t col = wg == 0 ? kColDV : kColDK;
-              tmem_ld_32x32(t_row + col, a0);
-              tmem_ld_32x32(t_row + col + 32, a1);
-              tmem_ld_wait();
-              if (key < n)
-                store_row64(p.dqkv + ((size_t)b * n + key) * (3 * p.inner) + (wg == 0 ? 2 : 1) * p.inner + h * kDh,
-                            a0, a1);
-            }
-            tc_fence_before_sync();
-            mbar_arrive(&bars->dkv_free);
-            ++dk;
-            { long long c2 = clock64(); pf_epi += c2 - c1; c1 = c2; }
-          }
+          PF(4)
+          if (i == p.q_tiles - 1) { pend_j = j; pend_b = b; pend_h = h; }   // dV_j / dK_j drained during the next step
         }
       }
       // ---- dQ epilogue: group w drains query tile w (the last dkv_full commit covered every MMA)
+      drain_dkv();
+      PF(6)
       if (wg < p.q_tiles && (wg * 128 + quad * 32) < n) {
         uint32_t a0[32], a1[32];
         tmem_ld_32x32(t_row + kColDQ + wg * 64, a0);
         tmem_ld_32x32(t_row + kColDQ + wg * 64 + 32, a1);
         tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->item_done);
         const int grow = wg * 128 + row;
         if (grow < n) store_row64(p.dqkv + ((size_t)b * n + grow) * (3 * p.inner) + h * kDh, a0, a1);
+      } else {
+        tc_fence_before_sync();
+        mbar_arrive(&bars->item_done);
       }
-      tc_fence_before_sync();
-      mbar_arrive(&bars->item_done);
-      { long long c2 = clock64(); pf_dq += c2 - c1; }
+      PF(7)
     }
-    if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
-      p.prof[0] = pf_delta; p.prof[1] = pf_wsdp; p.prof[2] = pf_work; p.prof[3] = pf_wdkv; p.prof[4] = pf_epi;
-      p.prof[5] = pf_dq; p.prof[6] = pf_n; p.prof[7] = clock64() - pf_t0; p.prof[8] = pf_wfree; p.prof[9] = pf_sts;
+#undef PF
+    if (p.prof && blockIdx.x == 0 && (warp == 2 || warp == 7) && lane == 0) {
+      const int o = warp == 2 ? 0 : 16;
+      for (int k = 0; k < 8; ++k) p.prof[o + k] = pf[k];
+      p.prof[o + 8] = g;
+      p.prof[o + 9] = clock64() - pf_t0;
     }
   }
   tc_fence_before_sync();
@@ -847,7 +924,12 @@ attn_small_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
 long long* attn_prof_buf() {
   static long long* buf = [] {
     long long* b = nullptr;
-    if (getenv("M3L_ATTN_PROF")) { cudaMalloc(&b, 64 * sizeof(long long)); cudaMemset(b, 0, 64 * sizeof(long long)); }
+    if (getenv("M3L_ATTN_PROF")) {
+      cudaMalloc(&b, 64 * sizeof(long long));
+      cudaMemset(b, 0, 64 * sizeof(long long));
+      const long long flag = getenv("M3L_ATTN_SERIAL") ? 1 : 0;     // [32]: wait for every MMA batch
+      cudaMemcpy(b + 32, &flag, sizeof(flag), cudaMemcpyHostToDevice);
+    }
     return b;
   }();
   return buf;
@@ -940,33 +1022,46 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
     M3L_CUDA(cudaGetLastError());
     return M3L_OK;
   }
-  const int NK = (n + 15) & ~15;
-  CUtensorMap map_q, map_kv, map_do;
-  s = make_tmap_3d_bf16(&map_q, qkv_bf16, 3 * inner, n, batch, 3 * inner, (uint64_t)n * 3 * inner, 128);
+  CUtensorMap map_qkv, map_do;
+  s = make_tmap_3d_bf16(&map_qkv, qkv_bf16, 3 * inner, n, batch, 3 * inner, (uint64_t)n * 3 * inner, 64);
   if (s) return s;
-  s = make_tmap_3d_bf16(&map_kv, qkv_bf16, 3 * inner, n, batch, 3 * inner, (uint64_t)n * 3 * inner, NK);
-  if (s) return s;
-  s = make_tmap_3d_bf16(&map_do, dout_bf16, inner, n, batch, inner, (uint64_t)n * inner, 128);
+  s = make_tmap_3d_bf16(&map_do, dout_bf16, inner, n, batch, inner, (uint64_t)n * inner, 64);
   if (s) return s;
   AttnBwdParams p;
   p.o = (const bf16*)out_bf16; p.dout = (const bf16*)dout_bf16; p.lse = lse; p.delta = delta; p.dqkv = (bf16*)dqkv_bf16;
   p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
   p.prof = attn_prof_buf();
   p.q_tiles = (n + 127) / 128;
-  p.key_tiles = (NK + 127) / 128;
+  p.key_tiles = p.q_tiles;
   p.num_items = batch * heads;
-  const int kv_region = (NK * 128 + 1023) & ~1023;
-  const int fixed = 1024 + 8 * 16384 + 256;
-  p.kv_bufs = (fixed + 2 * 2 * kv_region <= 227 * 1024) ? 2 : 1;
-  const int smem = fixed + p.kv_bufs * 2 * kv_region;
-  M3L_REQUIRE(smem <= 227 * 1024, "attention_bwd: shared memory budget exceeded (n=%d)", n);
+  p.q_region = 0;
+  for (int i = 0; i < 2; ++i) {
+    const int rows = i < p.q_tiles ? std::min(128, ((n - 128 * i) + 63) & ~63) : 0;   // 64-row TMA boxes
+    p.q_rows[i] = rows; p.k_rows[i] = rows;
+    p.q_off[i] = p.q_region;
+    p.q_region += rows * 128;
+  }
+  const int jl = p.key_tiles - 1;
+  p.kva_region = jl * 16384;
+  p.kvl_region = p.k_rows[jl] * 128;
+  // a query tile of 64 loaded rows is still read as a 128-row MMA operand: the over-read must stay inside
+  // the Q / dO regions (the P slabs follow them)
+  const int fixed = 1024 + 4 * 16384 + 2 * p.kva_region + 512;
+  int smem = 0;
+  p.qdo_bufs = p.kvl_bufs = 0;
+  const int tries[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};
+  for (int t = 0; t < 4 && p.qdo_bufs == 0; ++t) {
+    const int need = fixed + tries[t][0] * 2 * p.q_region + tries[t][1] * 2 * p.kvl_region;
+    if (need <= 227 * 1024) { p.qdo_bufs = tries[t][0]; p.kvl_bufs = tries[t][1]; smem = need; }
+  }
+  M3L_REQUIRE(p.qdo_bufs != 0, "attention_bwd: shared memory budget exceeded (n=%d)", n);
   static bool configured = false;
   if (!configured) {
     M3L_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int grid = std::min(p.num_items, device_sm_count());
-  M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_q, map_kv, map_do, p));
+  M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_qkv, map_do, p));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
@@ -977,6 +1072,6 @@ extern "C" int m3l_debug_attn_prof(long long* host_out, int n) {
   if (b == nullptr || n > 64) return M3L_ERR_INVALID;
   cudaDeviceSynchronize();
   cudaMemcpy(host_out, b, n * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemset(b, 0, 64 * sizeof(long long));
+  cudaMemset(b, 0, 32 * sizeof(long long));
   return M3L_OK;
 }
