@@ -163,6 +163,12 @@ int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void*
 int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int dim, float* dgamma,
                       float* dbeta, void* stream);
 
+/* Token mean of the rollout feature extractor (MAEExtractor.forward: torch.mean(tokens, dim=1),
+ * pretrain_models.py:837) and its backward.  x bf16 [batch, n_tokens, dim] -> out fp32 [batch, dim];
+ * dout fp32 [batch, dim] -> dx bf16 [batch, n_tokens, dim] (= dout / n_tokens on every token). */
+int m3l_token_mean_fwd(const void* x_bf16, int batch, int n_tokens, int dim, float* out, void* stream);
+int m3l_token_mean_bwd(const float* dout, int batch, int n_tokens, int dim, void* dx_bf16, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention, sequence length n <= 256, dim_head == 64 (tcgen05 / TMEM / TMA).
  * Replaces vit_pytorch Attention's softmax(q k^T * scale) v and its backward

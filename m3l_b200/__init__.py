@@ -8,7 +8,7 @@ from ._lib import M3LError  # noqa: F401
 
 
 def __getattr__(name):
-    if name in ("VTT", "VTMAE", "EarlyCNN", "Transformer", "pair"):
+    if name in ("VTT", "VTMAE", "EarlyCNN", "Transformer", "MAEExtractor", "pair"):
         from . import vtmae
         return getattr(vtmae, name)
     if name == "vt_load":

@@ -1050,6 +1050,56 @@ __global__ void ln_param_grad_kernel(const bf16* __restrict__ dA, const bf16* __
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 8. token mean (MAEExtractor: torch.mean(tokens, dim=1), pretrain_models.py:837) and its backward
+//    fwd: out[b, :] = mean_t x[b, t, :]   (bf16 in, fp32 out; one warp per (sample, 256-column slab))
+//    bwd: dx[b, t, :] = dout[b, :] / n    (fp32 in, bf16 out)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+token_mean_fwd_kernel(const bf16* __restrict__ x, int B, int n, int D, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int slabs = (D + 255) / 256;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= B * slabs) return;
+  const int b = w / slabs, col = (w - b * slabs) * 256 + lane * 8;
+  if (col >= D) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const bf16* p = x + (size_t)b * n * D + col;
+#pragma unroll 4
+  for (int t = 0; t < n; ++t) {
+    float v[8];
+    load8<bf16>(p + (size_t)t * D, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+  const float inv = 1.0f / n;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  store8(out + (size_t)b * D + col, acc);
+}
+
+__global__ void __launch_bounds__(256)
+token_mean_bwd_kernel(const float* __restrict__ dout, int B, int n, int D, bf16* __restrict__ dx) {
+  pdl_wait();
+  pdl_trigger();
+  const int chunks = D >> 3;
+  const size_t total = (size_t)B * n * chunks;
+  const float inv = 1.0f / n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    const int b = (int)(i / ((size_t)n * chunks));
+    float v[8];
+    load8<float>(dout + (size_t)b * D + ch * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= inv;
+    store8(dx + i * 8, v);
+  }
+}
+
 PatchSrc make_patch_src(const m3l_patch_source* s) {
   PatchSrc ps;
   for (int i = 0; i < 4; ++i) ps.src[i] = s->src[i];
@@ -1330,6 +1380,30 @@ extern "C" int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int
   if (gy < 1) gy = 1;
   M3L_CUDA(launch_kernel(ln_param_grad_kernel, dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream,
                          (const bf16*)da_bf16, (const bf16*)xhat_bf16, rows, dim, dgamma, dbeta));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_token_mean_fwd(const void* x_bf16, int batch, int n_tokens, int dim, float* out, void* stream) {
+  M3L_REQUIRE(x_bf16 && out, "token_mean_fwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0 && n_tokens > 0, "token_mean_fwd: dim %d must be a multiple of 8", dim);
+  if (batch == 0) return M3L_OK;
+  const int warps = batch * ((dim + 255) / 256);
+  M3L_CUDA(launch_kernel(token_mean_fwd_kernel, dim3((warps + 7) / 8), dim3(256), 0, (cudaStream_t)stream,
+                         (const bf16*)x_bf16, batch, n_tokens, dim, out));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_token_mean_bwd(const float* dout, int batch, int n_tokens, int dim, void* dx_bf16, void* stream) {
+  M3L_REQUIRE(dout && dx_bf16, "token_mean_bwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0 && n_tokens > 0, "token_mean_bwd: dim %d must be a multiple of 8", dim);
+  if (batch == 0) return M3L_OK;
+  const size_t total = (size_t)batch * n_tokens * (dim / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)device_sm_count() * 8) blocks = (size_t)device_sm_count() * 8;
+  M3L_CUDA(launch_kernel(token_mean_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dout, batch,
+                         n_tokens, dim, (bf16*)dx_bf16));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

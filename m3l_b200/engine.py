@@ -203,15 +203,20 @@ class Geometry:
         return self.nm_img + self.nm_tac_total
 
 
-def make_geometry(cfg, use_vision: bool, use_tactile: bool) -> Geometry:
+def make_geometry(cfg, use_vision: bool, use_tactile: bool, reconstruct_ratio: Optional[float] = None) -> Geometry:
     nt = cfg.num_tactiles if (cfg.num_tactiles > 0 and use_tactile) else 0
     n_img = cfg.n_img if use_vision else 0
     n_tac = cfg.n_tac if nt else 0
     n = n_img + nt * n_tac
-    # Python-float truncations exactly as pretrain_models.py:223-227
-    num_masked = int(cfg.masking_ratio * n)
-    nm_img = int(num_masked * (n_img / n))
-    nm_tac = (num_masked - nm_img) // cfg.num_tactiles if nt else 0
+    if reconstruct_ratio is None:
+        # Python-float truncations exactly as pretrain_models.py:223-227
+        num_masked = int(cfg.masking_ratio * n)
+        nm_img = int(num_masked * (n_img / n))
+        nm_tac = (num_masked - nm_img) // cfg.num_tactiles if nt else 0
+    else:
+        # reconstruct() splits per modality instead (pretrain_models.py:425,433)
+        nm_img = int(reconstruct_ratio * n_img) if n_img else 0
+        nm_tac = int(reconstruct_ratio * (nt * n_tac) / cfg.num_tactiles) if nt else 0
     segs = ([(0, n_img, nm_img)] if n_img else []) + [(n_img + i * n_tac, n_tac, nm_tac) for i in range(nt)]
     return Geometry(use_vision, nt, n_img, n_tac, nm_img, nm_tac, segs)
 
@@ -333,7 +338,7 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
 # masked-autoencoder forward / backward
 # --------------------------------------------------------------------------------------------
 def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geometry, training: bool,
-                gflat: Optional[torch.Tensor] = None):
+                gflat: Optional[torch.Tensor] = None, capture: Optional[dict] = None):
     """Returns (loss_acc fp32[1], ctx).  ctx holds what mae_backward needs (None if not training).
     gflat: the (zeroed) flat gradient buffer the backward pass will use; when given, the MSE kernel
     already accumulates the head bias gradients (column sums of dpred) into it."""
@@ -377,6 +382,8 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
         dpred = ops.mse_loss(ps, B, geo.nm_tac_total, pred, 10.0 / pred.numel(), loss_acc, tok_idx=masked, col0=geo.nm_img,
                              dpred_colsum=G("to_tactiles.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_tactiles", g_tac, dpred, r_img))
+        if capture is not None:
+            capture["pred_tactile"] = pred
     if geo.use_vision:
         g_img = gathered[:r_img]
         pred = ops.gemm(g_img, A.bf("to_pixels.weight"), bias=A.f32("to_pixels.bias"), out_dtype=torch.float32)
@@ -384,6 +391,8 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
         dpred = ops.mse_loss(ps, B, geo.nm_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=masked, col0=0,
                              dpred_colsum=G("to_pixels.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_pixels", g_img, dpred, 0))
+        if capture is not None:
+            capture["pred_image"] = pred
     if training:
         ctx.update(tabs=tabs, slots=slots, mrow=mrow, emb=emb_saved, enc=enc_saved, xe=xe, st_enc=st_enc,
                    enc_out=enc_out, dec=dec_saved, xd=xd, st_dec=st_dec, heads=heads, n_gathered=gathered.shape[0],

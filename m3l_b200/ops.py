@@ -230,6 +230,26 @@ def ln_param_grad(da, xhat, dgamma, dbeta):
                                         current_stream()), "m3l_ln_param_grad")
 
 
+def token_mean_fwd(x, batch, n_tokens):
+    """x bf16 [batch*n_tokens, dim] -> fp32 [batch, dim] (mean over the tokens of each sample)."""
+    _req_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[0] == batch * n_tokens
+    out = torch.empty((batch, x.shape[1]), dtype=torch.float32, device=x.device)
+    check(_lib.load().m3l_token_mean_fwd(ptr(x), batch, n_tokens, x.shape[1], ptr(out), current_stream()),
+          "m3l_token_mean_fwd")
+    return out
+
+
+def token_mean_bwd(dout, batch, n_tokens):
+    """dout fp32 [batch, dim] -> dx bf16 [batch*n_tokens, dim]."""
+    _req_cuda(dout)
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.shape[0] == batch
+    dx = torch.empty((batch * n_tokens, dout.shape[1]), dtype=torch.bfloat16, device=dout.device)
+    check(_lib.load().m3l_token_mean_bwd(ptr(dout), batch, n_tokens, dout.shape[1], ptr(dx), current_stream()),
+          "m3l_token_mean_bwd")
+    return dx
+
+
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------

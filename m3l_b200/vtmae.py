@@ -322,10 +322,10 @@ class VTMAE(nn.Module):
             names.append(k)
         return names
 
-    def _prep_inputs(self, x, use_vision, use_tactile):
+    def _prep_inputs(self, x, use_vision, use_tactile, reconstruct_ratio=None):
         if 'image' not in x:
             use_vision = False
-        geo = engine.make_geometry(self.cfg, use_vision, use_tactile)
+        geo = engine.make_geometry(self.cfg, use_vision, use_tactile, reconstruct_ratio)
         if self.early_conv_masking:
             raise M3LError("early_conv_masking=True is not implemented in the kernel path yet (DESIGN.md: next)")
         xs = {}
@@ -361,9 +361,53 @@ class VTMAE(nn.Module):
         live = self.live_param_names(geo, False)
         return _EmbFn.apply(self, xs, geo, B, tuple(live), *[A.params[k] for k in live])
 
-    def reconstruct(self, x, mask_ratio=None, use_vision=True, use_tactile=True):
-        raise M3LError("reconstruct() (visualisation helper, pretrain_models.py:344-586) is not part of the "
-                       "accelerated hot path yet; see DESIGN.md")
+    @torch.no_grad()
+    def reconstruct(self, x, mask_ratio=None, use_vision=True, use_tactile=True, noise=None):
+        """Visualisation helper (pretrain_models.py:344-586): masks `int(mask_ratio * 64)` patches PER MODALITY
+        (a different split rule from forward()), runs encoder + decoder + heads through the kernels and
+        returns the reference's dict: image_rec / image_masked (masked patches = 0.5) / recon_loss_image,
+        tactile_rec / tactile_masked (masked patches = inf) / recon_loss_tactile.  The patch <-> map
+        rearrangements of the outputs are torch indexing ops (not on the hot path); values are detached."""
+        if mask_ratio is None:
+            mask_ratio = self.masking_ratio
+        A = self._sync()
+        xs, geo, B = self._prep_inputs(x, use_vision, use_tactile, reconstruct_ratio=mask_ratio)
+        if noise is None:
+            noise = torch.rand(B, geo.n, device=A.device)
+        noise = noise.to(device=A.device, dtype=torch.float32).contiguous()
+        assert noise.shape == (B, geo.n), f"noise must be ({B}, {geo.n})"
+        cap = {}
+        engine.mae_forward(self, xs, noise, geo, training=False, capture=cap)
+        masked = self.last_masked_indices
+        br = torch.arange(B, device=A.device)[:, None]
+        e = self.encoder
+        out = {}
+        if geo.use_vision:
+            gh, gw = e.image_height // self.ph_img, e.image_width // self.pw_img
+            patches = self.image_to_patch(xs['image'])
+            mi = masked[:, :geo.nm_img]
+            pred = cap["pred_image"].view(B, geo.nm_img, -1)
+            out['recon_loss_image'] = torch.nn.functional.mse_loss(pred, patches[br, mi])
+            vis, rec = patches.clone(), patches.clone()
+            vis[br, mi] = 0.5
+            rec[br, mi] = pred
+            unp = lambda t: t.reshape(B, gh, gw, self.ph_img, self.pw_img, -1).permute(0, 5, 1, 3, 2, 4).reshape(
+                B, -1, gh * self.ph_img, gw * self.pw_img)       # 'b (h w) (p1 p2 c) -> b c (h p1) (w p2)'
+            out['image_rec'], out['image_masked'] = unp(rec), unp(vis)
+        if geo.nt:
+            gh, gw = e.tactile_height // self.ph_tac, e.tactile_width // self.pw_tac
+            patches = torch.cat([self.tactile_to_patch(xs[f'tactile{i + 1}']) for i in range(geo.nt)], dim=1)
+            mt = masked[:, geo.nm_img:] - geo.n_img
+            pred = cap["pred_tactile"].view(B, geo.nm_tac_total, -1)
+            out['recon_loss_tactile'] = torch.nn.functional.mse_loss(pred, patches[br, mt])
+            vis, rec = patches.clone(), patches.clone()
+            vis[br, mt] = float('inf')
+            rec[br, mt] = pred
+            unp = lambda t: t.reshape(B, geo.nt, gh, gw, self.ph_tac, self.pw_tac, -1).permute(0, 1, 6, 2, 4, 3, 5).reshape(
+                B, -1, gh * self.ph_tac, gw * self.pw_tac)       # 'b (n h w) (p1 p2 c) -> b (n c) (h p1) (w p2)'
+            out['tactile_rec'], out['tactile_masked'] = unp(rec), unp(vis)
+        order = ['image_rec', 'image_masked', 'recon_loss_image', 'tactile_rec', 'tactile_masked', 'recon_loss_tactile']
+        return {k: out[k] for k in order if k in out}
 
     def initialize_training(self, train_args):
         """pretrain_models.py:670-676: AdamW(lr) + batch size; the optimizer is the fused flat-arena one."""
@@ -402,6 +446,99 @@ class VTMAE(nn.Module):
             xd = {k: v.to(self.mask_token.device, non_blocking=True) for k, v in xd.items()}
             self.train_step(xd)
         self.eval()
+
+
+# --------------------------------------------------------------------------------------------
+# rollout feature extractor (pretrain_models.py:788-841)
+# --------------------------------------------------------------------------------------------
+try:                                       # SB3 only reads `.features_dim`; it is optional here
+    from stable_baselines3.common.torch_layers import BaseFeaturesExtractor as _ExtractorBase
+except Exception:                          # pragma: no cover - SB3 is not part of this image
+    class _ExtractorBase(nn.Module):
+        def __init__(self, observation_space, features_dim: int = 0):
+            super().__init__()
+            assert features_dim > 0
+            self._observation_space = observation_space
+            self._features_dim = features_dim
+
+        @property
+        def features_dim(self) -> int:
+            return self._features_dim
+
+
+class MAEExtractor(_ExtractorBase):
+    """SB3 features extractor of the PPO / SAC policies: obs dict -> MAE encoder over all tokens (no
+    masking) -> one extra transformer block (`vit_layer.transformer`) -> mean over tokens -> (B, dim).
+    Same constructor and attributes as the reference (pretrain_models.py:788-841); `vit_layer` is a
+    full VTT of which only `.transformer` is used (its other parameters exist in the state_dict and
+    never receive gradients, as in the reference).  The whole chain runs as one kernel sequence
+    (bf16 hand-off between the encoder, the extra block and the token mean) and is differentiable
+    w.r.t. the MAE and the extra block, as the PPO / SAC losses need (ppo_mae.py:280,340)."""
+
+    def __init__(self, observation_space, mae_model, dim_embeddings, vision_only_control, frame_stack) -> None:
+        super().__init__(observation_space, dim_embeddings)
+        self.flatten = nn.Flatten()
+        self.mae_model = mae_model
+        self.running_buffer = {}
+        self.vision_only_control = vision_only_control
+        self.frame_stack = frame_stack
+        self.vit_layer = VTT(image_size=(64, 64), tactile_size=(32, 32), image_patch_size=8, tactile_patch_size=4,
+                             dim=dim_embeddings, depth=1, heads=4, mlp_dim=dim_embeddings * 2, num_tactiles=2)
+
+    def forward(self, observations):
+        from .data import vt_load
+        mae = self.mae_model
+        dev = mae.mask_token.device
+        obs = {k: torch.as_tensor(v).to(dev) for k, v in observations.items() if k in ('image', 'tactile')}
+        if 'image' in obs and obs['image'].dim() == 5:            # (B, F, H, W, 3) -> (B, H, W, 3F)
+            im = obs['image'].permute(0, 2, 3, 1, 4)
+            obs['image'] = im.reshape(im.shape[0], im.shape[1], im.shape[2], -1)
+        if 'tactile' in obs and obs['tactile'].dim() == 5:        # (B, F, 6, h, w) -> (B, 6F, h, w)
+            t = obs['tactile']
+            obs['tactile'] = t.reshape(t.shape[0], -1, t.shape[3], t.shape[4])
+        vt = vt_load(obs, frame_stack=self.frame_stack)
+        mae.train()                                               # get_embeddings(eval=False) side effect (:590-593)
+        A = mae._sync()
+        xs, geo, B = mae._prep_inputs(vt, True, not self.vision_only_control)
+        tr = self.vit_layer.transformer
+        if tr.p_drop > 0 and tr.training:
+            raise M3LError("dropout > 0 in training mode is not supported by the fused kernels")
+        Av = tr._own_arena()
+        live = mae.live_param_names(geo, False)
+        vit_names = list(Av.names)
+        out = _ExtractorFn.apply(self, xs, geo, B, tuple(live), tuple(vit_names),
+                                 *[A.params[k] for k in live], *[Av.params[k] for k in vit_names])
+        return self.flatten(out)
+
+
+class _ExtractorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ext, xs, geo, B, live, vit_names, *params):
+        mae, tr = ext.mae_model, ext.vit_layer.transformer
+        Av = tr._arena
+        need = any(ctx.needs_input_grad)
+        emb, c = engine.embeddings_forward(mae, xs, geo, B, training=need)
+        spec = engine.StackSpec("t", tr.dim, tr.depth, tr.heads, tr.dim_head, tr.mlp_dim)
+        saved = [] if need else None
+        xe = engine.stack_fwd(Av, spec, emb, B, geo.n, saved)
+        y, st = ops.layernorm_fwd(xe, Av.f32("t.norm.weight"), Av.f32("t.norm.bias"), want_stats=need)
+        out = ops.token_mean_fwd(y, B, geo.n)
+        ctx.c = (mae, Av, spec, c, saved, xe, st, B, geo.n, live, vit_names)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        mae, Av, spec, c, saved, xe, st, B, n, live, vit_names = ctx.c
+        A = mae.arena
+        dy = ops.token_mean_bwd(gout.to(torch.float32).contiguous(), B, n)
+        gv = Av.new_grad_buffer()
+        Gv = engine.GradView(Av, gv)
+        dxe = ops.layernorm_bwd(dy, xe, st, Av.f32("t.norm.weight"), dgamma=Gv("t.norm.weight"), dbeta=Gv("t.norm.bias"),
+                                dx_colsum=Gv(engine.last_ff_bias(spec)))
+        demb = engine.stack_bwd(Av, Gv, spec, dxe, B, n, saved)
+        gm = A.new_grad_buffer()
+        engine.embeddings_backward(mae, c, demb, gm)
+        return (None, None, None, None, None, None, *[A.view(gm, k) for k in live], *[Av.view(gv, k) for k in vit_names])
 
 
 class _MAEFn(torch.autograd.Function):

@@ -354,6 +354,81 @@ def vtmae_forward(sd, cfg: VTMAEConfig, x: dict, noise: torch.Tensor, use_vision
     return loss
 
 
+def mask_counts_reconstruct(mask_ratio: float, n_img: int, n_tac_total: int, num_tactiles: int):
+    """reconstruct() masks per modality (pretrain_models.py:425,433) - a different rule from forward()."""
+    nm_img = int(mask_ratio * n_img) if n_img else 0
+    nm_tac = int(mask_ratio * n_tac_total / num_tactiles) if n_tac_total else 0
+    return nm_img, nm_tac
+
+
+def unpatchify_image(p, gh, gw, ph, pw):
+    """Rearrange('b (h w) (p1 p2 c) -> b c (h p1) (w p2)') (pretrain_models.py:463-465)."""
+    b = p.shape[0]
+    return p.reshape(b, gh, gw, ph, pw, -1).permute(0, 5, 1, 3, 2, 4).reshape(b, -1, gh * ph, gw * pw)
+
+
+def unpatchify_tactile(p, n, gh, gw, ph, pw):
+    """Rearrange('b (n h w) (p1 p2 c) -> b (n c) (h p1) (w p2)') (pretrain_models.py:476-478)."""
+    b = p.shape[0]
+    return p.reshape(b, n, gh, gw, ph, pw, -1).permute(0, 1, 6, 2, 4, 3, 5).reshape(b, -1, gh * ph, gw * pw)
+
+
+def vtmae_reconstruct(sd, cfg: VTMAEConfig, x: dict, noise: torch.Tensor, mask_ratio=None, use_vision=True,
+                      use_tactile=True):
+    """VTMAE.reconstruct (pretrain_models.py:344-586), early_conv_masking=False path, mask noise supplied
+    externally (image, tactile1, tactile2 order as the torch.rand calls at :426,439)."""
+    assert not cfg.early_conv_masking
+    if mask_ratio is None:
+        mask_ratio = cfg.masking_ratio
+    tokens, img_patches, tac_patches, use_vision, has_tac = _tokens(sd, cfg, x, use_vision, use_tactile)
+    b, n, _ = tokens.shape
+    n_img, n_tac_total = img_patches.shape[1], tac_patches.shape[1]
+    nt = cfg.num_tactiles if has_tac else 0
+    n_tac = n_tac_total // nt if nt else 0
+    nm_img, nm_tac = mask_counts_reconstruct(mask_ratio, n_img, n_tac_total, cfg.num_tactiles)
+    masked, unmasked = mask_indices(noise, n_img, n_tac, nt, nm_img, nm_tac)
+    masked_img, masked_tac = masked[:, :nm_img], masked[:, nm_img:]
+    br = torch.arange(b)[:, None]
+    encoded = transformer(tokens[br, unmasked], sd, "encoder.transformer", cfg.depth, cfg.heads, cfg.dim_head)
+    dec_tok = linear(encoded, sd, "enc_to_dec") if "enc_to_dec.weight" in sd else encoded
+    Dd = cfg.decoder_dim
+    mask_tokens = sd["mask_token"][None, None, :].expand(b, masked.shape[1], Dd)
+    if not cfg.use_sincosmod_encodings:
+        dec_tok = dec_tok + sd["decoder_pos_emb.weight"][unmasked]
+        mask_tokens = mask_tokens + sd["decoder_pos_emb.weight"][masked]
+    z = torch.zeros(b, n, Dd).index_put((br, unmasked), dec_tok).index_put((br, masked), mask_tokens)
+    if cfg.use_sincosmod_encodings:
+        mod = sd["decoder_modality_embedding.weight"]
+        parts = []
+        if use_vision:
+            parts.append(z[:, :n_img] + mod[0] + sd["image_dec_pos_embedding"])
+        if has_tac:
+            zt = torch.cat([z[:, n_img + i * n_tac:n_img + (i + 1) * n_tac] + mod[1 + i] for i in range(nt)], dim=1)
+            parts.append(zt + sd["tactile_dec_pos_embedding"])
+        z = torch.cat(parts, dim=1)
+    decoded = transformer(z, sd, "decoder", cfg.decoder_depth, cfg.decoder_heads, cfg.decoder_dim_head)
+    out = {}
+    if use_vision:
+        (H, W), (ph, pw) = _pair(cfg.image_size), _pair(cfg.image_patch_size)
+        pred = linear(decoded[br, masked_img], sd, "to_pixels")
+        vis, rec = img_patches.clone(), img_patches.clone()
+        vis[br, masked_img] = 0.5
+        rec[br, masked_img] = pred
+        out["image_rec"] = unpatchify_image(rec, H // ph, W // pw, ph, pw)
+        out["image_masked"] = unpatchify_image(vis, H // ph, W // pw, ph, pw)
+        out["recon_loss_image"] = F.mse_loss(pred, img_patches[br, masked_img])
+    if has_tac:
+        (H, W), (ph, pw) = _pair(cfg.tactile_size), _pair(cfg.tactile_patch_size)
+        pred = linear(decoded[br, masked_tac], sd, "to_tactiles")
+        vis, rec = tac_patches.clone(), tac_patches.clone()
+        vis[br, masked_tac - n_img] = float("inf")
+        rec[br, masked_tac - n_img] = pred
+        out["tactile_rec"] = unpatchify_tactile(rec, nt, H // ph, W // pw, ph, pw)
+        out["tactile_masked"] = unpatchify_tactile(vis, nt, H // ph, W // pw, ph, pw)
+        out["recon_loss_tactile"] = F.mse_loss(pred, tac_patches[br, masked_tac - n_img])
+    return out
+
+
 def extractor_forward(sd_mae, cfg: VTMAEConfig, sd_vit, observations: dict, vision_only_control=False):
     """MAEExtractor.forward (pretrain_models.py:819-841): 5-D obs -> (B, dim).
     `sd_vit` holds the extra 1-layer `vit_layer.transformer` (dim, 1, 4, 64, 2*dim)."""

@@ -270,6 +270,17 @@ def test_rowclass_colsum_lnparam(ops):
     assert rel_err(dg, (da.float() * xh.float()).sum(0)) < 1e-4 and rel_err(db, da.float().sum(0)) < 1e-4
 
 
+def test_token_mean(ops):
+    torch.manual_seed(12)
+    B, n, D = 37, 192, 256
+    x = torch.randn(B * n, D, device=DEV).bfloat16()
+    out = ops.token_mean_fwd(x, B, n)
+    assert rel_err(out, x.float().reshape(B, n, D).mean(1)) < 1e-5
+    g = torch.randn(B, D, device=DEV)
+    dx = ops.token_mean_bwd(g, B, n)
+    assert rel_err(dx, (g / n)[:, None, :].expand(B, n, D).reshape(B * n, D)) < 1e-2
+
+
 def test_mse_loss_and_grad(ops):
     torch.manual_seed(10)
     B, nm = 7, 60

@@ -49,6 +49,27 @@ def test_forward_backward_and_embeddings_match_reference(ecm, nt, sincos):
                                mae.get_embeddings(x, eval=False, use_tactile=False))
 
 
+@pytest.mark.parametrize("nt,sincos,ratio", [(2, True, None), (2, False, 0.5), (0, True, 0.8)])
+def test_reconstruct_matches_reference(nt, sincos, ratio):
+    """VTMAE.reconstruct (pretrain_models.py:344-586): per-modality mask counts, rec / masked maps, losses."""
+    cfg = O.VTMAEConfig(num_tactiles=nt, use_sincosmod_encodings=sincos, depth=2, decoder_depth=1)
+    mae = R.build_reference_model(cfg, seed=5)
+    sd = O.canonical({k: v.clone() for k, v in mae.state_dict().items()})
+    g = torch.Generator().manual_seed(11)
+    B = 3
+    x = {"image": torch.rand(B, 12, 64, 64, generator=g)}
+    for i in range(nt):
+        x[f"tactile{i + 1}"] = torch.rand(B, 12, 32, 32, generator=g)
+    noise = O.tie_free_noise(B, cfg.n_img + nt * cfg.n_tac, g, [64] * (1 + nt))
+    with torch.no_grad():
+        mine = O.vtmae_reconstruct(sd, cfg, x, noise, mask_ratio=ratio)
+        with R.injected_noise(R.split_noise(noise, cfg, True, nt > 0)):
+            ref = mae.reconstruct({k: v.clone() for k, v in x.items()}, mask_ratio=ratio)
+    assert list(mine) == list(ref)
+    for k in ref:
+        assert torch.equal(mine[k], ref[k]), k
+
+
 def test_vt_load_matches_reference():
     ref = R.load_reference_module()
     import numpy as np

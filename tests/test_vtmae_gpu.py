@@ -148,6 +148,75 @@ def test_standalone_transformer_matches_oracle():
         assert cos(p.grad, sd["transformer." + k].grad) >= 0.999, k
 
 
+@pytest.mark.parametrize("nt,ratio", [(2, None), (2, 0.5), (0, 0.8)])
+def test_reconstruct_vs_oracle(nt, ratio):
+    """VTMAE.reconstruct (pretrain_models.py:344-586): same dict, same masked patches, reconstruction close."""
+    cfg = O.VTMAEConfig(num_tactiles=nt, depth=2, decoder_depth=2)
+    sd = O.init_state_dict(cfg, seed=6)
+    gen = torch.Generator().manual_seed(8)
+    B = 3
+    x = {"image": torch.rand(B, 12, 64, 64, generator=gen)}
+    for i in range(nt):
+        x[f"tactile{i + 1}"] = torch.rand(B, 12, 32, 32, generator=gen)
+    noise = O.tie_free_noise(B, cfg.n_img + nt * cfg.n_tac, gen, [64] * (1 + nt))
+    mae = build_product(cfg, weights=sd)
+    out = mae.reconstruct(to_dev(x), mask_ratio=ratio, noise=noise.to(DEV))
+    with torch.no_grad():
+        ref = O.vtmae_reconstruct(sd, cfg, x, noise, mask_ratio=ratio)
+    assert list(out) == list(ref)
+    for k in ref:
+        a, b = out[k].cpu(), ref[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        if k.endswith("_masked"):
+            assert torch.equal(a, b), k                       # pure data movement + constants: bit-exact
+        elif k.startswith("recon_loss"):
+            assert abs(float(a) - float(b)) <= 1e-2 * abs(float(b)), (k, float(a), float(b))
+        else:
+            assert cos(a, b) >= 0.9995 and (a - b).abs().max() < 5e-2, (k, cos(a, b), float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("vision_only", [False, True])
+def test_mae_extractor_vs_oracle(vision_only):
+    """MAEExtractor.forward (pretrain_models.py:819-841): raw 5-D observations -> (B, dim) features, and the
+    gradients the PPO / SAC losses send through it into the extra block and the MAE encoder."""
+    from m3l_b200 import MAEExtractor
+    cfg = O.VTMAEConfig(depth=2)
+    sd = O.init_state_dict(cfg, seed=4)
+    gen = torch.Generator().manual_seed(6)
+    B, F_ = 3, cfg.frame_stack
+    obs = {"image": torch.rand(B, F_, 64, 64, 3, generator=gen),
+           "tactile": torch.rand(B, F_, 6, 32, 32, generator=gen) * 2 - 1}
+    mae = build_product(cfg, weights=sd)
+    torch.manual_seed(9)
+    ext = MAEExtractor(None, mae, cfg.dim, vision_only, F_).to(DEV)
+    assert ext.features_dim == cfg.dim
+    sd_vit = {"transformer." + k: v.detach().cpu().clone() for k, v in ext.vit_layer.transformer.state_dict().items()}
+    w = torch.randn(B, cfg.dim, generator=gen)
+    feats = ext({k: v.clone().to(DEV) for k, v in obs.items()})
+    assert feats.shape == (B, cfg.dim) and feats.dtype == torch.float32 and mae.training
+    (feats * w.to(DEV)).sum().backward()
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    for v in sd_vit.values():
+        v.requires_grad_(True)
+    ref = O.extractor_forward(sd, cfg, sd_vit, {k: v.clone() for k, v in obs.items()}, vision_only_control=vision_only)
+    (ref * w).sum().backward()
+    assert cos(feats, ref.detach()) >= 0.9995
+    for k, p in ext.vit_layer.transformer.named_parameters():
+        assert cos(p.grad, sd_vit["transformer." + k].grad) >= 0.999, k
+    assert all(p.grad is None for k, p in ext.vit_layer.named_parameters() if not k.startswith("transformer."))
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    for k in O.param_keys(sd):
+        if sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0:
+            assert named[k].grad is None, k
+        else:
+            assert cos(named[k].grad, sd[k].grad) >= 0.999, (k, cos(named[k].grad, sd[k].grad))
+    # rollout use: no autograd
+    with torch.no_grad():
+        f2 = ext({k: v.clone().to(DEV) for k, v in obs.items()})
+    assert torch.equal(f2, feats.detach())
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_fused_train_steps_vs_oracle(use_graph):
     """zero_grad + fwd + bwd + clip(0.5) + AdamW (pretrain_models.py:707-711): loss trajectory and
