@@ -47,7 +47,7 @@ typedef struct m3l_gemm_args {
   const void* residual; /* bf16 [m, ldr] or NULL; added after the activation (may alias out) */
   int32_t ldr;
   int32_t act;        /* 0 none; 1 exact-erf GELU (its derivative GELU'(pre-activation) stored to
-                         aux_out if non-NULL); 2 multiply by aux_in[m, n] (backward of 1) */
+                         aux_out if non-NULL); 2 multiply by aux_in[m, n] (backward of 1); 3 ReLU */
   void* aux_out;      /* bf16 [m, ld_aux] or NULL */
   const void* aux_in; /* bf16 [m, ld_aux] or NULL */
   int32_t ld_aux;
@@ -162,6 +162,32 @@ int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void*
 /* dgamma[p] += sum_r da[r,p] * xhat[r,p]; dbeta[p] += sum_r da[r,p] (patch LayerNorm parameters). */
 int m3l_ln_param_grad(const void* da_bf16, const void* xhat_bf16, int rows, int dim, float* dgamma,
                       float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EarlyCNN conv stem (early_conv_masking=True; pretrain_models.py:37-56,180-191).  Convolutions are
+ * im2col + m3l_gemm_bf16 (act 3 = ReLU); activations are NHWC bf16, i.e. [batch*H*W, C] matrices.
+ *   im2col       col[(b,oy,ox), ci*k*k + ky*k + kx] = x[b, ci, oy*stride-pad+ky, ox*stride-pad+kx] (0 outside);
+ *                x is fp32 NCHW (x_nhwc_bf16 = 0: the raw maps) or bf16 NHWC (= 1); the K order is that of
+ *                nn.Conv2d.weight.flatten(1), so the weights are used as stored
+ *   col2im_relu  dx[b,iy,ix,ci] = [relu_out[b,iy,ix,ci] > 0] * sum over taps of dcol (conv dgrad as a gather,
+ *                fused with the ReLU backward of the layer below; relu_out may be NULL)
+ *   token_finish out[dst_row[r]] = x[src(b, tok - tok_base)] + add0[tok_class[tok]] + add1[tok], r = b*ncols + jj,
+ *                tok = tok_idx ? tok_idx[b*idx_ld + col0 + jj] : tok_base + jj   (modality / position adds +
+ *                gather of the visible tokens, pretrain_models.py:202-216,256).  x stacks the modality's
+ *                sources (sensors share one CNN) along the batch: src(b, tl) = ((tl/n_per)*batch + b)*n_per + tl%n_per.
+ *                Its backward is the gather dtok[src(b,tl)] = slot >= 0 ? dx0[b*rows_per_sample + slot] : 0 with
+ *                slot = slot_of_token[b, tok_base+tl] (slot_of_token NULL: slot = tok_base + tl)
+ * ---------------------------------------------------------------------------------------- */
+int m3l_im2col(const void* x, int x_nhwc_bf16, int batch, int channels, int height, int width, int k, int stride,
+               int pad, void* col_bf16, void* stream);
+int m3l_col2im_relu(const void* dcol_bf16, int batch, int channels, int height, int width, int k, int stride, int pad,
+                    const void* relu_out_bf16, void* dx_bf16, void* stream);
+int m3l_token_finish(const void* x_bf16, int batch, int n_per, const int32_t* tok_idx, int idx_ld, int col0, int ncols,
+                     int tok_base, const float* add0, const int32_t* tok_class, const float* add1,
+                     const int32_t* dst_row, void* out_bf16, int dim, void* stream);
+int m3l_token_finish_bwd(const void* dx0_bf16, int batch, int rows_per_sample, int n_total,
+                         const int32_t* slot_of_token, int tok_base, int n_mod, int n_per, int dim, void* dtok_bf16,
+                         void* stream);
 
 /* Token mean of the rollout feature extractor (MAEExtractor.forward: torch.mean(tokens, dim=1),
  * pretrain_models.py:837) and its backward.  x bf16 [batch, n_tokens, dim] -> out fp32 [batch, dim];

@@ -53,9 +53,10 @@ class ParamArena:
         descs = []
         toff = 0
         for name, p in ordered:
-            if p.dim() == 2 and name.endswith(".weight") and min(p.shape) >= 8:
+            if p.dim() in (2, 4) and name.endswith(".weight") and min(p.shape[0], p.numel() // p.shape[0]) >= 8:
+                # nn.Linear [out, in]; nn.Conv2d [cout, cin, kh, kw] is handled as [cout, cin*kh*kw]
                 self.t_offset[name] = toff
-                descs.append((self.offset[name], toff, p.shape[0], p.shape[1]))
+                descs.append((self.offset[name], toff, p.shape[0], p.numel() // p.shape[0]))
                 toff += _round_up(p.numel())
         self.flat_t = torch.zeros(max(toff, 1), dtype=torch.bfloat16, device=device)
         carr = (_lib.MatrixDesc * max(len(descs), 1))()
@@ -112,8 +113,13 @@ class ParamArena:
 
     def bf_t(self, name: str) -> torch.Tensor:
         o, n = self.t_offset[name], self.numel[name]
-        r, c = self.params[name].shape
-        return self.flat_t[o:o + n].view(c, r)
+        r = self.params[name].shape[0]
+        return self.flat_t[o:o + n].view(n // r, r)
+
+    def bf2d(self, name: str) -> torch.Tensor:
+        """bf16 shadow of a weight as a 2-D [out, fan_in] matrix (conv weights flattened)."""
+        o, n = self.offset[name], self.numel[name]
+        return self.flat_bf16[o:o + n].view(self.params[name].shape[0], -1)
 
     def new_grad_buffer(self) -> torch.Tensor:
         return torch.zeros(self.total, dtype=torch.float32, device=self.device)

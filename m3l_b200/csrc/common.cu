@@ -43,8 +43,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it needs a current context on the calling thread, and
+// only runtime-API calls bind the primary context implicitly.  PyTorch runs backward() on its own
+// threads, where our first call can be this one (CUDA_ERROR_INVALID_CONTEXT, 201, otherwise).
+static void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize,
                         uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  bind_primary_context();
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -82,6 +94,7 @@ int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t s1, uint64_t s2, uint32_t box1) {
+  bind_primary_context();
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");

@@ -1100,6 +1100,135 @@ token_mean_bwd_kernel(const float* __restrict__ dout, int B, int n, int D, bf16*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 9. EarlyCNN conv stem (early_conv_masking=True, pretrain_models.py:37-56,180-191): the convolutions run
+//    as im2col + tcgen05 GEMM (+bias +ReLU epilogue); activations are NHWC bf16 ([B*H*W, C] matrices, which
+//    is also the token layout flatten(2).transpose(1,2) produces).  K order of the im2col matrix is
+//    (cin, ky, kx) = the flattening of nn.Conv2d.weight [cout, cin, kh, kw], so weights are used as stored.
+// ------------------------------------------------------------------------------------------
+template <bool NHWC_BF16>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const void* __restrict__ xin, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+              bf16* __restrict__ col) {
+  pdl_wait();
+  pdl_trigger();
+  const int K = C * k * k;
+  const int K2 = K >> 1;                                   // two K entries per thread (K is even: k*k even or C even)
+  const size_t total = (size_t)B * Ho * Wo * K2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % K2) * 2;
+    const size_t m = i / K2;
+    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((size_t)Wo * Ho));
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kq = kk + e;
+      const int ci = kq / (k * k), r = kq - ci * k * k, ky = r / k, kx = r - ky * k;
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      float t = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        if (NHWC_BF16) t = __bfloat162float(reinterpret_cast<const bf16*>(xin)[(((size_t)b * H + iy) * W + ix) * C + ci]);
+        else t = reinterpret_cast<const float*>(xin)[(((size_t)b * C + ci) * H + iy) * W + ix];
+      }
+      v[e] = t;
+    }
+    *reinterpret_cast<uint32_t*>(col + m * K + kk) = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+// dgrad of the convolution as a gather (no atomics): dx[b,iy,ix,ci] = sum over the (ky,kx) taps that hit an
+// output position; multiplied by the ReLU mask of the layer input (relu_out > 0) when given.
+__global__ void __launch_bounds__(256)
+col2im_relu_kernel(const bf16* __restrict__ dcol, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                   const bf16* __restrict__ relu_out, bf16* __restrict__ dx) {
+  pdl_wait();
+  pdl_trigger();
+  const int K = C * k * k;
+  const size_t total = (size_t)B * H * W * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    const size_t pix = i / C;
+    const int ix = (int)(pix % W), iy = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+    float acc = 0.f;
+    if (relu_out == nullptr || __bfloat162float(relu_out[i]) > 0.f) {
+      for (int ky = 0; ky < k; ++ky) {
+        const int ty = iy + pad - ky;
+        if (ty < 0 || ty % stride != 0) continue;
+        const int oy = ty / stride;
+        if (oy >= Ho) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int tx = ix + pad - kx;
+          if (tx < 0 || tx % stride != 0) continue;
+          const int ox = tx / stride;
+          if (ox >= Wo) continue;
+          acc += __bfloat162float(dcol[(((size_t)b * Ho + oy) * Wo + ox) * K + ci * k * k + ky * k + kx]);
+        }
+      }
+    }
+    dx[i] = __float2bfloat16(acc);
+  }
+}
+
+// token finish of the conv-stem tokens: out[dst_row[r]] = x[src(b, tok - tok_base)] + add0[tok_class[tok]] + add1[tok]
+//   r = b*ncols + jj ; tok = tok_idx ? tok_idx[b*idx_ld + col0 + jj] : tok_base + jj   (pretrain_models.py:202-216,256)
+//   x holds the modality's sources (sensors) stacked along the batch: src(b, tl) = ((tl / n_per)*B + b)*n_per + tl % n_per
+__global__ void __launch_bounds__(256)
+token_finish_kernel(const bf16* __restrict__ x, int B, int n_per, const int32_t* __restrict__ tok_idx, int idx_ld, int col0,
+                    int ncols, int tok_base, const float* __restrict__ add0, const int32_t* __restrict__ tok_class,
+                    const float* __restrict__ add1, const int32_t* __restrict__ dst_row, bf16* __restrict__ out, int D) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int nchunk = D >> 3;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B * ncols; r += gridDim.x * wpb) {
+    const int b = r / ncols, jj = r - b * ncols;
+    const int tok = tok_idx ? tok_idx[(size_t)b * idx_ld + col0 + jj] : tok_base + jj;
+    const int tl = tok - tok_base, sidx = tl / n_per;
+    const bf16* src = x + (((size_t)sidx * B + b) * n_per + (tl - sidx * n_per)) * D;
+    const int dr = dst_row ? dst_row[r] : r;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      float v[8];
+      load8<bf16>(src + ch * 8, v);
+      if (add0) {
+        float a[8];
+        load8<float>(add0 + (size_t)tok_class[tok] * D + ch * 8, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+      }
+      if (add1) {
+        float a[8];
+        load8<float>(add1 + (size_t)tok * D + ch * 8, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+      }
+      store8(out + (size_t)dr * D + ch * 8, v);
+    }
+  }
+}
+
+// backward of the token gather: dtok[src(b, tl)] = slot >= 0 ? dx0[b*rows_per_sample + slot] : 0,
+//   slot = slot_of_token ? slot_of_token[b*n_total + tok_base + tl] : tok_base + tl   (src() as above)
+__global__ void __launch_bounds__(256)
+token_finish_bwd_kernel(const bf16* __restrict__ dx0, int B, int rows_per_sample, int n_total,
+                        const int32_t* __restrict__ slot_of_token, int tok_base, int n_mod, int n_per, int D,
+                        bf16* __restrict__ dtok) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int nchunk = D >> 3;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B * n_mod; r += gridDim.x * wpb) {
+    const int b = r / n_mod, tl = r - b * n_mod;
+    const int slot = slot_of_token ? slot_of_token[(size_t)b * n_total + tok_base + tl] : tok_base + tl;
+    const int sidx = tl / n_per;
+    bf16* dst = dtok + (((size_t)sidx * B + b) * n_per + (tl - sidx * n_per)) * D;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (slot >= 0) u = *reinterpret_cast<const uint4*>(dx0 + ((size_t)b * rows_per_sample + slot) * D + ch * 8);
+      *reinterpret_cast<uint4*>(dst + ch * 8) = u;
+    }
+  }
+}
+
 PatchSrc make_patch_src(const m3l_patch_source* s) {
   PatchSrc ps;
   for (int i = 0; i < 4; ++i) ps.src[i] = s->src[i];
@@ -1404,6 +1533,70 @@ extern "C" int m3l_token_mean_bwd(const float* dout, int batch, int n_tokens, in
   if (blocks > (size_t)device_sm_count() * 8) blocks = (size_t)device_sm_count() * 8;
   M3L_CUDA(launch_kernel(token_mean_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, dout, batch,
                          n_tokens, dim, (bf16*)dx_bf16));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_im2col(const void* x, int x_nhwc_bf16, int batch, int channels, int height, int width, int k,
+                          int stride, int pad, void* col_bf16, void* stream) {
+  M3L_REQUIRE(x && col_bf16, "im2col: null pointer");
+  M3L_REQUIRE(k >= 1 && stride >= 1 && pad >= 0 && (channels * k * k) % 8 == 0,
+              "im2col: channels*k*k = %d must be a multiple of 8", channels * k * k);
+  const int Ho = (height + 2 * pad - k) / stride + 1, Wo = (width + 2 * pad - k) / stride + 1;
+  if (batch == 0) return M3L_OK;
+  const size_t total = (size_t)batch * Ho * Wo * (channels * k * k / 2);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)device_sm_count() * 16) blocks = (size_t)device_sm_count() * 16;
+  if (x_nhwc_bf16)
+    M3L_CUDA(launch_kernel(im2col_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, batch, channels,
+                           height, width, k, stride, pad, Ho, Wo, (bf16*)col_bf16));
+  else
+    M3L_CUDA(launch_kernel(im2col_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, batch, channels,
+                           height, width, k, stride, pad, Ho, Wo, (bf16*)col_bf16));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_col2im_relu(const void* dcol_bf16, int batch, int channels, int height, int width, int k, int stride,
+                               int pad, const void* relu_out_bf16, void* dx_bf16, void* stream) {
+  M3L_REQUIRE(dcol_bf16 && dx_bf16, "col2im_relu: null pointer");
+  M3L_REQUIRE(k >= 1 && stride >= 1 && pad >= 0, "col2im_relu: bad geometry");
+  const int Ho = (height + 2 * pad - k) / stride + 1, Wo = (width + 2 * pad - k) / stride + 1;
+  if (batch == 0) return M3L_OK;
+  const size_t total = (size_t)batch * height * width * channels;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)device_sm_count() * 16) blocks = (size_t)device_sm_count() * 16;
+  M3L_CUDA(launch_kernel(col2im_relu_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dcol_bf16,
+                         batch, channels, height, width, k, stride, pad, Ho, Wo, (const bf16*)relu_out_bf16, (bf16*)dx_bf16));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_token_finish(const void* x_bf16, int batch, int n_per, const int32_t* tok_idx, int idx_ld, int col0,
+                                int ncols, int tok_base, const float* add0, const int32_t* tok_class, const float* add1,
+                                const int32_t* dst_row, void* out_bf16, int dim, void* stream) {
+  M3L_REQUIRE(x_bf16 && out_bf16, "token_finish: null pointer");
+  M3L_REQUIRE(dim % 8 == 0, "token_finish: dim %d must be a multiple of 8", dim);
+  M3L_REQUIRE(add0 == nullptr || tok_class != nullptr, "token_finish: add0 needs tok_class");
+  M3L_REQUIRE(n_per > 0, "token_finish: n_per must be positive");
+  if (batch * ncols == 0) return M3L_OK;
+  M3L_CUDA(launch_kernel(token_finish_kernel, dim3(ln_grid(batch * ncols, 8)), dim3(256), 0, (cudaStream_t)stream,
+                         (const bf16*)x_bf16, batch, n_per, tok_idx, idx_ld, col0, ncols, tok_base, add0, tok_class, add1,
+                         dst_row, (bf16*)out_bf16, dim));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_token_finish_bwd(const void* dx0_bf16, int batch, int rows_per_sample, int n_total,
+                                    const int32_t* slot_of_token, int tok_base, int n_mod, int n_per, int dim,
+                                    void* dtok_bf16, void* stream) {
+  M3L_REQUIRE(dx0_bf16 && dtok_bf16, "token_finish_bwd: null pointer");
+  M3L_REQUIRE(dim % 8 == 0, "token_finish_bwd: dim %d must be a multiple of 8", dim);
+  M3L_REQUIRE(n_per > 0 && n_mod % n_per == 0, "token_finish_bwd: n_mod %d must be a multiple of n_per %d", n_mod, n_per);
+  if (batch * n_mod == 0) return M3L_OK;
+  M3L_CUDA(launch_kernel(token_finish_bwd_kernel, dim3(ln_grid(batch * n_mod, 8)), dim3(256), 0, (cudaStream_t)stream,
+                         (const bf16*)dx0_bf16, batch, rows_per_sample, n_total, slot_of_token, tok_base, n_mod, n_per, dim,
+                         (bf16*)dtok_bf16));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

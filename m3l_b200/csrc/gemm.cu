@@ -414,6 +414,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
             }
           }
+          if (EPI == EPI_BF16 && p.act == 3) {            // ReLU (EarlyCNN conv stem)
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+          }
           uint32_t w[32];
           if constexpr (EPI == EPI_GELU_FWD) {
             // out = GELU(v); aux_out = GELU'(v) (bf16) so that the backward pass is a plain multiply
@@ -586,6 +590,7 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
                   ((p.aux_in == nullptr && p.aux_out == nullptr) || p.ld_aux % 8 == 0),
               "gemm: output / residual / aux leading dimensions must be multiples of 8");
   M3L_REQUIRE((p.dot_out == nullptr) == (p.dot_side == nullptr), "gemm: dot_side and dot_out go together");
+  M3L_REQUIRE(p.act >= 0 && p.act <= 3 && (p.act != 3 || p.out_mode == 0), "gemm: act=%d unsupported here", p.act);
   M3L_REQUIRE(p.dot_out == nullptr || (p.out_mode == 0 && p.act == 0 && p.residual == nullptr && p.N % 64 == 0 &&
                                        p.ld_dot % 8 == 0 && !p.a_mn_major),
               "gemm: the fused row-dot needs a plain bf16 output with N %% 64 == 0");

@@ -20,7 +20,7 @@ struct GemmArgs {
   const float* bias = nullptr;      // [N] fp32
   const bf16* residual = nullptr;   // [M, ldr] bf16, added after activation
   int ldr = 0;
-  int act = 0;              // 0 none; 1 GELU (aux_out <- GELU'(pre-activation)); 2 multiply by aux_in
+  int act = 0;              // 0 none; 1 GELU (aux_out <- GELU'(pre-activation)); 2 multiply by aux_in; 3 ReLU
   bf16* aux_out = nullptr;
   const bf16* aux_in = nullptr;
   int ld_aux = 0;

@@ -247,6 +247,13 @@ class Tables:
         self.all_cls_tac = torch.tensor((cls[geo.n_img:] * B) if geo.nt else [0], **i32)
         self.all_pos_img = torch.arange(geo.n_img, device=device).repeat(B).to(torch.int32)
         self.all_pos_tac = (geo.n_img + torch.arange(geo.nt * geo.n_tac, device=device)).repeat(B).to(torch.int32)
+        # early_conv_masking: the heads run on ALL tokens; row of token (b, t) in the stacked head inputs
+        # [B*n_img image rows | B*nt*n_tac tactile rows]
+        t = torch.arange(geo.n, device=device)[None]
+        nta = geo.nt * geo.n_tac
+        img_row = b * geo.n_img + t
+        tac_row = B * geo.n_img + b * nta + (t - geo.n_img)
+        self.head_row_all = torch.where(t < geo.n_img, img_row, tac_row).reshape(-1).to(torch.int32)
         # sin-cos tables of the present tokens (constants, fp32)
         if cfg.use_sincosmod_encodings:
             enc, dec = [], []
@@ -259,6 +266,115 @@ class Tables:
             self.dec_pos = torch.cat(dec, 0).to(device=device, dtype=torch.float32).contiguous()
         else:
             self.enc_pos = self.dec_pos = None
+
+
+# --------------------------------------------------------------------------------------------
+# EarlyCNN conv stem (early_conv_masking=True; pretrain_models.py:37-56,180-191): im2col + GEMM
+# --------------------------------------------------------------------------------------------
+def cnn_layers(model, key: str):
+    """[(name, cin, cout, k, stride, pad)] of EarlyCNN(key) (pretrain_models.py:41-49)."""
+    cnn = model.early_conv_vision if key == "image" else model.early_conv_tactile
+    out = []
+    for nm in ("conv1", "conv2", "conv3", "conv4"):
+        c = getattr(cnn, nm)
+        out.append((nm, c.in_channels, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0]))
+    return out
+
+
+def _cnn_fwd(A, prefix: str, layers, maps: List[torch.Tensor], B: int, H: int, W: int, saved: Optional[list]):
+    """maps: fp32 NCHW [B, C, H, W], one per source (the sensors of a modality share the CNN and are stacked
+    along the batch).  Returns the tokens bf16 [len(maps)*B*h*w, D] in (source, sample, y, x) row order."""
+    beff = B * len(maps)
+    x, h, w = None, H, W
+    for li, (nm, cin, cout, k, st, pd) in enumerate(layers):
+        ho, wo = ops.conv_out_size(h, k, st, pd), ops.conv_out_size(w, k, st, pd)
+        if li == 0:
+            col = torch.empty((beff * ho * wo, cin * k * k), dtype=torch.bfloat16, device=A.device)
+            for si, m in enumerate(maps):
+                ops.im2col(m, B, cin, h, w, k, st, pd, False, out=col[si * B * ho * wo:(si + 1) * B * ho * wo])
+        elif k == 1 and st == 1 and pd == 0:
+            col = x                                         # 1x1 convolution: the activation matrix itself
+        else:
+            col = ops.im2col(x, beff, cin, h, w, k, st, pd, True)
+        y = ops.gemm(col, A.bf2d(f"{prefix}.{nm}.weight"), bias=A.f32(f"{prefix}.{nm}.bias"),
+                     act=ops.RELU if li < len(layers) - 1 else 0)
+        if saved is not None:
+            saved.append((col, y, h, w))
+        x, h, w = y, ho, wo
+    return x
+
+
+def _cnn_bwd(A, G, prefix: str, layers, dtok: torch.Tensor, saved: list, beff: int):
+    """dtok: bf16 gradient w.r.t. the conv-stem tokens (rows as _cnn_fwd returns them)."""
+    dy = dtok
+    for li in reversed(range(len(layers))):
+        nm, cin, cout, k, st, pd = layers[li]
+        col, y, h, w = saved[li]
+        ops.colsum(dy, G(f"{prefix}.{nm}.bias"))
+        wgrad(dy, col, G(f"{prefix}.{nm}.weight").view(cout, cin * k * k))
+        if li == 0:
+            break                                           # the raw maps need no gradient
+        dcol = ops.gemm(dy, A.bf_t(f"{prefix}.{nm}.weight"))
+        dy = ops.col2im_relu(dcol, beff, cin, h, w, k, st, pd, relu_out=saved[li - 1][1])
+
+
+def _modalities(model, geo, x):
+    """(key, prefix, maps, H, W, n_per_source, tok_base) of the modalities present."""
+    e = model.encoder
+    out = []
+    if geo.use_vision:
+        out.append(("image", "early_conv_vision", [x["image"]], e.image_height, e.image_width, geo.n_img, 0))
+    if geo.nt:
+        out.append(("tactile", "early_conv_tactile", [x[f"tactile{i + 1}"] for i in range(geo.nt)],
+                    e.tactile_height, e.tactile_width, geo.n_tac, geo.n_img))
+    return out
+
+
+def _embed_fwd_ecm(model, A, geo, tabs, x, B, masked: bool, saved: Optional[dict], unmasked32=None):
+    """Encoder input rows from the conv stems (+ modality + position), visible tokens only when masked."""
+    cfg = model.cfg
+    D = cfg.dim
+    n_rows = geo.nv if masked else geo.n
+    x0 = torch.empty((B * n_rows, D), dtype=torch.bfloat16, device=A.device)
+    sincos = cfg.use_sincosmod_encodings
+    for key, prefix, maps, H, W, n_per, tok_base in _modalities(model, geo, x):
+        layers = cnn_layers(model, key)
+        cs = [] if saved is not None else None
+        tok = _cnn_fwd(A, prefix, layers, maps, B, H, W, cs)
+        img = key == "image"
+        if masked:
+            ncols, col0 = (geo.nv_img, 0) if img else (geo.nv_tac, geo.nv_img)
+            dst = tabs.enc_dst_img if img else tabs.enc_dst_tac
+        else:
+            ncols, col0 = n_per * len(maps), 0
+            dst = tabs.all_dst_img if img else tabs.all_dst_tac
+        ops.token_finish(tok, B, n_per, ncols, tok_base, x0, tok_idx=unmasked32 if masked else None, col0=col0,
+                         add0=A.f32("encoder_modality_embedding.weight") if sincos else None,
+                         tok_class=tabs.tok_class if sincos else None,
+                         add1=tabs.enc_pos if sincos else A.f32("encoder.pos_embedding")[0, 1:geo.n + 1], dst_row=dst)
+        if saved is not None:
+            saved[key] = (cs, layers, len(maps), n_per, tok_base)
+    return x0
+
+
+def _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict, slots=None):
+    cfg = model.cfg
+    n_rows = geo.nv if masked else geo.n
+    if cfg.use_sincosmod_encodings:
+        ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.slot_class if masked else tabs.tok_class,
+                         dclass=G("encoder_modality_embedding.weight"))
+    else:
+        gpos = G("encoder.pos_embedding")[0, 1:geo.n + 1]
+        pos = saved["unmasked32"].view(-1) if masked else torch.arange(geo.n, device=dx0.device, dtype=torch.int32).repeat(B)
+        ops.rowclass_sum(dx0, B, n_rows, row_pos=pos, dpos=gpos)
+    for key in ("image", "tactile"):
+        if key not in saved:
+            continue
+        cs, layers, nsrc, n_per, tok_base = saved[key]
+        prefix = "early_conv_vision" if key == "image" else "early_conv_tactile"
+        dtok = ops.token_finish_bwd(dx0, B, n_rows, geo.n, tok_base, nsrc * n_per, n_per,
+                                    slot_of_token=slots if masked else None)
+        _cnn_bwd(A, G, prefix, layers, dtok, cs, B * nsrc)
 
 
 # --------------------------------------------------------------------------------------------
@@ -350,7 +466,11 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
     masked, unmasked, slots, unmasked32, mrow = ops.mask_indices(noise, geo.segs, extra=True, n_masked_first=geo.nm_img)
     model.last_masked_indices, model.last_unmasked_indices = masked, unmasked
     emb_saved = {"unmasked32": unmasked32} if training else None
-    x0 = _embed_fwd(model, A, geo, tabs, x, B, unmasked, True, emb_saved, unmasked32=unmasked32)
+    ecm = cfg.early_conv_masking
+    if ecm:
+        x0 = _embed_fwd_ecm(model, A, geo, tabs, x, B, True, emb_saved, unmasked32=unmasked32)
+    else:
+        x0 = _embed_fwd(model, A, geo, tabs, x, B, unmasked, True, emb_saved, unmasked32=unmasked32)
     enc_saved = [] if training else None
     xe = stack_fwd(A, model.enc_spec, x0, B, geo.nv, enc_saved)
     enc_out, st_enc = ops.layernorm_fwd(xe, A.f32("encoder.transformer.norm.weight"), A.f32("encoder.transformer.norm.bias"),
@@ -368,18 +488,22 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
                                      add1=A.f32("decoder_pos_emb.weight")[:geo.n])
     dec_saved = [] if training else None
     xd = stack_fwd(A, model.dec_spec, z, B, geo.n, dec_saved)
-    # final LayerNorm, written straight into the stacked head inputs (masked rows only)
+    # final LayerNorm, written straight into the stacked head inputs (masked rows only; with
+    # early_conv_masking the heads and the loss cover ALL tokens: pretrain_models.py:311-322)
+    if ecm:
+        mrow = tabs.head_row_all
+    h_img, h_tac = (geo.n_img, geo.nt * geo.n_tac) if ecm else (geo.nm_img, geo.nm_tac_total)
     gathered, st_dec = ops.layernorm_fwd(xd, A.f32("decoder.norm.weight"), A.f32("decoder.norm.bias"),
-                                         out_rows=B * geo.nm, dst_row=mrow, want_stats=training)
+                                         out_rows=B * (h_img + h_tac), dst_row=mrow, want_stats=training)
     loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
     heads = []
     G = GradView(A, gflat) if (training and gflat is not None) else None
-    r_img = B * geo.nm_img
+    r_img = B * h_img
     if geo.nt:
         g_tac = gathered[r_img:]
         pred = ops.gemm(g_tac, A.bf("to_tactiles.weight"), bias=A.f32("to_tactiles.bias"), out_dtype=torch.float32)
         ps = ops.make_patch_source([x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac, geo.n_img)
-        dpred = ops.mse_loss(ps, B, geo.nm_tac_total, pred, 10.0 / pred.numel(), loss_acc, tok_idx=masked, col0=geo.nm_img,
+        dpred = ops.mse_loss(ps, B, h_tac, pred, 10.0 / pred.numel(), loss_acc, tok_idx=None if ecm else masked, col0=geo.nm_img,
                              dpred_colsum=G("to_tactiles.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_tactiles", g_tac, dpred, r_img))
         if capture is not None:
@@ -388,7 +512,7 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
         g_img = gathered[:r_img]
         pred = ops.gemm(g_img, A.bf("to_pixels.weight"), bias=A.f32("to_pixels.bias"), out_dtype=torch.float32)
         ps = ops.make_patch_source([x["image"]], model.ph_img, model.pw_img, 0)
-        dpred = ops.mse_loss(ps, B, geo.nm_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=masked, col0=0,
+        dpred = ops.mse_loss(ps, B, h_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=None if ecm else masked, col0=0,
                              dpred_colsum=G("to_pixels.bias") if G is not None and pred.shape[1] <= 1024 else None)
         heads.append(("to_pixels", g_img, dpred, 0))
         if capture is not None:
@@ -441,7 +565,10 @@ def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
                             dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
                             dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
-    _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
+    if cfg.early_conv_masking:
+        _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, True, ctx["emb"], slots=ctx["slots"])
+    else:
+        _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
 
 
 # --------------------------------------------------------------------------------------------
@@ -451,7 +578,10 @@ def embeddings_forward(model, x, geo: Geometry, B: int, training: bool):
     A = model.arena
     tabs = model.tables(geo, B)
     emb_saved = {} if training else None
-    x0 = _embed_fwd(model, A, geo, tabs, x, B, None, False, emb_saved)
+    if model.cfg.early_conv_masking:
+        x0 = _embed_fwd_ecm(model, A, geo, tabs, x, B, False, emb_saved)
+    else:
+        x0 = _embed_fwd(model, A, geo, tabs, x, B, None, False, emb_saved)
     enc_saved = [] if training else None
     xe = stack_fwd(A, model.enc_spec, x0, B, geo.n, enc_saved)
     out, st = ops.layernorm_fwd(xe, A.f32("encoder.transformer.norm.weight"), A.f32("encoder.transformer.norm.bias"),
@@ -468,4 +598,7 @@ def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor):
                             dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
                             dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.n, ctx["enc"])
-    _embed_bwd(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])
+    if model.cfg.early_conv_masking:
+        _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])
+    else:
+        _embed_bwd(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])

@@ -15,6 +15,7 @@ from ._lib import GemmArgs, check, current_stream, ptr
 
 GELU_FWD = 1
 GELU_BWD = 2
+RELU = 3
 
 
 _WS = {}
@@ -228,6 +229,56 @@ def colsum(x, out):
 def ln_param_grad(da, xhat, dgamma, dbeta):
     check(_lib.load().m3l_ln_param_grad(ptr(da), ptr(xhat), da.shape[0], da.shape[1], ptr(dgamma), ptr(dbeta),
                                         current_stream()), "m3l_ln_param_grad")
+
+
+# ------------------------------------------------------------------------------------------
+# EarlyCNN conv stem (im2col + GEMM)
+# ------------------------------------------------------------------------------------------
+def conv_out_size(size, k, stride, pad):
+    return (size + 2 * pad - k) // stride + 1
+
+
+def im2col(x, batch, channels, height, width, k, stride, pad, nhwc_bf16, out=None):
+    """x: fp32 NCHW maps (nhwc_bf16=False) or bf16 [B*H*W, C] (True) -> bf16 [B*Ho*Wo, C*k*k]."""
+    _req_cuda(x)
+    assert x.is_contiguous() and x.dtype == (torch.bfloat16 if nhwc_bf16 else torch.float32)
+    ho, wo = conv_out_size(height, k, stride, pad), conv_out_size(width, k, stride, pad)
+    col = out if out is not None else torch.empty((batch * ho * wo, channels * k * k), dtype=torch.bfloat16, device=x.device)
+    assert col.shape == (batch * ho * wo, channels * k * k) and col.is_contiguous() and col.dtype == torch.bfloat16
+    check(_lib.load().m3l_im2col(ptr(x), 1 if nhwc_bf16 else 0, batch, channels, height, width, k, stride, pad, ptr(col),
+                                 current_stream()), "m3l_im2col")
+    return col
+
+
+def col2im_relu(dcol, batch, channels, height, width, k, stride, pad, relu_out=None):
+    """dcol bf16 [B*Ho*Wo, C*k*k] -> dx bf16 [B*H*W, C] (x [relu_out > 0] when given)."""
+    _req_cuda(dcol, relu_out)
+    assert dcol.dtype == torch.bfloat16 and dcol.is_contiguous()
+    dx = torch.empty((batch * height * width, channels), dtype=torch.bfloat16, device=dcol.device)
+    check(_lib.load().m3l_col2im_relu(ptr(dcol), batch, channels, height, width, k, stride, pad, ptr(relu_out), ptr(dx),
+                                      current_stream()), "m3l_col2im_relu")
+    return dx
+
+
+def token_finish(x, batch, n_per, ncols, tok_base, out, *, tok_idx=None, col0=0, add0=None, tok_class=None, add1=None,
+                 dst_row=None):
+    _req_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and out.dtype == torch.bfloat16
+    idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
+    assert tok_idx is None or tok_idx.dtype == torch.int32
+    check(_lib.load().m3l_token_finish(ptr(x), batch, n_per, ptr(tok_idx), idx_ld, col0, ncols, tok_base, ptr(add0),
+                                       ptr(tok_class), ptr(add1), ptr(dst_row), ptr(out), x.shape[1], current_stream()),
+          "m3l_token_finish")
+    return out
+
+
+def token_finish_bwd(dx0, batch, rows_per_sample, n_total, tok_base, n_mod, n_per, *, slot_of_token=None):
+    _req_cuda(dx0)
+    assert dx0.dtype == torch.bfloat16 and dx0.is_contiguous()
+    dtok = torch.empty((batch * n_mod, dx0.shape[1]), dtype=torch.bfloat16, device=dx0.device)
+    check(_lib.load().m3l_token_finish_bwd(ptr(dx0), batch, rows_per_sample, n_total, ptr(slot_of_token), tok_base, n_mod,
+                                           n_per, dx0.shape[1], ptr(dtok), current_stream()), "m3l_token_finish_bwd")
+    return dtok
 
 
 def token_mean_fwd(x, batch, n_tokens):

@@ -280,9 +280,9 @@ class VTMAE(nn.Module):
             raise M3LError("m3l_b200.VTMAE needs its parameters on a CUDA device: the compute path is the sm_100a "
                            "kernel library and there is no CPU fallback (call .cuda() first)")
         if self.arena is None or self.arena.device != dev:
+            dead = ("image_patch_to_emb", "tactile_patch_to_emb") if self.early_conv_masking else ("early_conv",)
             late = [k for k, _ in self._canonical_named_params()
-                    if k in self.LATE or k.startswith("early_conv")] if self.use_sincosmod_encodings else \
-                   [k for k, _ in self._canonical_named_params() if k.startswith("early_conv")]
+                    if (k in self.LATE and self.use_sincosmod_encodings) or k.startswith(dead)]
             self.arena = ParamArena(self._canonical_named_params(), dev, late_names=late)
             self._tables = {}
             self._trainer = None
@@ -299,8 +299,12 @@ class VTMAE(nn.Module):
         """Parameters that receive a gradient in this mode (the reference leaves .grad None on the rest)."""
         names = []
         for k in self.arena.names:
-            if k.startswith("early_conv"):
-                continue  # TODO(next): early_conv_masking=True path
+            if k.startswith("early_conv_vision") and not (self.early_conv_masking and geo.use_vision):
+                continue
+            if k.startswith("early_conv_tactile") and not (self.early_conv_masking and geo.nt):
+                continue
+            if k.startswith(("image_patch_to_emb", "tactile_patch_to_emb")) and self.early_conv_masking:
+                continue  # the conv stems replace the patch embeddings (pretrain_models.py:180-191)
             if k == "encoder.pos_embedding" and self.use_sincosmod_encodings:
                 continue
             if k == "decoder_pos_emb.weight" and (self.use_sincosmod_encodings or not masked):
@@ -326,8 +330,6 @@ class VTMAE(nn.Module):
         if 'image' not in x:
             use_vision = False
         geo = engine.make_geometry(self.cfg, use_vision, use_tactile, reconstruct_ratio)
-        if self.early_conv_masking:
-            raise M3LError("early_conv_masking=True is not implemented in the kernel path yet (DESIGN.md: next)")
         xs = {}
         keys = (['image'] if geo.use_vision else []) + [f'tactile{i + 1}' for i in range(geo.nt)]
         for k in keys:
@@ -370,6 +372,8 @@ class VTMAE(nn.Module):
         rearrangements of the outputs are torch indexing ops (not on the hot path); values are detached."""
         if mask_ratio is None:
             mask_ratio = self.masking_ratio
+        if self.early_conv_masking:
+            raise M3LError("reconstruct() with early_conv_masking=True (pretrain_models.py:560-575) is not implemented")
         A = self._sync()
         xs, geo, B = self._prep_inputs(x, use_vision, use_tactile, reconstruct_ratio=mask_ratio)
         if noise is None:

@@ -270,6 +270,70 @@ def test_rowclass_colsum_lnparam(ops):
     assert rel_err(dg, (da.float() * xh.float()).sum(0)) < 1e-4 and rel_err(db, da.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("C,H,W,k,st,pd", [(12, 64, 64, 4, 2, 1), (32, 16, 16, 4, 2, 1), (64, 8, 8, 3, 1, 1), (128, 8, 8, 1, 1, 0)])
+def test_conv_stem_pieces(ops, C, H, W, k, st, pd):
+    """im2col + GEMM(+bias+ReLU) == Conv2d + ReLU; col2im_relu + GEMMs == its backward (pretrain_models.py:37-56)."""
+    torch.manual_seed(13)
+    B, cout = 3, 64
+    x = torch.randn(B, C, H, W, device=DEV)
+    conv = torch.nn.Conv2d(C, cout, k, stride=st, padding=pd).to(DEV)
+    wb = conv.weight.detach().bfloat16()
+    xq = x.bfloat16().float()                                   # the kernels see bf16 activations
+    ho, wo = ops.conv_out_size(H, k, st, pd), ops.conv_out_size(W, k, st, pd)
+    col = ops.im2col(x, B, C, H, W, k, st, pd, False)
+    ref_col = F.unfold(xq, k, padding=pd, stride=st).transpose(1, 2).reshape(B * ho * wo, C * k * k)
+    assert torch.equal(col.float(), ref_col.bfloat16().float())
+    x_nhwc = xq.permute(0, 2, 3, 1).reshape(B * H * W, C).bfloat16().contiguous()
+    assert torch.equal(ops.im2col(x_nhwc, B, C, H, W, k, st, pd, True), col)
+    y = ops.gemm(col, wb.reshape(cout, -1).contiguous(), bias=conv.bias.detach(), act=ops.RELU)
+    xr = xq.clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wb.float(), conv.bias, stride=st, padding=pd))
+    assert rel_err(y, yr.permute(0, 2, 3, 1).reshape(B * ho * wo, cout)) < 1e-2
+    # backward of the convolution input (dgrad GEMM + gather) fused with a ReLU mask of the layer below
+    dy = torch.randn(B * ho * wo, cout, device=DEV).bfloat16()
+    mask_src = torch.randn(B * H * W, C, device=DEV).bfloat16()
+    dcol = ops.gemm(dy, wb.reshape(cout, -1).T.contiguous())
+    dx = ops.col2im_relu(dcol, B, C, H, W, k, st, pd, relu_out=mask_src)
+    g = torch.autograd.grad(F.conv2d(xr, wb.float(), None, stride=st, padding=pd),
+                            xr, dy.float().reshape(B, ho, wo, cout).permute(0, 3, 1, 2))[0]
+    ref_dx = g.permute(0, 2, 3, 1).reshape(B * H * W, C) * (mask_src.float() > 0)
+    assert rel_err(dx, ref_dx) < 2e-2
+    assert rel_err(ops.col2im_relu(dcol, B, C, H, W, k, st, pd), g.permute(0, 2, 3, 1).reshape(B * H * W, C)) < 2e-2
+
+
+def test_token_finish_fwd_bwd(ops):
+    torch.manual_seed(14)
+    B, n_per, nsrc, D, n_total, tok_base, nv = 5, 16, 2, 128, 48, 16, 6
+    x = torch.randn(nsrc * B * n_per, D, device=DEV).bfloat16()
+    tok = torch.stack([torch.randperm(nsrc * n_per)[:nv] + tok_base for _ in range(B)]).to(DEV).to(torch.int32)
+    idx = torch.zeros(B, 9, dtype=torch.int32, device=DEV)
+    idx[:, 3:] = tok
+    add0, add1 = torch.randn(3, D, device=DEV), torch.randn(n_total, D, device=DEV)
+    cls = torch.tensor([0] * 16 + [1] * 16 + [2] * 16, dtype=torch.int32, device=DEV)
+    dst = (torch.arange(B, device=DEV)[:, None] * 10 + 2 + torch.arange(nv, device=DEV)[None]).reshape(-1).to(torch.int32)
+    out = torch.zeros(B * 10, D, device=DEV, dtype=torch.bfloat16)
+    ops.token_finish(x, B, n_per, nv, tok_base, out, tok_idx=idx, col0=3, add0=add0, tok_class=cls, add1=add1, dst_row=dst)
+    xs = x.float().reshape(nsrc, B, n_per, D)
+    for b in range(B):
+        for j in range(nv):
+            t = int(tok[b, j]); tl = t - tok_base
+            ref = xs[tl // n_per, b, tl % n_per] + add0[int(cls[t])] + add1[t]
+            assert rel_err(out[b * 10 + 2 + j], ref) < 1e-2
+    # backward: gather with a slot map (-1 = masked token -> zero row)
+    slots = torch.full((B, n_total), -1, dtype=torch.int32, device=DEV)
+    for b in range(B):
+        for j in range(nv):
+            slots[b, int(tok[b, j])] = 2 + j
+    dx0 = torch.randn(B * 10, D, device=DEV).bfloat16()
+    dtok = ops.token_finish_bwd(dx0, B, 10, n_total, tok_base, nsrc * n_per, n_per, slot_of_token=slots)
+    ref = torch.zeros(nsrc, B, n_per, D, device=DEV)
+    for b in range(B):
+        for j in range(nv):
+            tl = int(tok[b, j]) - tok_base
+            ref[tl // n_per, b, tl % n_per] = dx0[b * 10 + 2 + j].float()
+    assert torch.equal(dtok.float(), ref.reshape(-1, D))
+
+
 def test_token_mean(ops):
     torch.manual_seed(12)
     B, n, D = 37, 192, 256

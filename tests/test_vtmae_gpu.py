@@ -13,7 +13,7 @@ from tests._golden import CASES, Golden
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-KERNEL_CASES = [c for c in CASES if "ecm" not in c]
+KERNEL_CASES = list(CASES)     # incl. tiny_ecm: early_conv_masking=True (conv stems, loss over all patches)
 
 
 def cos(a, b):
@@ -76,10 +76,11 @@ def _oracle_grads(cfg, sd, x, noise):
     return loss.detach(), {k: sd[k].grad for k in O.param_keys(sd)}
 
 
-@pytest.mark.parametrize("nt", [2, 0])
-def test_all_gradients_vs_oracle_canonical(nt):
-    """Every parameter gradient of the canonical model against the CPU oracle, same inputs."""
-    cfg = O.VTMAEConfig(num_tactiles=nt)
+@pytest.mark.parametrize("nt,ecm", [(2, False), (0, False), (2, True), (0, True)])
+def test_all_gradients_vs_oracle_canonical(nt, ecm):
+    """Every parameter gradient of the canonical model against the CPU oracle, same inputs
+    (ecm=True is train.py's default: EarlyCNN conv stems, loss over all patches)."""
+    cfg = O.VTMAEConfig(num_tactiles=nt, early_conv_masking=ecm)
     sd = O.init_state_dict(cfg, seed=1)
     gen = torch.Generator().manual_seed(99)
     B = 16
@@ -217,12 +218,12 @@ def test_mae_extractor_vs_oracle(vision_only):
     assert torch.equal(f2, feats.detach())
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_fused_train_steps_vs_oracle(use_graph):
+@pytest.mark.parametrize("use_graph,ecm", [(False, False), (True, False), (True, True)])
+def test_fused_train_steps_vs_oracle(use_graph, ecm):
     """zero_grad + fwd + bwd + clip(0.5) + AdamW (pretrain_models.py:707-711): loss trajectory and
     updated weights against the oracle's restatement of torch AdamW, 3 steps."""
     from m3l_b200.trainer import FusedTrainer
-    cfg = O.VTMAEConfig()
+    cfg = O.VTMAEConfig(early_conv_masking=ecm)
     sd = O.init_state_dict(cfg, seed=4)
     gen = torch.Generator().manual_seed(17)
     B = 8
@@ -241,7 +242,10 @@ def test_fused_train_steps_vs_oracle(use_graph):
         assert abs(l.item() - lo.item()) <= 1e-2 * abs(lo.item()), (it, l.item(), lo.item())
         assert abs(mae._trainer.state[2].item() - norm.item()) <= 3e-2 * norm.item()
     named = dict(mae.named_parameters())
-    for k in ("decoder.layers.0.1.net.1.weight", "to_pixels.weight", "mask_token", "encoder.transformer.layers.0.0.to_qkv.weight"):
+    keys = ["decoder.layers.0.1.net.1.weight", "to_pixels.weight", "mask_token", "encoder.transformer.layers.0.0.to_qkv.weight"]
+    if ecm:
+        keys += ["early_conv_vision.conv1.weight", "early_conv_tactile.conv3.weight", "early_conv_vision.conv4.bias"]
+    for k in keys:
         upd_ref = sd[k].detach() - w0[k]
         upd = named[k].detach().cpu() - w0[k]
         assert cos(upd, upd_ref) >= 0.99, (k, cos(upd, upd_ref))
