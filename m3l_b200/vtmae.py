@@ -372,8 +372,6 @@ class VTMAE(nn.Module):
         rearrangements of the outputs are torch indexing ops (not on the hot path); values are detached."""
         if mask_ratio is None:
             mask_ratio = self.masking_ratio
-        if self.early_conv_masking:
-            raise M3LError("reconstruct() with early_conv_masking=True (pretrain_models.py:560-575) is not implemented")
         A = self._sync()
         xs, geo, B = self._prep_inputs(x, use_vision, use_tactile, reconstruct_ratio=mask_ratio)
         if noise is None:
@@ -390,11 +388,15 @@ class VTMAE(nn.Module):
             gh, gw = e.image_height // self.ph_img, e.image_width // self.pw_img
             patches = self.image_to_patch(xs['image'])
             mi = masked[:, :geo.nm_img]
-            pred = cap["pred_image"].view(B, geo.nm_img, -1)
-            out['recon_loss_image'] = torch.nn.functional.mse_loss(pred, patches[br, mi])
             vis, rec = patches.clone(), patches.clone()
             vis[br, mi] = 0.5
-            rec[br, mi] = pred
+            if self.early_conv_masking:      # heads on ALL tokens; the reconstruction is the prediction (:560-567)
+                rec = cap["pred_image"].view(B, geo.n_img, -1)
+                out['recon_loss_image'] = torch.nn.functional.mse_loss(rec, patches)
+            else:
+                pred = cap["pred_image"].view(B, geo.nm_img, -1)
+                out['recon_loss_image'] = torch.nn.functional.mse_loss(pred, patches[br, mi])
+                rec[br, mi] = pred
             unp = lambda t: t.reshape(B, gh, gw, self.ph_img, self.pw_img, -1).permute(0, 5, 1, 3, 2, 4).reshape(
                 B, -1, gh * self.ph_img, gw * self.pw_img)       # 'b (h w) (p1 p2 c) -> b c (h p1) (w p2)'
             out['image_rec'], out['image_masked'] = unp(rec), unp(vis)
@@ -402,11 +404,15 @@ class VTMAE(nn.Module):
             gh, gw = e.tactile_height // self.ph_tac, e.tactile_width // self.pw_tac
             patches = torch.cat([self.tactile_to_patch(xs[f'tactile{i + 1}']) for i in range(geo.nt)], dim=1)
             mt = masked[:, geo.nm_img:] - geo.n_img
-            pred = cap["pred_tactile"].view(B, geo.nm_tac_total, -1)
-            out['recon_loss_tactile'] = torch.nn.functional.mse_loss(pred, patches[br, mt])
             vis, rec = patches.clone(), patches.clone()
             vis[br, mt] = float('inf')
-            rec[br, mt] = pred
+            if self.early_conv_masking:
+                rec = cap["pred_tactile"].view(B, geo.nt * geo.n_tac, -1)
+                out['recon_loss_tactile'] = torch.nn.functional.mse_loss(rec, patches)
+            else:
+                pred = cap["pred_tactile"].view(B, geo.nm_tac_total, -1)
+                out['recon_loss_tactile'] = torch.nn.functional.mse_loss(pred, patches[br, mt])
+                rec[br, mt] = pred
             unp = lambda t: t.reshape(B, geo.nt, gh, gw, self.ph_tac, self.pw_tac, -1).permute(0, 1, 6, 2, 4, 3, 5).reshape(
                 B, -1, gh * self.ph_tac, gw * self.pw_tac)       # 'b (n h w) (p1 p2 c) -> b (n c) (h p1) (w p2)'
             out['tactile_rec'], out['tactile_masked'] = unp(rec), unp(vis)

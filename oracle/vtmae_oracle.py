@@ -375,9 +375,9 @@ def unpatchify_tactile(p, n, gh, gw, ph, pw):
 
 def vtmae_reconstruct(sd, cfg: VTMAEConfig, x: dict, noise: torch.Tensor, mask_ratio=None, use_vision=True,
                       use_tactile=True):
-    """VTMAE.reconstruct (pretrain_models.py:344-586), early_conv_masking=False path, mask noise supplied
-    externally (image, tactile1, tactile2 order as the torch.rand calls at :426,439)."""
-    assert not cfg.early_conv_masking
+    """VTMAE.reconstruct (pretrain_models.py:344-586), mask noise supplied externally (image, tactile1,
+    tactile2 order as the torch.rand calls at :426,439).  With early_conv_masking the heads run on all
+    tokens and the reconstruction is the prediction itself (:560-575)."""
     if mask_ratio is None:
         mask_ratio = cfg.masking_ratio
     tokens, img_patches, tac_patches, use_vision, has_tac = _tokens(sd, cfg, x, use_vision, use_tactile)
@@ -410,22 +410,32 @@ def vtmae_reconstruct(sd, cfg: VTMAEConfig, x: dict, noise: torch.Tensor, mask_r
     out = {}
     if use_vision:
         (H, W), (ph, pw) = _pair(cfg.image_size), _pair(cfg.image_patch_size)
-        pred = linear(decoded[br, masked_img], sd, "to_pixels")
         vis, rec = img_patches.clone(), img_patches.clone()
         vis[br, masked_img] = 0.5
-        rec[br, masked_img] = pred
+        if cfg.early_conv_masking:
+            rec = linear(decoded[:, :n_img], sd, "to_pixels")
+            loss_img = F.mse_loss(rec, img_patches)
+        else:
+            pred = linear(decoded[br, masked_img], sd, "to_pixels")
+            rec[br, masked_img] = pred
+            loss_img = F.mse_loss(pred, img_patches[br, masked_img])
         out["image_rec"] = unpatchify_image(rec, H // ph, W // pw, ph, pw)
         out["image_masked"] = unpatchify_image(vis, H // ph, W // pw, ph, pw)
-        out["recon_loss_image"] = F.mse_loss(pred, img_patches[br, masked_img])
+        out["recon_loss_image"] = loss_img
     if has_tac:
         (H, W), (ph, pw) = _pair(cfg.tactile_size), _pair(cfg.tactile_patch_size)
-        pred = linear(decoded[br, masked_tac], sd, "to_tactiles")
         vis, rec = tac_patches.clone(), tac_patches.clone()
         vis[br, masked_tac - n_img] = float("inf")
-        rec[br, masked_tac - n_img] = pred
+        if cfg.early_conv_masking:
+            rec = linear(decoded[:, n_img:], sd, "to_tactiles")
+            loss_tac = F.mse_loss(rec, tac_patches)
+        else:
+            pred = linear(decoded[br, masked_tac], sd, "to_tactiles")
+            rec[br, masked_tac - n_img] = pred
+            loss_tac = F.mse_loss(pred, tac_patches[br, masked_tac - n_img])
         out["tactile_rec"] = unpatchify_tactile(rec, nt, H // ph, W // pw, ph, pw)
         out["tactile_masked"] = unpatchify_tactile(vis, nt, H // ph, W // pw, ph, pw)
-        out["recon_loss_tactile"] = F.mse_loss(pred, tac_patches[br, masked_tac - n_img])
+        out["recon_loss_tactile"] = loss_tac
     return out
 
 

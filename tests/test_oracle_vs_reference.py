@@ -49,10 +49,11 @@ def test_forward_backward_and_embeddings_match_reference(ecm, nt, sincos):
                                mae.get_embeddings(x, eval=False, use_tactile=False))
 
 
-@pytest.mark.parametrize("nt,sincos,ratio", [(2, True, None), (2, False, 0.5), (0, True, 0.8)])
-def test_reconstruct_matches_reference(nt, sincos, ratio):
+@pytest.mark.parametrize("nt,sincos,ratio,ecm", [(2, True, None, False), (2, False, 0.5, False), (0, True, 0.8, False),
+                                                 (2, True, 0.6, True)])
+def test_reconstruct_matches_reference(nt, sincos, ratio, ecm):
     """VTMAE.reconstruct (pretrain_models.py:344-586): per-modality mask counts, rec / masked maps, losses."""
-    cfg = O.VTMAEConfig(num_tactiles=nt, use_sincosmod_encodings=sincos, depth=2, decoder_depth=1)
+    cfg = O.VTMAEConfig(num_tactiles=nt, use_sincosmod_encodings=sincos, depth=2, decoder_depth=1, early_conv_masking=ecm)
     mae = R.build_reference_model(cfg, seed=5)
     sd = O.canonical({k: v.clone() for k, v in mae.state_dict().items()})
     g = torch.Generator().manual_seed(11)

@@ -149,10 +149,10 @@ def test_standalone_transformer_matches_oracle():
         assert cos(p.grad, sd["transformer." + k].grad) >= 0.999, k
 
 
-@pytest.mark.parametrize("nt,ratio", [(2, None), (2, 0.5), (0, 0.8)])
-def test_reconstruct_vs_oracle(nt, ratio):
+@pytest.mark.parametrize("nt,ratio,ecm", [(2, None, False), (2, 0.5, False), (0, 0.8, False), (2, 0.6, True)])
+def test_reconstruct_vs_oracle(nt, ratio, ecm):
     """VTMAE.reconstruct (pretrain_models.py:344-586): same dict, same masked patches, reconstruction close."""
-    cfg = O.VTMAEConfig(num_tactiles=nt, depth=2, decoder_depth=2)
+    cfg = O.VTMAEConfig(num_tactiles=nt, depth=2, decoder_depth=2, early_conv_masking=ecm)
     sd = O.init_state_dict(cfg, seed=6)
     gen = torch.Generator().manual_seed(8)
     B = 3
