@@ -275,6 +275,23 @@ def run_gpu_arm(args):
         ev.record()
     h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4
     e2e_steps = args.steps
+    # H2D alone (reported next to e2e: the floor the PCIe link sets for a step)
+    barrier()
+    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hs.record(copy_stream)
+    for i in range(4):
+        prefetch(i)
+        consumed[i % 2].record(copy_stream)
+    he.record(copy_stream)
+    barrier()
+    h2d_ms = hs.elapsed_time(he) / 4
+    for ev in consumed:
+        ev.record()
+    # every step's loss is copied D2H into pinned memory on the compute stream and READ by the host one
+    # step later (after its event), so the host never drains the GPU queue; all K losses are read
+    # inside the timed region
+    loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(e2e_steps)]
     barrier()
     t0 = time.perf_counter()
     s.record()
@@ -287,9 +304,16 @@ def run_gpu_arm(args):
         torch.cuda.current_stream().wait_event(ready[slot])
         l = trainer.step(stage[slot][0], noise=stage[slot][1])
         consumed[slot].record()
-        losses.append(float(l.item()))        # D2H read of the step result
+        loss_host[i:i + 1].copy_(l.reshape(1), non_blocking=True)     # D2H of the step result
+        loss_ev[i].record()
+        if i > 0:
+            loss_ev[i - 1].synchronize()
+            losses.append(float(loss_host[i - 1]))
+    loss_ev[e2e_steps - 1].synchronize()
+    losses.append(float(loss_host[e2e_steps - 1]))
     e.record()
     barrier()
+    assert len(losses) == e2e_steps and all(x == x for x in losses)
     ms_e2e = s.elapsed_time(e)
     t = torch.tensor([ms_e2e], device=dev)
     if world > 1:
@@ -312,8 +336,9 @@ def run_gpu_arm(args):
                        "cuda_graph": bool(trainer.use_graph), "loss_last_step": loss_val},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "note": "pinned host batch -> H2D prefetched one step ahead on a copy stream; loss.item() every step",
-                    "wall_s": wall_e2e},
+                    "note": "pinned host batch -> H2D prefetched one step ahead on a copy stream; every step's loss "
+                            "copied D2H to pinned memory and read by the host one step later",
+                    "h2d_ms_per_step_alone": h2d_ms, "wall_s": wall_e2e},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "roofline": roof,

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libm3l_b200.so"
+# M3L_B200_LIB: development override (A/B runs of kernel variants built next to the shipped library)
+_LIB_PATH = Path(os.environ.get("M3L_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libm3l_b200.so"))
 _lib = None
 
 

@@ -21,6 +21,14 @@
 #include "common.cuh"
 #include "m3l_internal.h"
 
+// Cycle-counter probes (tools/attn_probe.py) are compiled in only with -DM3L_ATTN_PROFILE: the counters
+// cost 18 registers in the backward kernel (spills) and a CS2R per phase.
+#ifdef M3L_ATTN_PROFILE
+#define M3L_CLK() clock64()
+#else
+#define M3L_CLK() 0LL
+#endif
+
 namespace m3l {
 namespace {
 
@@ -196,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int nchunks = (NK + 31) / 32;
     int it = 0, jt = 0;
     long long pf_ws = 0, pf_p1 = 0, pf_p2 = 0, pf_wo = 0, pf_ep = 0, pf_n = 0;
-    const long long pf_t0 = clock64();
+    const long long pf_t0 = M3L_CLK();
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int h = item % p.heads, b = item / p.heads;
       for (int t = 0; t < p.q_tiles; ++t, ++jt) {
@@ -205,10 +213,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int grow = t * p.tile_rows + row;
         const bool warp_active = (quad * 32 < p.tile_rows) && (t * p.tile_rows + quad * 32 < n);
         const bool valid = row < p.tile_rows && grow < n;
-        long long c0 = clock64();
+        long long c0 = M3L_CLK();
         mbar_wait(&bars->s_full[wg], ph);
         tc_fence_after_sync();
-        long long c1 = clock64(); pf_ws += c1 - c0;
+        long long c1 = M3L_CLK(); pf_ws += c1 - c0;
         float mx = -INFINITY, sum = 0.f;
         if (warp_active) {
           for (int c = 0; c < nchunks; ++c) {
@@ -220,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
           const float mxs = mx * sl2;
-          { long long c2 = clock64(); pf_p1 += c2 - c1; c1 = c2; }
+          { long long c2 = M3L_CLK(); pf_p1 += c2 - c1; c1 = c2; }
           for (int c = 0; c < nchunks; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(t_row + c * 32, v);
@@ -248,11 +256,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(&bars->p_full[wg]);
-        { long long c2 = clock64(); pf_p2 += c2 - c1; c1 = c2; }
+        { long long c2 = M3L_CLK(); pf_p2 += c2 - c1; c1 = c2; }
         // ---- epilogue
         mbar_wait(&bars->o_full[wg], ph);
         tc_fence_after_sync();
-        { long long c2 = clock64(); pf_wo += c2 - c1; c1 = c2; }
+        { long long c2 = M3L_CLK(); pf_wo += c2 - c1; c1 = c2; }
         if (warp_active) {
           const float inv = 1.0f / sum;
           uint32_t o0[32], o1[32];
@@ -280,12 +288,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         tc_fence_before_sync();
         mbar_arrive(&bars->slot_free[wg]);
-        { long long c2 = clock64(); pf_ep += c2 - c1; pf_n += 1; }
+        { long long c2 = M3L_CLK(); pf_ep += c2 - c1; pf_n += 1; }
       }
     }
     if (p.prof && blockIdx.x == 0 && warp == 2 && lane == 0) {
       p.prof[0] = pf_ws; p.prof[1] = pf_p1; p.prof[2] = pf_p2; p.prof[3] = pf_wo; p.prof[4] = pf_ep;
-      p.prof[5] = pf_n; p.prof[6] = clock64() - pf_t0;
+      p.prof[5] = pf_n; p.prof[6] = M3L_CLK() - pf_t0;
     }
   }
   tc_fence_before_sync();
@@ -510,17 +518,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             if (j2 == p.key_tiles) { j2 = 0; ++it2; }
             if (it2 < my_items && (it2 == it || cross)) {
               if (it2 != it) wait_loads(it2);
-              long long c0 = clock64();
+              long long c0 = M3L_CLK();
               mbar_wait(&bars->sdp_free, g & 1);       // the producers hold step g's S / dP in registers
               tc_fence_after_sync();
-              long long c1 = clock64(); m_w1 += c1 - c0;
+              long long c1 = M3L_CLK(); m_w1 += c1 - c0;
               issue_sdp(it2, j2, i2);
-              if (serial) { mbar_wait(&bars->sdp_full, (g + 1) & 1); m_sdp += clock64() - c1; }
+              if (serial) { mbar_wait(&bars->sdp_full, (g + 1) & 1); m_sdp += M3L_CLK() - c1; }
             }
             // ---- wait for P_ij / dS_ij, then the three accumulating products
-            long long c2 = clock64();
+            long long c2 = M3L_CLK();
             mbar_wait(&bars->pds_full, g & 1);
-            long long c3 = clock64(); m_w2 += c3 - c2;
+            long long c3 = M3L_CLK(); m_w2 += c3 - c2;
             if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);               // dV/dK accumulators drained
             if (j == 0 && i == 0 && it > 0) mbar_wait(&bars->item_done, (it - 1) & 1);   // dQ accumulators drained
             tc_fence_after_sync();
@@ -543,7 +551,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
               ++dk;
               if (j == jl - 1) umma_commit(&bars->kva_empty);        // last product on the early key tiles
             }
-            if (serial) { long long c4 = clock64(); mbar_wait(&bars->pds_free, g & 1); m_acc += clock64() - c4; }
+            if (serial) { long long c4 = M3L_CLK(); mbar_wait(&bars->pds_free, g & 1); m_acc += M3L_CLK() - c4; }
           }
         }
         umma_commit(&bars->qdo_empty[qdo_buf(it)]);
@@ -560,10 +568,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint32_t p_slab = smem_u32(sP + wg * 16384), ds_slab = smem_u32(sDS + wg * 16384);
     const float sl2 = p.scale * kLog2e;
     int g = 0, dk = 0;
-    const long long pf_t0 = clock64();
+    const long long pf_t0 = M3L_CLK();
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pc = pf_t0;
-#define PF(k) { const long long c_ = clock64(); pf[k] += c_ - pc; pc = c_; }
+#define PF(k) { const long long c_ = M3L_CLK(); pf[k] += c_ - pc; pc = c_; }
     // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile; with a
     // precomputed delta the next item's values are fetched one item ahead
     float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f}, delta_n[2] = {0.f, 0.f}, l2_n[2] = {0.f, 0.f};
@@ -713,7 +721,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const int o = warp == 2 ? 0 : 16;
       for (int k = 0; k < 8; ++k) p.prof[o + k] = pf[k];
       p.prof[o + 8] = g;
-      p.prof[o + 9] = clock64() - pf_t0;
+      p.prof[o + 9] = M3L_CLK() - pf_t0;
     }
   }
   tc_fence_before_sync();

@@ -11,8 +11,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 model = bench.build_model(dev)
-tr = FusedTrainer(model, use_cuda_graph=False)
 A = model._sync()
+tr = FusedTrainer(model, use_cuda_graph=False)
 x_host, noise_host = bench.synth_batch(B, 1234)
 xs = {k: v.to(dev) for k, v in x_host.items()}
 noise = noise_host.to(dev)
