@@ -106,3 +106,29 @@ def test_train_step_matches_reference_optimizer():
     ref_sd = mae.state_dict()
     for k in O.param_keys(sd):
         assert torch.allclose(sd[k].detach(), ref_sd[k], rtol=1e-6, atol=1e-8), k
+
+
+def test_dino_tac_mae_config_matches_reference():
+    """BASELINE.json configs[3], MAE side: 70x70 maps, patch 14, dim 384, tactile-only call (x without 'image':
+    pretrain_models.py:148-152), mask 0.8 (train_dino_tac_mae.py:76-80,139-164)."""
+    cfg = O.VTMAEConfig(image_size=(70, 70), tactile_size=(70, 70), image_patch_size=14, tactile_patch_size=14,
+                        dim=384, depth=2, heads=4, mlp_dim=768, decoder_dim=384, decoder_depth=1, decoder_heads=4,
+                        masking_ratio=0.8)
+    mae = R.build_reference_model(cfg, seed=9)
+    sd = O.canonical({k: v.clone() for k, v in mae.state_dict().items()})
+    g = torch.Generator().manual_seed(21)
+    B = 3
+    x = {f"tactile{i + 1}": torch.rand(B, 12, 70, 70, generator=g) for i in range(2)}
+    noise = O.tie_free_noise(B, 2 * cfg.n_tac, g, [cfg.n_tac] * 2)
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    loss = O.vtmae_forward(sd, cfg, x, noise)
+    loss.backward()
+    # tactile-only: the reference still draws an empty (B, 0) image noise first (:229)
+    with R.injected_noise([noise[:, :0]] + R.split_noise(noise, cfg, False, True)):
+        lref = mae(x)
+    lref.backward()
+    assert torch.equal(loss.detach(), lref.detach())
+    for k, p in mae.named_parameters():
+        if k in sd and p.grad is not None:
+            assert torch.allclose(sd[k].grad, p.grad, rtol=1e-5, atol=1e-7), k

@@ -105,6 +105,36 @@ def test_all_gradients_vs_oracle_canonical(nt, ecm):
     assert cos(torch.cat(flat_a), torch.cat(flat_b)) >= 0.9995
 
 
+def test_dino_tac_mae_shape_vs_oracle():
+    """BASELINE.json configs[3] (DINO-tac-MAE, MAE side): VTT(70x70, patch 14, dim 384, depth 4, heads 4,
+    mlp 768, C=12) + VTMAE(r=0.8, decoder_dim 384, depth 3, heads 4) run tactile-only (x without 'image',
+    train_dino_tac_mae.py:76-80,139-164): 50 tokens, 40 masked, 10 visible; inner (256) != dim (384)."""
+    cfg = O.VTMAEConfig(image_size=(70, 70), tactile_size=(70, 70), image_patch_size=14, tactile_patch_size=14,
+                        dim=384, depth=4, heads=4, mlp_dim=768, decoder_dim=384, decoder_depth=3, decoder_heads=4,
+                        masking_ratio=0.8)
+    sd = O.init_state_dict(cfg, seed=4)
+    gen = torch.Generator().manual_seed(17)
+    B = 6
+    x = {f"tactile{i + 1}": torch.rand(B, 12, 70, 70, generator=gen) for i in range(2)}
+    noise = O.tie_free_noise(B, 2 * cfg.n_tac, gen, [cfg.n_tac] * 2)
+    mae = build_product(cfg, weights=sd)
+    loss = mae(to_dev(x), noise=noise.to(DEV))
+    loss.backward()
+    assert mae.last_masked_indices.shape == (B, 40) and mae.last_unmasked_indices.shape == (B, 10)
+    lref, gref = _oracle_grads(cfg, sd, x, noise)
+    assert abs(loss.item() - lref.item()) <= 1e-2 * abs(lref.item())
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    for k, gr in gref.items():
+        if gr is None:
+            assert named[k].grad is None, k
+        else:
+            assert cos(named[k].grad, gr) >= 0.999, (k, cos(named[k].grad, gr))
+    with torch.no_grad():
+        emb = mae.get_embeddings(to_dev(x), eval=False)
+    ref = O.vtmae_embeddings(sd, cfg, x)
+    assert emb.shape == ref.shape == (B, 50, 384) and cos(emb, ref) >= 0.9995
+
+
 def test_embeddings_backward_vs_oracle():
     cfg = O.VTMAEConfig(depth=2)
     sd = O.init_state_dict(cfg, seed=2)
