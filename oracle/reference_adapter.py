@@ -77,3 +77,27 @@ def split_noise(noise, cfg, use_vision=True, use_tactile=True):
         for _ in range(cfg.num_tactiles):
             segs.append(noise[:, off:off + cfg.n_tac]); off += cfg.n_tac
     return segs
+
+
+def load_reference_vtt_module():
+    """The unmodified /root/reference/models/VTT.py (DINO-side encoder), behind the omegaconf / lightning shims."""
+    if not (REFERENCE_ROOT / "models" / "VTT.py").exists():
+        raise FileNotFoundError("reference tree not present")
+    for p in (str(STUBS), str(REFERENCE_ROOT)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return importlib.import_module("models.VTT")
+
+
+def build_reference_vtt_dino(cfg, seed: int = 0):
+    """Reference models/VTT.py::VTT for an oracle VTTDinoConfig (ctor call as models/ppo_dino.py:563-578)."""
+    ref = load_reference_vtt_module()
+    torch.manual_seed(seed)
+    return ref.VTT(image_size=cfg.image_size, tactile_size=cfg.tactile_size, image_patch_size=cfg.image_patch_size,
+                   tactile_patch_size=cfg.tactile_patch_size, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads,
+                   mlp_dim=cfg.mlp_dim, num_tactiles=cfg.num_tactiles, image_channels=cfg.image_channels,
+                   tactile_channels=cfg.tactile_channels, dim_head=cfg.dim_head,
+                   num_register_tokens=cfg.num_register_tokens, pos_embed_fn="sinusoidal")

@@ -132,3 +132,63 @@ def test_dino_tac_mae_config_matches_reference():
     for k, p in mae.named_parameters():
         if k in sd and p.grad is not None:
             assert torch.allclose(sd[k].grad, p.grad, rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("regs,with_masks", [(1, False), (1, True), (0, False), (2, True)])
+def test_vtt_dino_forward_features_match_reference(regs, with_masks):
+    """models/VTT.py::VTT.forward_features (SURVEY §8 a-16): sinusoidal table, three patch embeddings, shared
+    keep-index masks, register tokens, final LayerNorm(eps=1e-6)."""
+    from oracle import vtt_dino_oracle as VD
+    cfg = VD.VTTDinoConfig(depth=2, num_register_tokens=regs)
+    ref = R.build_reference_vtt_dino(cfg, seed=13)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    if regs:                                    # std 1e-6 at init (models/VTT.py:225): make them matter
+        with torch.no_grad():
+            ref.register_tokens.normal_(0, 0.5)
+        sd["register_tokens"] = ref.register_tokens.detach().clone()
+    g = torch.Generator().manual_seed(3)
+    B = 3
+    x = {"image": torch.rand(B, 12, 64, 64, generator=g), "tactile1": torch.rand(B, 12, 32, 32, generator=g),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=g)}
+    masks = None
+    if with_masks:
+        masks = [torch.stack([torch.randperm(64, generator=g)[:k] for _ in range(B)]) for k in (40, 40)]
+    assert torch.equal(VD.sinusoidal_table(cfg.pos_grid, cfg.dim), ref.pos_embed(torch.device("cpu")))
+    for k in sd:
+        if sd[k].dtype.is_floating_point and k != "pos_embed.frequency_bands":
+            sd[k].requires_grad_(True)
+    out = VD.forward_features(sd, cfg, x, masks)
+    want = ref.forward_features(x, masks)
+    for k in ("x_norm_regtokens", "x_norm_patchtokens", "x_prenorm"):
+        assert out[k].shape == want[k].shape and torch.equal(out[k].detach(), want[k].detach()), k
+    w = torch.randn(out["x_prenorm"].shape, generator=g)
+    (VD.forward_features(sd, cfg, x, masks)["x_norm_patchtokens"].sum() + (out["x_norm_regtokens"] ** 2).sum()).backward()
+    o2 = ref.forward_features(x, masks)
+    (o2["x_norm_patchtokens"].sum() + (want["x_norm_regtokens"] ** 2).sum()).backward()
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+        else:
+            assert torch.allclose(sd[k].grad, p.grad, rtol=1e-5, atol=1e-7), k
+
+
+def test_vtt_dino_product_module_mirrors_reference_state_dict():
+    """m3l_b200.vtt.VTT: same state_dict keys / shapes / buffers as models/VTT.py::VTT, same init statistics."""
+    from oracle import vtt_dino_oracle as VD
+    from m3l_b200.vtt import VTT
+    cfg = VD.VTTDinoConfig(num_register_tokens=1)
+    ref = R.build_reference_vtt_dino(cfg, seed=0)
+    torch.manual_seed(0)
+    mine = VTT(image_size=cfg.image_size, tactile_size=cfg.tactile_size, image_patch_size=cfg.image_patch_size,
+               tactile_patch_size=cfg.tactile_patch_size, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim,
+               num_tactiles=cfg.num_tactiles, image_channels=cfg.image_channels, tactile_channels=cfg.tactile_channels,
+               dim_head=cfg.dim_head, num_register_tokens=1, pos_embed_fn="sinusoidal")
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+    assert torch.equal(a["pos_embed.frequency_bands"], b["pos_embed.frequency_bands"])
+    assert torch.equal(ref.pos_embed(torch.device("cpu")), mine.pos_embed(torch.device("cpu")))
+    w = b["transformer.layers.0.1.net.1.weight"]
+    assert abs(float(w.std()) - 0.02) < 2e-3 and float(b["transformer.layers.0.1.net.1.bias"].abs().max()) == 0.0
+    mine.load_state_dict(a)

@@ -1,0 +1,81 @@
+"""GPU parity of m3l_b200.vtt.VTT (drop-in for /root/reference/models/VTT.py::VTT) against the CPU
+oracle (oracle/vtt_dino_oracle.py, pinned bit-for-bit against the unmodified reference in
+tests/test_oracle_vs_reference.py).  Tolerances as for the MAE path: outputs cosine >= 0.9995, every parameter
+gradient cosine >= 0.999 (bf16 tensor-core compute, fp32 LayerNorm / softmax / accumulation)."""
+import pytest
+import torch
+
+from oracle import vtt_dino_oracle as VD
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cos(a, b):
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
+    return float(a @ b / (a.norm() * b.norm() + 1e-300))
+
+
+def build(cfg, seed):
+    from m3l_b200.vtt import VTT
+    torch.manual_seed(seed)
+    m = VTT(image_size=cfg.image_size, tactile_size=cfg.tactile_size, image_patch_size=cfg.image_patch_size,
+            tactile_patch_size=cfg.tactile_patch_size, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim,
+            num_tactiles=cfg.num_tactiles, image_channels=cfg.image_channels, tactile_channels=cfg.tactile_channels,
+            dim_head=cfg.dim_head, num_register_tokens=cfg.num_register_tokens, pos_embed_fn="sinusoidal")
+    with torch.no_grad():
+        if m.register_tokens is not None:
+            m.register_tokens.normal_(0, 0.5)
+        for k, p in m.named_parameters():       # timm init has zero biases / unit LN: perturb so every term matters
+            if k.endswith(".bias"):
+                p.normal_(0, 0.05)
+            elif p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    return m
+
+
+@pytest.mark.parametrize("regs,n_masks,keep,heads", [(1, 0, 0, 8), (1, 2, 40, 8), (0, 1, 17, 4), (2, 3, 8, 4)])
+def test_forward_features_and_grads_vs_oracle(regs, n_masks, keep, heads):
+    cfg = VD.VTTDinoConfig(depth=2, num_register_tokens=regs, heads=heads)
+    m = build(cfg, seed=20 + regs)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(31)
+    B = 3
+    x = {"image": torch.rand(B, 12, 64, 64, generator=g), "tactile1": torch.rand(B, 12, 32, 32, generator=g),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=g)}
+    masks = [torch.stack([torch.randperm(64, generator=g)[:keep] for _ in range(B)]) for _ in range(n_masks)] or None
+    out = m.forward_features({k: v.to(DEV) for k, v in x.items()}, [mk.to(DEV) for mk in masks] if masks else None)
+    for k in sd:
+        if sd[k].dtype.is_floating_point and k != "pos_embed.frequency_bands":
+            sd[k].requires_grad_(True)
+    ref = VD.forward_features(sd, cfg, x, masks)
+    for k in ("x_norm_regtokens", "x_norm_patchtokens", "x_prenorm"):
+        assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32, k
+        if out[k].numel():
+            assert cos(out[k], ref[k]) >= 0.9995, (k, cos(out[k], ref[k]))
+    w1 = torch.randn(ref["x_norm_patchtokens"].shape, generator=g)
+    w2 = torch.randn(ref["x_prenorm"].shape, generator=g)
+    ((out["x_norm_patchtokens"] * w1.to(DEV)).sum() + (out["x_norm_regtokens"] ** 2).sum()
+     + 0.5 * (out["x_prenorm"] * w2.to(DEV)).sum()).backward()
+    ((ref["x_norm_patchtokens"] * w1).sum() + (ref["x_norm_regtokens"] ** 2).sum() + 0.5 * (ref["x_prenorm"] * w2).sum()).backward()
+    named = dict(m.named_parameters())
+    for k, p in named.items():
+        gr = sd[k].grad
+        if gr is None or float(gr.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert p.grad is not None and cos(p.grad, gr) >= 0.999, (k, cos(p.grad, gr) if p.grad is not None else None)
+
+
+def test_forward_returns_patch_tokens_and_fails_on_cpu():
+    from m3l_b200._lib import M3LError
+    cfg = VD.VTTDinoConfig(depth=1, num_register_tokens=1)
+    m = build(cfg, seed=1)
+    x = {"image": torch.rand(2, 12, 64, 64), "tactile1": torch.rand(2, 12, 32, 32), "tactile2": torch.rand(2, 12, 32, 32)}
+    with pytest.raises(M3LError):
+        m(x)
+    m = m.to(DEV)
+    with torch.no_grad():
+        y = m({k: v.to(DEV) for k, v in x.items()})
+    assert y.shape == (2, 192, 256)
