@@ -139,6 +139,65 @@ M3L_DEVINL float gelu_erf_grad(float x) {
   return fmaf(x, g.pdf, g.cdf);
 }
 
+// ---- packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per issue slot) -----------------
+// The issue-bound epilogues (exact-erf GELU: ~20 scalar instructions per element) spend most of their slots
+// on FFMA / FMUL / FADD; the packed forms halve that with bit-identical per-lane arithmetic.
+typedef unsigned long long f32x2;
+M3L_DEVINL f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+M3L_DEVINL f32x2 f2_packu(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+M3L_DEVINL void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+M3L_DEVINL void f2_unpacku(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+M3L_DEVINL f32x2 f2_splat(float c) { return f2_pack(c, c); }
+M3L_DEVINL f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+M3L_DEVINL f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+M3L_DEVINL f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// GELU(x) and GELU'(x) of two pre-activations at once; same Abramowitz & Stegun 7.1.26 evaluation as
+// gelu_parts (one MUFU.RCP + one MUFU.EX2 per element), polynomial / products in packed fp32.
+//   u = 0.5 poly(t) t e,  Phi(x) = x >= 0 ? 1 - u : u = base + sg * (-u),  sg = copysign(1, x), base = (sg + 1) / 2
+M3L_DEVINL void gelu_pair(uint32_t x0u, uint32_t x1u, f32x2& gelu, f32x2& dgelu) {
+  const f32x2 x = f2_packu(x0u, x1u);
+  const f32x2 ax = f2_packu(x0u & 0x7fffffffu, x1u & 0x7fffffffu);
+  const f32x2 sg = f2_packu((x0u & 0x80000000u) | 0x3f800000u, (x1u & 0x80000000u) | 0x3f800000u);
+  const f32x2 den = f2_fma(ax, f2_splat(0.3275911f * 0.70710678118654752f), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(den, d0, d1);
+  const f32x2 t = f2_pack(__fdividef(1.0f, d0), __fdividef(1.0f, d1));           // MUFU.RCP x 2
+  const f32x2 ea = f2_mul(f2_mul(x, x), f2_splat(-0.5f * 1.4426950408889634f));
+  float a0, a1;
+  f2_unpack(ea, a0, a1);
+  const f32x2 e = f2_pack(exp2f(a0), exp2f(a1));                                  // exp(-x^2 / 2), MUFU.EX2 x 2
+  // -0.5 * poly(t): coefficients pre-multiplied
+  f32x2 q = f2_fma(f2_splat(-0.5f * 1.061405429f), t, f2_splat(0.5f * 1.453152027f));
+  q = f2_fma(q, t, f2_splat(-0.5f * 1.421413741f));
+  q = f2_fma(q, t, f2_splat(0.5f * 0.284496736f));
+  q = f2_fma(q, t, f2_splat(-0.5f * 0.254829592f));
+  const f32x2 nu = f2_mul(f2_mul(q, t), e);                                       // -u
+  const f32x2 base = f2_fma(sg, f2_splat(0.5f), f2_splat(0.5f));
+  const f32x2 cdf = f2_fma(sg, nu, base);
+  gelu = f2_mul(x, cdf);
+  dgelu = f2_fma(f2_mul(x, e), f2_splat(0.39894228040143268f), cdf);
+}
+
 M3L_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

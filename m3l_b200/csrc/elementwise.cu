@@ -882,6 +882,15 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
     const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
     int sensor;
     const float* origin = patch_origin(ps, b, tok, &sensor);
+    // the predictions of this row are requested BEFORE the target gather so that both global round trips
+    // overlap (they used to be exposed back to back, one row at a time per warp)
+    const float* prow = pred + (size_t)r * P;
+    float4 pvr[kMseMaxT];
+#pragma unroll
+    for (int t = 0; t < kMseMaxT; ++t) {
+      const int e = t * 128 + lane * 4;
+      if (e < P) pvr[t] = __ldcs(reinterpret_cast<const float4*>(prow + e));
+    }
     for (int i = lane; i < src_rows; i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
       const int p1 = i / ps.C, c = i - p1 * ps.C;
       const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
@@ -897,7 +906,6 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
       }
     }
     __syncwarp();
-    const float* prow = pred + (size_t)r * P;
     bf16* drow = dpred + (size_t)r * P;
 #pragma unroll
     for (int t = 0; t < kMseMaxT; ++t) {
@@ -905,7 +913,7 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
       if (e < P) {
         const int p1 = e / rowlen;
         const float4 tv = *reinterpret_cast<const float4*>(patch + p1 * pitch + (e - p1 * rowlen));
-        const float4 pv = *reinterpret_cast<const float4*>(prow + e);
+        const float4 pv = pvr[t];
         const float d0 = pv.x - tv.x, d1 = pv.y - tv.y, d2 = pv.z - tv.z, d3 = pv.w - tv.w;
         acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         const float g0 = w2 * d0, g1 = w2 * d1, g2 = w2 * d2, g3 = w2 * d3;

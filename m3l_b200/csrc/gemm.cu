@@ -425,11 +425,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (p.aux_out != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-                const GeluParts g0 = gelu_parts(x0), g1 = gelu_parts(x1);
-                w[j] = pack_bf16x2(fmaf(x0, g0.pdf, g0.cdf), fmaf(x1, g1.pdf, g1.cdf));
-                v[2 * j] = __float_as_uint(x0 * g0.cdf);
-                v[2 * j + 1] = __float_as_uint(x1 * g1.cdf);
+                f32x2 hh, gg;
+                gelu_pair(v[2 * j], v[2 * j + 1], hh, gg);
+                float g0, g1;
+                f2_unpack(gg, g0, g1);
+                w[j] = pack_bf16x2(g0, g1);
+                f2_unpacku(hh, v[2 * j], v[2 * j + 1]);
               }
               stage_and_store(&map_aux, w, gcol, row0, false);
             } else {
