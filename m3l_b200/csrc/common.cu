@@ -55,7 +55,7 @@ static void bind_primary_context() {
 }
 
 static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize,
-                        uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+                        uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, int row_bytes = 128) {
   bind_primary_context();
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
@@ -68,10 +68,10 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
   M3L_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows %u out of range", box_rows);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * esize};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box_rows=%u esize=%d) failed: %d",
@@ -85,6 +85,11 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows) {
   return make_tmap_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, ld, box_rows);
+}
+
+int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, ld, box_rows, 64);
 }
 
 int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,

@@ -436,6 +436,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
 // (128 B, SWIZZLE_128B) x box_rows rows.  Out-of-bounds elements are zero-filled.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows);
+// bf16 with a 32-column box (64 B rows, SWIZZLE_64B): the half-width epilogue tiles of gemm_gelu.cu
+int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld, uint32_t box_rows);
 // same for fp32: box = 32 columns (128 B, SWIZZLE_128B) x box_rows rows
 int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t ld, uint32_t box_rows);

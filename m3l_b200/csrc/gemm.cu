@@ -435,7 +435,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               stage_and_store(&map_aux, w, gcol, row0, false);
             } else {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf(__uint_as_float(v[j])));
+              for (int j = 0; j < 32; ++j) {      // same packed evaluation as above: eval and training agree bitwise
+                f32x2 hh, gg;
+                gelu_pair(v[2 * j], v[2 * j + 1], hh, gg);
+                f2_unpacku(hh, v[2 * j], v[2 * j + 1]);
+              }
             }
           }
           if (has_side) {
@@ -634,6 +638,17 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   plan->ws = ws_allowed && !p.a_mn_major && kb_total <= kWsMaxKb && p.splits == 1 && bn >= 128 &&
              p.residual == nullptr && p.dot_out == nullptr && p.act != 2 && tiles >= 2 * device_sm_count() &&
              tiles_n <= plan->grid;
+  // decoder feed-forward forward shape (GELU + GELU' outputs, K <= 256, N % 256 == 0): dedicated kernel
+  // with 16 epilogue warps (M3L_GELU16=0 falls back to the generic epilogue, for A/B measurements)
+  static const bool g16_allowed = [] { const char* e = getenv("M3L_GELU16"); return !(e && e[0] == '0'); }();
+  plan->gelu16 = g16_allowed && plan->ws && bn == 256 && p.act == 1 && p.out_mode == 0 && p.N % 256 == 0 &&
+                 p.colsum_out == nullptr;
+  if (plan->gelu16) {
+    if ((s = make_tmap_2d_bf16_sw64(&plan->map_out32, p.out, p.M, p.N, p.ldo, 32))) return s;
+    plan->map_aux32 = plan->map_out32;
+    if (p.aux_out != nullptr &&
+        (s = make_tmap_2d_bf16_sw64(&plan->map_aux32, p.aux_out, p.M, p.N, p.ld_aux, 32))) return s;
+  }
   if (p.colsum_out != nullptr) {
     M3L_REQUIRE(p.out_mode == 0, "gemm: colsum_out needs the bf16 output mode");
     // keep every CTA on one N tile so the column sums stay in registers across its tiles
@@ -643,6 +658,7 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
 }
 
 int gemm_run(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.gelu16) return gemm_gelu16_run(plan, stream);
   switch (plan.bn) {
     case 64: return launch_bn<64>(plan, stream);
     case 128: return launch_bn<128>(plan, stream);

@@ -38,10 +38,13 @@ struct GemmPlan {
   int bn = 0;
   int grid = 0;
   bool ws = false;          // weight-stationary schedule (gemm.cu)
+  bool gelu16 = false;      // FF1 forward shape: the 16-epilogue-warp GELU kernel (gemm_gelu.cu)
+  CUtensorMap map_out32, map_aux32;   // its 32-column (64 B, SWIZZLE_64B) output tiles
 };
 
 int gemm_pick_bn(int M, int N);
 int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn /*0 = auto*/);
 int gemm_run(const GemmPlan& plan, cudaStream_t stream);
+int gemm_gelu16_run(const GemmPlan& plan, cudaStream_t stream);   // gemm_gelu.cu
 
 }  // namespace m3l

@@ -84,6 +84,31 @@ def test_gemm_epilogues(ops):
     assert rel_err(inplace, z + bias + res.float()) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(12288 + 77, 1024, 256), (49152, 1024, 256), (20000, 512, 192)])
+def test_gemm_gelu_fwd_16_warp_kernel(ops, M, N, K):
+    """Feed-forward forward shapes that take the dedicated 16-epilogue-warp GELU kernel (gemm_gelu.cu:
+    weight-stationary, N % 256 == 0, K <= 256, >= 2 tiles per SM), ragged M tail included: GELU and GELU'
+    against torch, and elementwise against the generic epilogue (M3L_GELU16 is read once, so the generic
+    path is reached through BN = 128 here)."""
+    torch.manual_seed(3)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.07).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    dg = torch.full((M, N), 9.0, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=dg, bn=256)
+    z = a.float() @ b.float().T + bias
+    zz = z.clone().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    assert rel_err(h, F.gelu(z)) < 1e-2 and rel_err(dg, zz.grad) < 1e-2
+    dg2 = torch.empty_like(dg)
+    h2 = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=dg2, bn=128)
+    # same fp32 accumulators and the same A&S erf; only the packed-vs-scalar association of the last products
+    # differs, i.e. at most one bf16 ulp on a few elements
+    assert (h.float() - h2.float()).abs().max() <= 2 ** -7 * max(1.0, float(h2.float().abs().max()))
+    assert (dg.float() - dg2.float()).abs().max() <= 2 ** -7 * 2.0
+    assert float((h != h2).float().mean()) < 0.02 and float((dg != dg2).float().mean()) < 0.02
+
+
 # ------------------------------------------------------------------------------- mask indices
 @pytest.mark.parametrize("B,segs", [(37, [(0, 64, 60), (64, 64, 61), (128, 64, 61)]), (5, [(0, 64, 60)]),
                                     (9, [(0, 25, 20), (25, 25, 20)]), (3, [(0, 300, 17)])])
