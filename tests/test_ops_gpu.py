@@ -107,6 +107,18 @@ def test_gemm_gelu_fwd_16_warp_kernel(ops, M, N, K):
     assert (h.float() - h2.float()).abs().max() <= 2 ** -7 * max(1.0, float(h2.float().abs().max()))
     assert (dg.float() - dg2.float()).abs().max() <= 2 ** -7 * 2.0
     assert float((h != h2).float().mean()) < 0.02 and float((dg != dg2).float().mean()) < 0.02
+    # backward through the GELU at the same shape (generic epilogue; a 16-warp variant with a single staging
+    # buffer per warp measured no faster: 49 vs 49 us): dPre = (dY W2) * GELU', fused column sums (bias gradient)
+    dy = torch.randn(M, K, device=DEV).bfloat16()
+    cs = torch.ones(N, device=DEV)
+    dpre = ops.gemm(dy, b, act=ops.GELU_BWD, aux_in=dg, colsum_out=cs, bn=256)
+    zb = dy.float() @ b.float().T
+    assert rel_err(dpre, zb * dg.float()) < 1e-2
+    assert rel_err(cs, 1 + dpre.float().sum(0)) < 1e-4
+    cs128 = torch.ones(N, device=DEV)
+    dpre128 = ops.gemm(dy, b, act=ops.GELU_BWD, aux_in=dg, colsum_out=cs128, bn=128)
+    assert torch.equal(dpre, dpre128) and rel_err(cs, cs128) < 1e-5
+    assert torch.equal(ops.gemm(dy, b, act=ops.GELU_BWD, aux_in=dg, bn=256), dpre)
 
 
 # ------------------------------------------------------------------------------- mask indices
