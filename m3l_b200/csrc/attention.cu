@@ -734,95 +734,157 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
 // ------------------------------------------------------------------------------------------
 // short sequences (n <= 16, e.g. the 10 visible tokens the masked encoder sees): one warp per
-// (sample, head), lane = query row, everything in registers / warp-private smem on the CUDA cores.
-// A 128-row tensor-core tile would be > 90 % padding here and the persistent pipeline's barrier
-// round trips dominate (measured 14.6 us forward / 32 us backward for 1024 items of n = 10).
+// (sample, head) on mma.sync m16n8k16 (bf16 x bf16 -> fp32) with every tile padded to 16 rows.
+// A 128-row tcgen05 tile would be > 90 % padding here and the persistent pipeline's barrier round
+// trips dominate (measured 14.6 us forward / 32 us backward for 1024 items of n = 10); a first CUDA-core
+// version (lane = query row, 10 of 32 lanes busy, ~8 k dependent instructions per item) took 10 / 25 us.
+// Here an item is 24 (forward) / 56 (backward) tensor instructions:
+//   forward : S = Q K^T, row softmax on the accumulator fragments (4 lanes share a row), the bf16 P fragments
+//             ARE the A operand of O = P V (accumulator layout == A layout), V through ldmatrix.trans
+//   backward: S, dP = dO V^T and their transposes S^T = K Q^T, dP^T = V dO^T (8 instructions each - cheaper
+//             than transposing fragments across lanes); P / dS feed dQ = dS K, P^T / dS^T feed dV = P^T dO and
+//             dK = dS^T Q; delta_i = rowsum(P * dP) is shuffled to the lanes that hold column i of the transposes
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallMaxN = 16;
-constexpr int kSmallPad = kDh + 1;      // fp32 row pitch: lane i reading [i][d] hits bank (i + d) % 32
+constexpr int kSmallPitch = kDh + 8;    // bf16 row pitch 144 B: fragment reads and ldmatrix rows are conflict free
+constexpr int kSmallTile = kSmallMaxN * kSmallPitch;      // bf16 elements per staged matrix
 
-M3L_DEVINL void small_load_rows(const bf16* g, int ld, int n, float* dst, int lane) {
-  // g: first row of this (sample, head) slice, 64 contiguous bf16 per row; lane loads 2 elements
-  for (int j = 0; j < n; ++j) {
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + (size_t)j * ld + lane * 2));
-    dst[j * kSmallPad + lane * 2] = v.x;
-    dst[j * kSmallPad + lane * 2 + 1] = v.y;
+M3L_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16 rows x 64 bf16 of one (sample, head) slice -> staged tile; rows >= n are zero
+M3L_DEVINL void small_stage(const bf16* g, int ld, int n, bf16* dst, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i, row = c >> 3, ch = c & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n) v = *reinterpret_cast<const uint4*>(g + (size_t)row * ld + ch * 8);
+    *reinterpret_cast<uint4*>(dst + row * kSmallPitch + ch * 8) = v;
+  }
+}
+// A fragment (16 x 16, rows of T, k = columns k0 .. k0 + 15)
+M3L_DEVINL void small_frag_a(const bf16* T, int k0, int lane, uint32_t (&a)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  a[0] = *reinterpret_cast<const uint32_t*>(T + g * kSmallPitch + k0 + 2 * t);
+  a[1] = *reinterpret_cast<const uint32_t*>(T + (g + 8) * kSmallPitch + k0 + 2 * t);
+  a[2] = *reinterpret_cast<const uint32_t*>(T + g * kSmallPitch + k0 + 8 + 2 * t);
+  a[3] = *reinterpret_cast<const uint32_t*>(T + (g + 8) * kSmallPitch + k0 + 8 + 2 * t);
+}
+// B fragment with B[k][n] = T[n0 + n][k0 + k] (T rows along n, contiguous in k)
+M3L_DEVINL void small_frag_b(const bf16* T, int n0, int k0, int lane, uint32_t& b0, uint32_t& b1) {
+  const int g = lane >> 2, t = lane & 3;
+  b0 = *reinterpret_cast<const uint32_t*>(T + (n0 + g) * kSmallPitch + k0 + 2 * t);
+  b1 = *reinterpret_cast<const uint32_t*>(T + (n0 + g) * kSmallPitch + k0 + 8 + 2 * t);
+}
+// two B fragments with B[k][n] = T[k][n0 + n] (T rows along k = 0 .. 15): n tiles n0 and n0 + 8
+M3L_DEVINL void small_frag_bt(const bf16* T, int n0, int lane, uint32_t (&r)[4]) {
+  const int row = (lane & 7) + ((lane >> 3) & 1) * 8, col = n0 + (lane >> 4) * 8;
+  const uint32_t addr = smem_u32(T + row * kSmallPitch + col);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// C[16 x 16] = X Y^T over the 64 feature columns (X rows = output rows, Y rows = output columns)
+M3L_DEVINL void small_xyt(const bf16* X, const bf16* Y, int lane, float (&c)[2][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < kDh / 16; ++ks) {
+    uint32_t a[4];
+    small_frag_a(X, ks * 16, lane, a);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      uint32_t b0, b1;
+      small_frag_b(Y, nt * 8, ks * 16, lane, b0, b1);
+      mma_bf16_16816(c[nt], a, b0, b1);
+    }
+  }
+}
+// C[16 x 64] = A(16 x 16 fragments) * T (16 rows k, 64 columns)
+M3L_DEVINL void small_ax(const uint32_t (&a)[4], const bf16* T, int lane, float (&o)[8][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t r[4];
+    small_frag_bt(T, np * 16, lane, r);
+    mma_bf16_16816(o[2 * np], a, r[0], r[1]);
+    mma_bf16_16816(o[2 * np + 1], a, r[2], r[3]);
+  }
+}
+// rows g / g + 8 of a 16 x 64 accumulator -> bf16 global rows (row stride ld), scaled per row
+M3L_DEVINL void small_store_rows(bf16* dst, int ld, int n, int lane, const float (&o)[8][4], float s_lo, float s_hi) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (g < n)
+      *reinterpret_cast<uint32_t*>(dst + (size_t)g * ld + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0] * s_lo, o[nt][1] * s_lo);
+    if (g + 8 < n)
+      *reinterpret_cast<uint32_t*>(dst + (size_t)(g + 8) * ld + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2] * s_hi, o[nt][3] * s_hi);
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 attn_small_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int n,
                       int heads, int inner, int num_items, float scale) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm_small[];
+  extern __shared__ __align__(16) uint8_t sm_small_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  float* sK = sm_small + (size_t)warp * 2 * kSmallMaxN * kSmallPad;
-  float* sV = sK + kSmallMaxN * kSmallPad;
+  bf16* sQ = reinterpret_cast<bf16*>(sm_small_raw) + (size_t)warp * 3 * kSmallTile;
+  bf16* sK = sQ + kSmallTile;
+  bf16* sV = sK + kSmallTile;
   const int ld = 3 * inner;
+  const int g = lane >> 2, t = lane & 3;
   for (int item = blockIdx.x * wpb + warp; item < num_items; item += gridDim.x * wpb) {
     const int h = item % heads, b = item / heads;
     const bf16* base = qkv + (size_t)b * n * ld + h * kDh;
     __syncwarp();
-    small_load_rows(base + inner, ld, n, sK, lane);
-    small_load_rows(base + 2 * inner, ld, n, sV, lane);
+    small_stage(base, ld, n, sQ, lane);
+    small_stage(base + inner, ld, n, sK, lane);
+    small_stage(base + 2 * inner, ld, n, sV, lane);
     __syncwarp();
-    if (lane < n) {
-      float q[kDh];
-      const bf16* qrow = base + (size_t)lane * ld;
+    float sc[2][4];
+    small_xyt(sQ, sK, lane, sc);                    // sc[nt][0,1]: row g, cols nt*8 + 2t, +1; [2,3]: row g + 8
+    float m_lo = -INFINITY, m_hi = -INFINITY;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 u = *reinterpret_cast<const uint4*>(qrow + g * 8);
-        const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        q[g * 8 + 0] = a.x; q[g * 8 + 1] = a.y; q[g * 8 + 2] = bb.x; q[g * 8 + 3] = bb.y;
-        q[g * 8 + 4] = c.x; q[g * 8 + 5] = c.y; q[g * 8 + 6] = d.x; q[g * 8 + 7] = d.y;
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = nt * 8 + 2 * t + e < n;
+        sc[nt][e] = ok ? sc[nt][e] * scale : -INFINITY;
+        sc[nt][2 + e] = ok ? sc[nt][2 + e] * scale : -INFINITY;
+        m_lo = fmaxf(m_lo, sc[nt][e]);
+        m_hi = fmaxf(m_hi, sc[nt][2 + e]);
       }
-      float sc[kSmallMaxN];
-      float mx = -INFINITY;
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1)); m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1)); m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
-        float acc = 0.f;
-        if (j < n) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int d = 0; d < kDh; d += 4) {
-            a0 = fmaf(q[d], sK[j * kSmallPad + d], a0);
-            a1 = fmaf(q[d + 1], sK[j * kSmallPad + d + 1], a1);
-            a2 = fmaf(q[d + 2], sK[j * kSmallPad + d + 2], a2);
-            a3 = fmaf(q[d + 3], sK[j * kSmallPad + d + 3], a3);
-          }
-          acc = ((a0 + a1) + (a2 + a3)) * scale;
-          mx = fmaxf(mx, acc);
-        }
-        sc[j] = acc;
+      for (int e = 0; e < 2; ++e) {
+        sc[nt][e] = __expf(sc[nt][e] - m_lo);       // exp(-inf) = 0 for the padded key columns
+        sc[nt][2 + e] = __expf(sc[nt][2 + e] - m_hi);
+        s_lo += sc[nt][e];
+        s_hi += sc[nt][2 + e];
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
-        sc[j] = j < n ? __expf(sc[j] - mx) : 0.f;
-        sum += sc[j];
-      }
-      const float inv = 1.0f / sum;
-      float o[kDh];
-#pragma unroll
-      for (int d = 0; d < kDh; ++d) o[d] = 0.f;
-#pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
-        if (j < n) {
-          const float pj = sc[j] * inv;
-#pragma unroll
-          for (int d = 0; d < kDh; ++d) o[d] = fmaf(pj, sV[j * kSmallPad + d], o[d]);
-        }
-      }
-      bf16* dst = out + ((size_t)b * n + lane) * inner + h * kDh;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(o[g * 8 + 0], o[g * 8 + 1]); u.y = pack_bf16x2(o[g * 8 + 2], o[g * 8 + 3]);
-        u.z = pack_bf16x2(o[g * 8 + 4], o[g * 8 + 5]); u.w = pack_bf16x2(o[g * 8 + 6], o[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(dst + g * 8) = u;
-      }
-      if (lse) lse[((size_t)b * heads + h) * n + lane] = mx + __logf(sum);
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+    const uint32_t pa[4] = {pack_bf16x2(sc[0][0], sc[0][1]), pack_bf16x2(sc[0][2], sc[0][3]),
+                            pack_bf16x2(sc[1][0], sc[1][1]), pack_bf16x2(sc[1][2], sc[1][3])};
+    float o[8][4];
+    small_ax(pa, sV, lane, o);
+    small_store_rows(out + (size_t)b * n * inner + h * kDh, inner, n, lane, o, 1.0f / s_lo, 1.0f / s_hi);
+    if (lse && t == 0) {
+      float* l = lse + ((size_t)b * heads + h) * n;
+      if (g < n) l[g] = m_lo + __logf(s_lo);
+      if (g + 8 < n) l[g + 8] = m_hi + __logf(s_hi);
     }
   }
 }
@@ -832,99 +894,86 @@ attn_small_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
                       bf16* __restrict__ dqkv, int n, int heads, int inner, int num_items, float scale) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm_small[];
+  extern __shared__ __align__(16) uint8_t sm_small_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  constexpr int kTile = kSmallMaxN * kSmallPad;
-  float* sQ = sm_small + (size_t)warp * (4 * kTile + 2 * kSmallMaxN * (kSmallMaxN + 1));
-  float* sK = sQ + kTile;
-  float* sV = sK + kTile;
-  float* sDO = sV + kTile;
-  float* sP = sDO + kTile;                       // [n][17]
-  float* sDS = sP + kSmallMaxN * (kSmallMaxN + 1);
+  bf16* sQ = reinterpret_cast<bf16*>(sm_small_raw) + (size_t)warp * 4 * kSmallTile;
+  bf16* sK = sQ + kSmallTile;
+  bf16* sV = sK + kSmallTile;
+  bf16* sDO = sV + kSmallTile;
   const int ld = 3 * inner;
+  const int g = lane >> 2, t = lane & 3;
   for (int item = blockIdx.x * wpb + warp; item < num_items; item += gridDim.x * wpb) {
     const int h = item % heads, b = item / heads;
     const bf16* base = qkv + (size_t)b * n * ld + h * kDh;
     __syncwarp();
-    small_load_rows(base, ld, n, sQ, lane);
-    small_load_rows(base + inner, ld, n, sK, lane);
-    small_load_rows(base + 2 * inner, ld, n, sV, lane);
-    small_load_rows(dout + (size_t)b * n * inner + h * kDh, inner, n, sDO, lane);
+    small_stage(base, ld, n, sQ, lane);
+    small_stage(base + inner, ld, n, sK, lane);
+    small_stage(base + 2 * inner, ld, n, sV, lane);
+    small_stage(dout + (size_t)b * n * inner + h * kDh, inner, n, sDO, lane);
     __syncwarp();
+    const float* l = lse + ((size_t)b * heads + h) * n;
     bf16* dbase = dqkv + (size_t)b * n * ld + h * kDh;
-    if (lane < n) {                                 // phase 1: lane = query row
-      const int i = lane;
-      const float li = lse[((size_t)b * heads + h) * n + i];
-      float p[kSmallMaxN], dp[kSmallMaxN];
-      float delta = 0.f;
+    // ---- query-major pass: P, dP, delta, dS -> dQ
+    float s[2][4], dp[2][4];
+    small_xyt(sQ, sK, lane, s);
+    small_xyt(sDO, sV, lane, dp);
+    const float l_lo = g < n ? l[g] : 0.f, l_hi = g + 8 < n ? l[g + 8] : 0.f;
+    float d_lo = 0.f, d_hi = 0.f;
 #pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
-        float s = 0.f, t = 0.f;
-        if (j < n) {
-          float s1 = 0.f, t1 = 0.f;
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int d = 0; d < kDh; d += 2) {
-            s = fmaf(sQ[i * kSmallPad + d], sK[j * kSmallPad + d], s);
-            t = fmaf(sDO[i * kSmallPad + d], sV[j * kSmallPad + d], t);
-            s1 = fmaf(sQ[i * kSmallPad + d + 1], sK[j * kSmallPad + d + 1], s1);
-            t1 = fmaf(sDO[i * kSmallPad + d + 1], sV[j * kSmallPad + d + 1], t1);
-          }
-          s += s1; t += t1;
-          p[j] = __expf(s * scale - li);
-          dp[j] = t;
-          delta = fmaf(p[j], t, delta);
-        } else {
-          p[j] = 0.f; dp[j] = 0.f;
-        }
+      for (int e = 0; e < 2; ++e) {
+        const bool col_ok = nt * 8 + 2 * t + e < n;
+        s[nt][e] = (col_ok && g < n) ? __expf(s[nt][e] * scale - l_lo) : 0.f;
+        s[nt][2 + e] = (col_ok && g + 8 < n) ? __expf(s[nt][2 + e] * scale - l_hi) : 0.f;
+        d_lo = fmaf(s[nt][e], dp[nt][e], d_lo);
+        d_hi = fmaf(s[nt][2 + e], dp[nt][2 + e], d_hi);
       }
-      float dq[kDh];
-#pragma unroll
-      for (int d = 0; d < kDh; ++d) dq[d] = 0.f;
-#pragma unroll
-      for (int j = 0; j < kSmallMaxN; ++j) {
-        if (j < n) {
-          const float ds = p[j] * (dp[j] - delta) * scale;
-          sP[i * (kSmallMaxN + 1) + j] = p[j];
-          sDS[i * (kSmallMaxN + 1) + j] = ds;
-#pragma unroll
-          for (int d = 0; d < kDh; ++d) dq[d] = fmaf(ds, sK[j * kSmallPad + d], dq[d]);
-        }
-      }
-      bf16* dst = dbase + (size_t)i * ld;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(dq[g * 8 + 0], dq[g * 8 + 1]); u.y = pack_bf16x2(dq[g * 8 + 2], dq[g * 8 + 3]);
-        u.z = pack_bf16x2(dq[g * 8 + 4], dq[g * 8 + 5]); u.w = pack_bf16x2(dq[g * 8 + 6], dq[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(dst + g * 8) = u;
-      }
+    d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 1); d_lo += __shfl_xor_sync(0xffffffffu, d_lo, 2);
+    d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 1); d_hi += __shfl_xor_sync(0xffffffffu, d_hi, 2);
+    {
+      uint32_t dsa[4];
+      dsa[0] = pack_bf16x2(s[0][0] * (dp[0][0] - d_lo) * scale, s[0][1] * (dp[0][1] - d_lo) * scale);
+      dsa[1] = pack_bf16x2(s[0][2] * (dp[0][2] - d_hi) * scale, s[0][3] * (dp[0][3] - d_hi) * scale);
+      dsa[2] = pack_bf16x2(s[1][0] * (dp[1][0] - d_lo) * scale, s[1][1] * (dp[1][1] - d_lo) * scale);
+      dsa[3] = pack_bf16x2(s[1][2] * (dp[1][2] - d_hi) * scale, s[1][3] * (dp[1][3] - d_hi) * scale);
+      float dq[8][4];
+      small_ax(dsa, sK, lane, dq);
+      small_store_rows(dbase, ld, n, lane, dq, 1.f, 1.f);
     }
-    __syncwarp();
-    if (lane < n) {                                 // phase 2: lane = key row
-      const int j = lane;
-      float dk[kDh], dv[kDh];
+    // ---- key-major pass: P^T, dS^T (rows = keys j, columns = queries i) -> dV, dK
+    // this lane's columns are queries 2t, 2t+1, 2t+8, 2t+9: their LSE / delta come from the lanes that own those rows
+    const int src0 = (2 * t) * 4, src1 = (2 * t + 1) * 4;
+    const float lc[4] = {__shfl_sync(0xffffffffu, l_lo, src0), __shfl_sync(0xffffffffu, l_lo, src1),
+                         __shfl_sync(0xffffffffu, l_hi, src0), __shfl_sync(0xffffffffu, l_hi, src1)};
+    const float dc[4] = {__shfl_sync(0xffffffffu, d_lo, src0), __shfl_sync(0xffffffffu, d_lo, src1),
+                         __shfl_sync(0xffffffffu, d_hi, src0), __shfl_sync(0xffffffffu, d_hi, src1)};
+    small_xyt(sK, sQ, lane, s);                      // S^T
+    small_xyt(sV, sDO, lane, dp);                    // dP^T
+    uint32_t pta[4], dsta[4];
 #pragma unroll
-      for (int d = 0; d < kDh; ++d) dk[d] = dv[d] = 0.f;
-      for (int i = 0; i < n; ++i) {
-        const float ds = sDS[i * (kSmallMaxN + 1) + j], pp = sP[i * (kSmallMaxN + 1) + j];
+    for (int nt = 0; nt < 2; ++nt) {
+      float pv[4], dv_[4];
 #pragma unroll
-        for (int d = 0; d < kDh; ++d) {
-          dk[d] = fmaf(ds, sQ[i * kSmallPad + d], dk[d]);
-          dv[d] = fmaf(pp, sDO[i * kSmallPad + d], dv[d]);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t + (e & 1);    // query index
+        const int row = g + (e >> 1) * 8;            // key index
+        const float lcv = lc[nt * 2 + (e & 1)], dcv = dc[nt * 2 + (e & 1)];
+        const float pp = (col < n && row < n) ? __expf(s[nt][e] * scale - lcv) : 0.f;
+        pv[e] = pp;
+        dv_[e] = pp * (dp[nt][e] - dcv) * scale;
       }
-      bf16* dstk = dbase + (size_t)j * ld + inner;
-      bf16* dstv = dbase + (size_t)j * ld + 2 * inner;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(dk[g * 8 + 0], dk[g * 8 + 1]); u.y = pack_bf16x2(dk[g * 8 + 2], dk[g * 8 + 3]);
-        u.z = pack_bf16x2(dk[g * 8 + 4], dk[g * 8 + 5]); u.w = pack_bf16x2(dk[g * 8 + 6], dk[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(dstk + g * 8) = u;
-        u.x = pack_bf16x2(dv[g * 8 + 0], dv[g * 8 + 1]); u.y = pack_bf16x2(dv[g * 8 + 2], dv[g * 8 + 3]);
-        u.z = pack_bf16x2(dv[g * 8 + 4], dv[g * 8 + 5]); u.w = pack_bf16x2(dv[g * 8 + 6], dv[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(dstv + g * 8) = u;
-      }
+      pta[nt * 2] = pack_bf16x2(pv[0], pv[1]);
+      pta[nt * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+      dsta[nt * 2] = pack_bf16x2(dv_[0], dv_[1]);
+      dsta[nt * 2 + 1] = pack_bf16x2(dv_[2], dv_[3]);
+    }
+    {
+      float acc[8][4];
+      small_ax(pta, sDO, lane, acc);                 // dV = P^T dO
+      small_store_rows(dbase + 2 * inner, ld, n, lane, acc, 1.f, 1.f);
+      small_ax(dsta, sQ, lane, acc);                 // dK = dS^T Q
+      small_store_rows(dbase + inner, ld, n, lane, acc, 1.f, 1.f);
     }
   }
 }
@@ -963,14 +1012,9 @@ extern "C" int m3l_attention_fwd(const void* qkv_bf16, int batch, int n, int hea
   if (batch == 0) return M3L_OK;
   const int inner = heads * kDh;
   if (n <= kSmallMaxN) {
-    const int items = batch * heads, wpb = 8;
-    const size_t smem = (size_t)wpb * 2 * kSmallMaxN * kSmallPad * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      M3L_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      configured = true;
-    }
-    const int grid = std::min((items + wpb - 1) / wpb, device_sm_count() * 4);
+    const int items = batch * heads, wpb = 4;
+    const size_t smem = (size_t)wpb * 3 * kSmallTile * sizeof(bf16);
+    const int grid = std::min((items + wpb - 1) / wpb, device_sm_count() * 8);
     M3L_CUDA(launch_kernel(attn_small_fwd_kernel, dim3(grid), dim3(wpb * 32), smem, (cudaStream_t)stream, (const bf16*)qkv_bf16, (bf16*)out_bf16, lse, n,
                                                                          heads, inner, items, scale));
     M3L_CUDA(cudaGetLastError());
@@ -1018,12 +1062,7 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
   const int inner = heads * kDh;
   if (n <= kSmallMaxN) {
     const int items = batch * heads, wpb = 4;
-    const size_t smem = (size_t)wpb * (4 * kSmallMaxN * kSmallPad + 2 * kSmallMaxN * (kSmallMaxN + 1)) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      M3L_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      configured = true;
-    }
+    const size_t smem = (size_t)wpb * 4 * kSmallTile * sizeof(bf16);
     const int grid = std::min((items + wpb - 1) / wpb, device_sm_count() * 8);
     M3L_CUDA(launch_kernel(attn_small_bwd_kernel, dim3(grid), dim3(wpb * 32), smem, (cudaStream_t)stream, (const bf16*)qkv_bf16, (const bf16*)dout_bf16, lse,
                                                                          (bf16*)dqkv_bf16, n, heads, inner, items, scale));
