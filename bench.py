@@ -336,7 +336,8 @@ def run_gpu_arm(args):
     if rank == 0:
         roof = dominant_kernel_roofline(peaks)
         step_tflops = value / world * FLOPS_PER_SAMPLE / 1e12
-        cpu_sps, cpu_ms, cores = cpu_reference_run(steps=30, warmup=3)
+        # CPU baseline: rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1; the driver's reference arm times it)
+        cpu_sps, cpu_ms, cores = cpu_reference_run(steps=30, warmup=3) if world == 1 else (None, None, None)
         launches = (trainer.kernel_launches_per_step or 0)
         line = {
             "metric": "VTMAE train samples/sec (fwd+bwd+AdamW)", "value": value, "unit": "samples/s",
@@ -357,9 +358,11 @@ def run_gpu_arm(args):
             "step_tensor_utilisation": {"achieved": step_tflops, "unit": "TFLOP/s (3404.7 MFLOP/sample x samples/s/GPU)",
                                         "peak": peaks["tf_sustained"], "frac": step_tflops / peaks["tf_sustained"],
                                         "peak_source": peaks["source"] + ", sustained"},
-            "cpu_baseline": {"value": cpu_sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"batch 32 slice of the workload, fp32 torch CPU oracle, 30 timed steps, {cpu_ms:.1f} ms/step"},
         }
+        if cpu_sps is not None:
+            line["cpu_baseline"] = {"value": cpu_sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"batch 32 slice of the workload, fp32 torch CPU oracle, 30 timed steps, "
+                                              f"{cpu_ms:.1f} ms/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

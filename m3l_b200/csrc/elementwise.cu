@@ -967,7 +967,7 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int w = 0; w < nwarps; ++w) tot += red[w];
-    *loss_acc += tot;
+    atomicAdd(loss_acc, tot);      // the two heads may run on parallel graph branches; a two-term sum is order free
     *rws.counter = 0u;
   }
 }

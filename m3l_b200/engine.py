@@ -55,16 +55,53 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, gview: torch.Tensor) -> None:
 _SIDE_STREAMS: Dict = {}
 
 
-def side_stream(device) -> "torch.cuda.Stream":
+def side_stream(device, index: int = 0) -> "torch.cuda.Stream":
     """Second stream for the weight-gradient GEMMs: they only feed the gradient arena, so they run
     beside the dgrad chain (the critical path) instead of inside it.  Forks/joins are event based and
     are captured as parallel branches of the CUDA graph."""
-    key = (device.type, device.index)
+    key = (device.type, device.index, index)
     st = _SIDE_STREAMS.get(key)
     if st is None:
         st = torch.cuda.Stream(device=device)
         _SIDE_STREAMS[key] = st
     return st
+
+
+class Branch:
+    """Second, parallel branch of the kernel sequence (captured as a parallel branch of the CUDA graph): the image
+    and the tactile halves of the patch embedding and of the reconstruction heads are independent chains of
+    small, latency-bound kernels, so they run side by side instead of back to back.
+
+        br = Branch(device)
+        with br:            # kernels issued here go to the side stream, ordered after everything issued so far
+            ...
+        ...                 # main-stream work that does not depend on the branch
+        br.join()           # main stream waits for the branch
+
+    Buffers used inside the branch are allocated BEFORE entering it (main stream) and stay referenced until
+    after join(), so the caching allocator never hands them to the other stream early."""
+
+    def __init__(self, device, enabled: bool = True, index: int = 1):
+        self.enabled = enabled
+        self.main = torch.cuda.current_stream(device)
+        self.side = side_stream(device, index) if enabled else None
+        self._ctx = None
+
+    def __enter__(self):
+        if self.enabled:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
 
 
 class WgradFork:
@@ -400,7 +437,7 @@ def _embed_fwd(model, A, geo, tabs, x, B, tok_idx, masked: bool, saved: Optional
         ncols = geo.nv_tac if masked else geo.nt * geo.n_tac
         mods.append(("tactile", ps, geo.nv_img if masked else 0, ncols, tabs.enc_dst_tac if masked else tabs.all_dst_tac,
                      tabs.enc_cls_tac if masked else tabs.all_cls_tac, None if masked else tabs.all_pos_tac))
-    for name, ps, col0, ncols, dst, cls_rows, pos_rows in mods:
+    def embed_one(name, ps, col0, ncols, dst, cls_rows, pos_rows):
         pre = f"{name}_patch_to_emb"
         a, xhat = ops.patch_layernorm(ps, B, ncols, A.f32(pre + ".0.weight"), A.f32(pre + ".0.bias"),
                                       tok_idx=tok_idx if masked else None, col0=col0, want_xhat=saved is not None)
@@ -418,6 +455,14 @@ def _embed_fwd(model, A, geo, tabs, x, B, tok_idx, masked: bool, saved: Optional
                                   want_stats=saved is not None)
         if saved is not None:
             saved[name] = (a, xhat, e, st, dst, pos_rows)
+
+    # image and tactile embeddings write disjoint rows of x0: parallel branches
+    br = Branch(dev, enabled=len(mods) == 2)
+    with br:
+        embed_one(*mods[0])
+    for m in mods[1:]:
+        embed_one(*m)
+    br.join()
     return x0
 
 
@@ -437,9 +482,7 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
         else:
             pos = torch.arange(geo.n, device=dx0.device, dtype=torch.int32).repeat(B)
             ops.rowclass_sum(dx0, B, n_rows, row_pos=pos, dpos=gpos)
-    for name in ("image", "tactile"):
-        if name not in saved:
-            continue
+    def embed_bwd_one(name):
         pre = f"{name}_patch_to_emb"
         a, xhat, e, st, dst, _ = saved[name]
         de = ops.layernorm_bwd(dx0, e, st, A.f32(pre + ".2.weight"), dgamma=G(pre + ".2.weight"),
@@ -448,6 +491,16 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
         wgrad(de, a, G(pre + ".1.weight"))
         da = ops.gemm(de, A.bf_t(pre + ".1.weight"))
         ops.ln_param_grad(da, xhat, G(pre + ".0.weight"), G(pre + ".0.bias"))
+        return de, da                    # kept alive until the branches have joined
+
+    names = [nm for nm in ("image", "tactile") if nm in saved]
+    br = Branch(A.device, enabled=len(names) == 2)
+    with br:
+        keep = [embed_bwd_one(names[0])]
+    for nm in names[1:]:
+        keep.append(embed_bwd_one(nm))
+    br.join()
+    del keep
 
 
 # --------------------------------------------------------------------------------------------
@@ -499,24 +552,26 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
     heads = []
     G = GradView(A, gflat) if (training and gflat is not None) else None
     r_img = B * h_img
+
+    def head(name, g_in, maps, ph, pw, tok_base, h_cols, weight, col0, row0, cap_key, ws_slot):
+        pred = ops.gemm(g_in, A.bf(name + ".weight"), bias=A.f32(name + ".bias"), out_dtype=torch.float32)
+        ps = ops.make_patch_source(maps, ph, pw, tok_base)
+        dpred = ops.mse_loss(ps, B, h_cols, pred, weight / pred.numel(), loss_acc, tok_idx=None if ecm else masked, col0=col0,
+                             dpred_colsum=G(name + ".bias") if G is not None and pred.shape[1] <= 1024 else None,
+                             ws_slot=ws_slot)
+        heads.append((name, g_in, dpred, row0))
+        if capture is not None:
+            capture[cap_key] = pred
+
+    # the two heads (GEMM + masked-patch MSE each) are independent: parallel branches
+    br = Branch(dev, enabled=bool(geo.nt) and geo.use_vision)
     if geo.nt:
-        g_tac = gathered[r_img:]
-        pred = ops.gemm(g_tac, A.bf("to_tactiles.weight"), bias=A.f32("to_tactiles.bias"), out_dtype=torch.float32)
-        ps = ops.make_patch_source([x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac, geo.n_img)
-        dpred = ops.mse_loss(ps, B, h_tac, pred, 10.0 / pred.numel(), loss_acc, tok_idx=None if ecm else masked, col0=geo.nm_img,
-                             dpred_colsum=G("to_tactiles.bias") if G is not None and pred.shape[1] <= 1024 else None)
-        heads.append(("to_tactiles", g_tac, dpred, r_img))
-        if capture is not None:
-            capture["pred_tactile"] = pred
+        with br:
+            head("to_tactiles", gathered[r_img:], [x[f"tactile{i + 1}"] for i in range(geo.nt)], model.ph_tac, model.pw_tac,
+                 geo.n_img, h_tac, 10.0, geo.nm_img, r_img, "pred_tactile", 1)
     if geo.use_vision:
-        g_img = gathered[:r_img]
-        pred = ops.gemm(g_img, A.bf("to_pixels.weight"), bias=A.f32("to_pixels.bias"), out_dtype=torch.float32)
-        ps = ops.make_patch_source([x["image"]], model.ph_img, model.pw_img, 0)
-        dpred = ops.mse_loss(ps, B, h_img, pred, 1.0 / pred.numel(), loss_acc, tok_idx=None if ecm else masked, col0=0,
-                             dpred_colsum=G("to_pixels.bias") if G is not None and pred.shape[1] <= 1024 else None)
-        heads.append(("to_pixels", g_img, dpred, 0))
-        if capture is not None:
-            capture["pred_image"] = pred
+        head("to_pixels", gathered[:r_img], [x["image"]], model.ph_img, model.pw_img, 0, h_img, 1.0, 0, 0, "pred_image", 0)
+    br.join()
     if training:
         ctx.update(tabs=tabs, slots=slots, mrow=mrow, emb=emb_saved, enc=enc_saved, xe=xe, st_enc=st_enc,
                    enc_out=enc_out, dec=dec_saved, xd=xd, st_dec=st_dec, heads=heads, n_gathered=gathered.shape[0],
@@ -532,11 +587,19 @@ def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
     Dd = cfg.decoder_dim
     dgath = torch.empty((ctx["n_gathered"], Dd), dtype=torch.bfloat16, device=A.device)
     bias_done = ctx.get("gflat_fwd") is gflat and gflat is not None   # fused into the MSE kernel
-    for name, g_in, dpred, row0 in ctx["heads"]:
+    def head_bwd(name, g_in, dpred, row0):
         if not (bias_done and dpred.shape[1] <= 1024):
             ops.colsum(dpred, G(name + ".bias"))
         wgrad(dpred, g_in, G(name + ".weight"))
         ops.gemm(dpred, A.bf_t(name + ".weight"), out=dgath[row0:row0 + g_in.shape[0]])
+
+    hs = ctx["heads"]
+    br = Branch(A.device, enabled=len(hs) == 2)
+    with br:
+        head_bwd(*hs[0])
+    for h_ in hs[1:]:
+        head_bwd(*h_)
+    br.join()
     dxd = ops.layernorm_bwd(dgath, ctx["xd"], ctx["st_dec"], A.f32("decoder.norm.weight"),
                             dgamma=G("decoder.norm.weight"), dbeta=G("decoder.norm.bias"), src_row=ctx["mrow"],
                             dx_colsum=G(last_ff_bias(model.dec_spec)))

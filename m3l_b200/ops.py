@@ -22,9 +22,10 @@ _WS = {}
 _WS_BYTES = 1 << 20
 
 
-def workspace(device):
-    """Zero-initialised reduction scratch, one per device (kernels restore the leading counter to 0)."""
-    key = (device.type, device.index)
+def workspace(device, slot: int = 0):
+    """Zero-initialised reduction scratch, one per (device, slot) (kernels restore the leading counter to 0).
+    Kernels that may run concurrently on two streams (the two reconstruction heads) use different slots."""
+    key = (device.type, device.index, slot)
     ws = _WS.get(key)
     if ws is None:
         ws = torch.zeros(_WS_BYTES, dtype=torch.uint8, device=device)
@@ -207,14 +208,15 @@ def rowclass_sum(dx, batch, n_visible, *, slot_class=None, dclass=None, row_pos=
                                        ptr(row_pos), ptr(dpos), current_stream()), "m3l_rowclass_sum")
 
 
-def mse_loss(ps, batch, ncols, pred, weight, loss_acc, *, tok_idx=None, col0=0, dpred=None, dpred_colsum=None):
+def mse_loss(ps, batch, ncols, pred, weight, loss_acc, *, tok_idx=None, col0=0, dpred=None, dpred_colsum=None,
+             ws_slot: int = 0):
     assert pred.dtype == torch.float32 and pred.is_contiguous()
     if dpred is None:
         dpred = torch.empty(pred.shape, dtype=torch.bfloat16, device=pred.device)
     idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
     check(_lib.load().m3l_mse_loss(C.byref(ps), batch, ptr(tok_idx), idx_ld, col0, ncols, ptr(pred),
                                    C.c_float(weight), ptr(dpred), ptr(loss_acc), ptr(dpred_colsum),
-                                   ptr(workspace(pred.device)),
+                                   ptr(workspace(pred.device, ws_slot)),
                                    C.c_size_t(_WS_BYTES), current_stream()), "m3l_mse_loss")
     return dpred
 
