@@ -105,6 +105,34 @@ def test_all_gradients_vs_oracle_canonical(nt, ecm):
     assert cos(torch.cat(flat_a), torch.cat(flat_b)) >= 0.9995
 
 
+@pytest.mark.parametrize("B,use_tactile", [(1, True), (7, True), (5, False)])
+def test_ragged_batches_vs_oracle(B, use_tactile):
+    """Batch sizes that fill no tile (1, 7) and the nt = 2 model called with use_tactile=False
+    (MAEExtractor's vision_only_control path, pretrain_models.py:834): loss, indices, gradients."""
+    cfg = O.VTMAEConfig(depth=2, decoder_depth=2)
+    sd = O.init_state_dict(cfg, seed=8)
+    gen = torch.Generator().manual_seed(40 + B)
+    x = {"image": torch.rand(B, 12, 64, 64, generator=gen), "tactile1": torch.rand(B, 12, 32, 32, generator=gen),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=gen)}
+    n = 192 if use_tactile else 64
+    noise = O.tie_free_noise(B, n, gen, [64] * (3 if use_tactile else 1))
+    mae = build_product(cfg, weights=sd)
+    loss = mae(to_dev(x), use_tactile=use_tactile, noise=noise.to(DEV))
+    loss.backward()
+    for k in O.param_keys(sd):
+        sd[k].requires_grad_(True)
+    lref = O.vtmae_forward(sd, cfg, x, noise, use_tactile=use_tactile)
+    lref.backward()
+    assert abs(loss.item() - lref.item()) <= 1e-2 * abs(lref.item())
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    for k in O.param_keys(sd):
+        gr = sd[k].grad
+        if gr is None or float(gr.abs().max()) == 0.0:
+            assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
+        else:
+            assert cos(named[k].grad, gr) >= 0.999, (k, cos(named[k].grad, gr))
+
+
 def test_dino_tac_mae_shape_vs_oracle():
     """BASELINE.json configs[3] (DINO-tac-MAE, MAE side): VTT(70x70, patch 14, dim 384, depth 4, heads 4,
     mlp 768, C=12) + VTMAE(r=0.8, decoder_dim 384, depth 3, heads 4) run tactile-only (x without 'image',
