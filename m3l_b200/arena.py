@@ -96,9 +96,14 @@ class ParamArena:
             self._version_seen = v
 
     def refresh_shadows(self) -> None:
+        # the plain and the transposed bf16 copies only read the fp32 arena: two parallel graph branches
+        from .engine import Branch
+        br = Branch(self.device, enabled=bool(self.n_descs), index=2)
+        with br:
+            if self.n_descs:
+                ops.transpose_cast_bf16(self.flat, self.flat_t, self.descs_dev, self.n_descs)
         ops.cast_bf16(self.flat, self.flat_bf16)
-        if self.n_descs:
-            ops.transpose_cast_bf16(self.flat, self.flat_t, self.descs_dev, self.n_descs)
+        br.join()
 
     # ------------------------------------------------------------------------------ accessors
     def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:

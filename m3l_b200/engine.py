@@ -469,19 +469,23 @@ def _embed_fwd(model, A, geo, tabs, x, B, tok_idx, masked: bool, saved: Optional
 def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
     cfg = model.cfg
     n_rows = geo.nv if masked else geo.n
-    # broadcast adds: modality embedding / learned positions
-    if cfg.use_sincosmod_encodings:
-        if masked:
-            ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.slot_class, dclass=G("encoder_modality_embedding.weight"))
+    # broadcast adds: modality embedding / learned positions (only reads dx0: a branch of its own, beside the
+    # per-modality chains below)
+    br0 = Branch(A.device, index=3)
+    with br0:
+        if cfg.use_sincosmod_encodings:
+            if masked:
+                ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.slot_class, dclass=G("encoder_modality_embedding.weight"))
+            else:
+                ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.tok_class, dclass=G("encoder_modality_embedding.weight"))
         else:
-            ops.rowclass_sum(dx0, B, n_rows, slot_class=tabs.tok_class, dclass=G("encoder_modality_embedding.weight"))
-    else:
-        gpos = G("encoder.pos_embedding")[0, 1:geo.n + 1]
-        if masked:
-            ops.rowclass_sum(dx0, B, n_rows, row_pos=saved["unmasked32"].view(-1), dpos=gpos)
-        else:
-            pos = torch.arange(geo.n, device=dx0.device, dtype=torch.int32).repeat(B)
-            ops.rowclass_sum(dx0, B, n_rows, row_pos=pos, dpos=gpos)
+            gpos = G("encoder.pos_embedding")[0, 1:geo.n + 1]
+            if masked:
+                ops.rowclass_sum(dx0, B, n_rows, row_pos=saved["unmasked32"].view(-1), dpos=gpos)
+            else:
+                pos = torch.arange(geo.n, device=dx0.device, dtype=torch.int32).repeat(B)
+                ops.rowclass_sum(dx0, B, n_rows, row_pos=pos, dpos=gpos)
+
     def embed_bwd_one(name):
         pre = f"{name}_patch_to_emb"
         a, xhat, e, st, dst, _ = saved[name]
@@ -500,6 +504,7 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
     for nm in names[1:]:
         keep.append(embed_bwd_one(nm))
     br.join()
+    br0.join()
     del keep
 
 
