@@ -25,8 +25,14 @@
 // cost 18 registers in the backward kernel (spills) and a CS2R per phase.
 #ifdef M3L_ATTN_PROFILE
 #define M3L_CLK() clock64()
+// event timeline of CTA 0 (backward): prof[64 + role * 512 + step * 8 + event] = clock64(), first 64 steps
+#define M3L_EVT(role, step, ev)                                                          \
+  do {                                                                                   \
+    if (p.prof && blockIdx.x == 0 && (step) < 64) p.prof[64 + (role) * 512 + (step) * 8 + (ev)] = clock64(); \
+  } while (0)
 #else
 #define M3L_CLK() 0LL
+#define M3L_EVT(role, step, ev) do { } while (0)
 #endif
 
 namespace m3l {
@@ -126,7 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       int it = 0, jt = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int h = item % p.heads, b = item / p.heads;
@@ -148,7 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       const uint32_t idesc_s = umma_idesc_bf16(128, NK, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, kDh, 0, 1);
       int pv_slot = -1, pv_kb = 0, pv_last = 0;
@@ -421,7 +427,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int h = item % p.heads, b = item / p.heads;
@@ -462,7 +468,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------
-    if (lane == 0 && my_items > 0) {
+    if (my_items > 0 && elect_one()) {
       const uint32_t idesc_dq = umma_idesc_bf16(128, kDh, 0, 1);     // A K-major (dS), B MN-major (K)
       const uint32_t idesc_dkv = umma_idesc_bf16(128, kDh, 1, 1);    // both MN-major
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
@@ -522,13 +528,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
               mbar_wait(&bars->sdp_free, g & 1);       // the producers hold step g's S / dP in registers
               tc_fence_after_sync();
               long long c1 = M3L_CLK(); m_w1 += c1 - c0;
+              M3L_EVT(0, g, 0);
               issue_sdp(it2, j2, i2);
+              M3L_EVT(0, g, 1);
               if (serial) { mbar_wait(&bars->sdp_full, (g + 1) & 1); m_sdp += M3L_CLK() - c1; }
             }
             // ---- wait for P_ij / dS_ij, then the three accumulating products
             long long c2 = M3L_CLK();
             mbar_wait(&bars->pds_full, g & 1);
             long long c3 = M3L_CLK(); m_w2 += c3 - c2;
+            M3L_EVT(0, g, 2);
             if (i == 0 && dk > 0) mbar_wait(&bars->dkv_free, (dk - 1) & 1);               // dV/dK accumulators drained
             if (j == 0 && i == 0 && it > 0) mbar_wait(&bars->item_done, (it - 1) & 1);   // dQ accumulators drained
             tc_fence_after_sync();
@@ -546,6 +555,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
                         umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                         umma_smem_desc(kj + kk * 2048, 8192, 1024), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&bars->pds_free);                            // P / dS slabs may be rewritten
+            M3L_EVT(0, g, 3);
             if (i == p.q_tiles - 1) {
               umma_commit(&bars->dkv_full);
               ++dk;
@@ -571,7 +581,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const long long pf_t0 = M3L_CLK();
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pc = pf_t0;
-#define PF(k) { const long long c_ = M3L_CLK(); pf[k] += c_ - pc; pc = c_; }
+#define PF(k) { const long long c_ = M3L_CLK(); pf[k] += c_ - pc; pc = c_; \
+                if (lane == 0 && (warp == 2 || warp == 6)) M3L_EVT(warp == 2 ? 1 : 2, g, k); }
     // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile; with a
     // precomputed delta the next item's values are fetched one item ahead
     float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f}, delta_n[2] = {0.f, 0.f}, l2_n[2] = {0.f, 0.f};
@@ -982,8 +993,8 @@ long long* attn_prof_buf() {
   static long long* buf = [] {
     long long* b = nullptr;
     if (getenv("M3L_ATTN_PROF")) {
-      cudaMalloc(&b, 64 * sizeof(long long));
-      cudaMemset(b, 0, 64 * sizeof(long long));
+      cudaMalloc(&b, 2048 * sizeof(long long));
+      cudaMemset(b, 0, 2048 * sizeof(long long));
       const long long flag = getenv("M3L_ATTN_SERIAL") ? 1 : 0;     // [32]: wait for every MMA batch
       cudaMemcpy(b + 32, &flag, sizeof(flag), cudaMemcpyHostToDevice);
     }
@@ -1116,7 +1127,7 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
 // measurement only (M3L_ATTN_PROF=1): read and reset the in-kernel cycle counters of CTA 0
 extern "C" int m3l_debug_attn_prof(long long* host_out, int n) {
   long long* b = m3l::attn_prof_buf();
-  if (b == nullptr || n > 64) return M3L_ERR_INVALID;
+  if (b == nullptr || n > 2048) return M3L_ERR_INVALID;
   cudaDeviceSynchronize();
   cudaMemcpy(host_out, b, n * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaMemset(b, 0, 32 * sizeof(long long));

@@ -367,6 +367,32 @@ M3L_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
 }
 // All tcgen05.mma issued so far by this thread -> arrive(1) on `bar` when they complete.
 // (implies tcgen05.fence::before_thread_sync)
+// Same, issued by the lane(s) whose `pred` is non-zero while the WHOLE warp executes the surrounding code:
+// operands computed by converged, warp-uniform code live in uniform registers, whereas an `if (lane == 0)` body
+// makes the compiler move every descriptor into uniform registers through an ELECT / R2UR.BROADCAST waterfall
+// loop per instruction (~22 SASS instructions, 100-150 clk per MMA; measured on the attention backward issue path).
+M3L_DEVINL void umma_bf16_p(uint32_t pred, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
+M3L_DEVINL void umma_commit_p(uint32_t pred, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(pred)
+      : "memory");
+}
 M3L_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))

@@ -196,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       int stage = 0;
       uint32_t phase = 0;
       if (WS && sched.count > 0) {
@@ -236,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -338,18 +338,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tma_load_2d_u32(stg + b * kStgTileBytes, &map_side, &bars->side_full[ew][b],
                       n0 + span0 + (gi % kRounds) * kRoundCols, m0 + quad * 32);
     };
-    if (has_side && lane == 0 && total_rounds > 0) issue_side(0);
+    if (has_side && total_rounds > 0 && elect_one()) issue_side(0);
     int g = 0;      // global round counter of this warp
     int ob = 0;     // staging buffer of the next output tile (modes without a side operand)
     // stage one 32 x 128 B tile (row-mapped registers) and hand it to TMA; returns the smem tile
     auto stage_and_store = [&](const CUtensorMap* map, const uint32_t* w, int col, int row, bool reduce) {
       const uint32_t dst = stg + ob * kStgTileBytes;
-      if (lane == 0) tma_wait_group_read<kBufs - 1>();   // the tile last stored from this buffer was read
+      tma_wait_group_read<kBufs - 1>();   // (issuing lane) the tile last stored from this buffer was read
       __syncwarp();
       stg_store_row(dst, lane, w);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if (reduce) tma_reduce_add_2d(map, dst, col, row); else tma_store_2d(map, dst, col, row);
         tma_commit_group();
       }
@@ -390,7 +390,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tmem_ld_32x32(t_acc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           if (has_side && g + 1 < total_rounds) {
             __syncwarp();    // every lane is done with buffer (g+1)&1 (round g-1: row + column-sum reads)
-            if (lane == 0) {
+            if (elect_one()) {
               tma_wait_group_read<0>();     // ... and so is the TMA store that was issued from it
               fence_proxy_async_smem();
               issue_side(g + 1);
@@ -473,7 +473,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             stg_store_row(sb, lane, w);      // in place: every thread only touches its own row
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
               tma_store_2d(&map_out, sb, gcol, row0);
               tma_commit_group();
             }
@@ -512,7 +512,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (want_colsum && active) flush_colsum();
-    if (lane == 0) tma_wait_group<0>();   // every store / reduce of this warp has been performed
+    tma_wait_group<0>();   // (issuing lane) every store / reduce of this warp has been performed
   }
 
   tc_fence_before_sync();

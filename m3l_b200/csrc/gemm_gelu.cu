@@ -41,7 +41,7 @@ static_assert(sizeof(Bars) <= 256, "barrier block");
 
 // one 32 x 32 bf16 unit: registers (thread = row, 16 packed words) -> 64 B-swizzled staging -> TMA store
 M3L_DEVINL void store_unit(const CUtensorMap* map, uint32_t stg, int lane, const uint32_t (&w)[16], int col, int row) {
-  if (lane == 0) tma_wait_group_read<0>();               // the previous store from this buffer has been read
+  tma_wait_group_read<0>();               // (issuing lane) the previous store from this buffer has been read
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -52,7 +52,7 @@ M3L_DEVINL void store_unit(const CUtensorMap* map, uint32_t stg, int lane, const
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one()) {
     tma_store_2d(map, stg, col, row);
     tma_commit_group();
   }
@@ -107,7 +107,7 @@ gemm_gelu16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (warp == 0) {
     // ------------------------------- TMA producer ---------------------------------------
-    if (lane == 0 && count > 0) {
+    if (count > 0 && elect_one()) {
       mbar_arrive_expect_tx(&bars->b_full, kb_total * kBBytes);
       for (int kb = 0; kb < kb_total; ++kb) tma_load_2d(resident + kb * kBBytes, &map_b, &bars->b_full, kb * kBK, n0);
       int stage = 0;
@@ -124,7 +124,7 @@ gemm_gelu16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -----------------------------------------
-    if (lane == 0 && count > 0) {
+    if (count > 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -192,7 +192,7 @@ gemm_gelu16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         store_unit(&map_out, stg, lane, hp, n0 + c0, row0);
       }
     }
-    if (lane == 0) tma_wait_group<0>();        // every store of this warp has been performed
+    tma_wait_group<0>();        // (issuing lane) every store of this warp has been performed
   }
 
   tc_fence_before_sync();
