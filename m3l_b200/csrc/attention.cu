@@ -543,17 +543,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             tc_fence_after_sync();
             const uint32_t qi = q_addr(it, i), doi = do_addr(it, i);
             const int qk = p.q_rows[i] / 16;                         // contraction over the loaded query rows
-            for (int kk = 0; kk < qk; ++kk) {
-              const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-              umma_bf16(tmem_base + kColDV, umma_smem_desc(p_addr + kk * 2048, 16384, 1024),
-                        umma_smem_desc(doi + kk * 2048, 8192, 1024), idesc_dkv, acc);
-              umma_bf16(tmem_base + kColDK, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024),
-                        umma_smem_desc(qi + kk * 2048, 8192, 1024), idesc_dkv, acc);
+            {
+              // descriptors advance by a constant per k-step: one 64-bit add each instead of rebuilding the bit
+              // fields (the start-address field holds addr >> 4 and cannot carry out: smem addresses < 256 KB)
+              uint64_t d_p = umma_smem_desc(p_addr, 16384, 1024), d_do = umma_smem_desc(doi, 8192, 1024);
+              uint64_t d_ds = umma_smem_desc(ds_addr, 16384, 1024), d_q = umma_smem_desc(qi, 8192, 1024);
+              for (int kk = 0; kk < qk; ++kk) {
+                const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+                umma_bf16(tmem_base + kColDV, d_p, d_do, idesc_dkv, acc);
+                umma_bf16(tmem_base + kColDK, d_ds, d_q, idesc_dkv, acc);
+                d_p += 2048 >> 4; d_do += 2048 >> 4; d_ds += 2048 >> 4; d_q += 2048 >> 4;
+              }
+              uint64_t d_k = umma_smem_desc(kj, 8192, 1024);
+              const uint32_t tq = tmem_base + kColDQ + i * 64;
+              for (int kp = 0; kp < nkj / 64; ++kp) {                // contraction over this tile's keys, 64-key panels
+                const uint64_t d_a = umma_smem_desc(ds_addr + kp * 16384, 16, 1024);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  umma_bf16(tq, d_a + k4 * (32 >> 4), d_k, idesc_dq, (j > 0 || kp > 0 || k4 > 0) ? 1u : 0u);
+                  d_k += 2048 >> 4;
+                }
+              }
+              for (int kk = (nkj / 64) * 4; kk < nkj / 16; ++kk) {   // remaining 16-key steps of a partial panel
+                umma_bf16(tq, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024), d_k, idesc_dq,
+                          (j > 0 || kk > 0) ? 1u : 0u);
+                d_k += 2048 >> 4;
+              }
             }
-            for (int kk = 0; kk < nkj / 16; ++kk)                    // contraction over this tile's keys
-              umma_bf16(tmem_base + kColDQ + i * 64,
-                        umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                        umma_smem_desc(kj + kk * 2048, 8192, 1024), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&bars->pds_free);                            // P / dS slabs may be rewritten
             M3L_EVT(0, g, 3);
             if (i == p.q_tiles - 1) {
