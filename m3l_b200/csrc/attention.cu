@@ -165,9 +165,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t p_addr = smem_u32(sP + pv_slot * p_slabs * 16384);
         const uint32_t v_addr = smem_u32(sKV + pv_kb * 2 * kv_region + kv_region);
         const uint32_t tmem_o = tmem_base + pv_slot * p.slot_cols;
-        for (int kk = 0; kk < NK / 16; ++kk)
-          umma_bf16(tmem_o, umma_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc(v_addr + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
+        uint64_t d_v = umma_smem_desc(v_addr, 8192, 1024);       // advanced by a constant add per 16-key step
+        for (int kp = 0; kp < NK / 64; ++kp) {
+          const uint64_t d_p = umma_smem_desc(p_addr + kp * 16384, 16, 1024);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_bf16(tmem_o, d_p + k4 * (32 >> 4), d_v, idesc_o, (kp > 0 || k4 > 0) ? 1u : 0u);
+            d_v += 2048 >> 4;
+          }
+        }
+        for (int kk = (NK / 64) * 4; kk < NK / 16; ++kk) {
+          umma_bf16(tmem_o, umma_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024), d_v, idesc_o,
+                    kk > 0 ? 1u : 0u);
+          d_v += 2048 >> 4;
+        }
         umma_commit(&bars->o_full[pv_slot]);
         if (pv_last) umma_commit(&bars->kv_empty[pv_kb]);
         pv_slot = -1;
@@ -608,7 +619,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       for (int i = 0; i < p.q_tiles; ++i) {
         const int grow = i * 128 + row;
         d[i] = 0.f; l[i] = 0.f;
+#ifdef M3L_EXP_NOSTATS
+        if (grow < 0) {
+#else
         if (grow < n) {
+#endif
           l[i] = p.lse[((size_t)b * p.heads + h) * n + grow];     // raw: scaled at use, so the load stays in flight
           if (p.delta != nullptr) {
             d[i] = p.delta[((size_t)b * n + grow) * p.heads + h];
