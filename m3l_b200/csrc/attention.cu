@@ -236,31 +236,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         long long c1 = M3L_CLK(); pf_ws += c1 - c0;
         float mx = -INFINITY, sum = 0.f;
         if (warp_active) {
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c * 32, v);
-            tmem_ld_wait();
+          // both passes read S from TMEM in 32-column chunks, software-pipelined over two register
+          // buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+          uint32_t va[32], vb[32];
+          // four independent running maxima: a single fmaxf chain over 192 columns is ~1 k clk of pure latency
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          auto max_chunk = [&](const uint32_t (&v)[32], int c) {
+            if (c * 32 + 32 <= n) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < n) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+            }
+          };
+          tmem_ld_32x32(t_row, va);
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
+            max_chunk(va, c);
+            if (c + 1 < nchunks) {
+              tmem_ld_wait();
+              if (c + 2 < nchunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
+              max_chunk(vb, c + 1);
+            }
           }
+          mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           const float mxs = mx * sl2;
           { long long c2 = M3L_CLK(); pf_p1 += c2 - c1; c1 = c2; }
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c * 32, v);
-            tmem_ld_wait();
+          float sum1 = 0.f;                          // two partial sums: shorter FADD dependency chains
+          const f32x2 sl2_2 = f2_splat(sl2), nmx_2 = f2_splat(-mxs);
+          auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
             const int col0 = c * 32;
+            const bool full = col0 + 32 <= n;          // no padded key column in this chunk: no per-element select
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (col0 + g * 8 < NK) {
                 float pv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float e = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), sl2, -mxs));
-                  pv[j] = (col0 + g * 8 + j < n) ? e : 0.f;
-                  sum += pv[j];
+                for (int j = 0; j < 8; j += 2) {
+                  float a0, a1;                        // x * scale * log2(e) - max, two columns per FFMA2
+                  f2_unpack(f2_fma(f2_packu(v[g * 8 + j], v[g * 8 + j + 1]), sl2_2, nmx_2), a0, a1);
+                  pv[j] = exp2f(a0);
+                  pv[j + 1] = exp2f(a1);
                 }
+                if (!full) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) pv[j] = (col0 + g * 8 + j < n) ? pv[j] : 0.f;
+                }
+                sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+                sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
                 uint4 u;
                 u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
                 u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
@@ -268,7 +294,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 st_swz_chunk(p_u32 + (col >> 6) * 16384, row, (col & 63) >> 3, u);
               }
             }
+          };
+          tmem_ld_32x32(t_row, va);
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nchunks) tmem_ld_32x32(t_row + (c + 1) * 32, vb);
+            exp_chunk(va, c);
+            if (c + 1 < nchunks) {
+              tmem_ld_wait();
+              if (c + 2 < nchunks) tmem_ld_32x32(t_row + (c + 2) * 32, va);
+              exp_chunk(vb, c + 1);
+            }
           }
+          sum += sum1;
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
