@@ -624,52 +624,73 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_
 #pragma unroll
   for (int s = 0; s < kStages; ++s) issue(r0 + s * rstride, s);
   int stage = 0;
-  for (int r = r0; r < M; r += rstride) {
-    const float2 ms = *reinterpret_cast<const float2*>(stats + 2 * r);
-    cp_async_wait<kStages - 1>();
-    const float mean = ms.x, rstd = ms.y;
-    const uint32_t base = ring + stage * kStageBytes;
-    float xh[NCH][8], g[NCH][8], sk[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
+  // TWO rows per iteration: their dependent chains (smem reads -> sums -> two warp reductions -> output) interleave,
+  // which hides the ~500 clk of per-row latency that four warps per scheduler could not (IPC 0.45 before)
+  static_assert(kStages % 2 == 0 && kStages >= 4, "two rows in compute, at least two in flight");
+  for (int r = r0; r < M; r += 2 * rstride) {
+    const int rb = r + rstride;
+    const bool has_b = rb < M;
+    const float2 ms_a = *reinterpret_cast<const float2*>(stats + 2 * r);
+    const float2 ms_b = has_b ? *reinterpret_cast<const float2*>(stats + 2 * rb) : make_float2(0.f, 0.f);
+    cp_async_wait<kStages - 2>();
+    const uint32_t base_a = ring + stage * kStageBytes, base_b = ring + (stage + 1) * kStageBytes;
+    float xh_a[NCH][8], g_a[NCH][8], sk_a[NCH][8], xh_b[NCH][8], g_b[NCH][8], sk_b[NCH][8];
+    float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+    auto phase1 = [&](uint32_t base, float mean, float rstd, bool on, float (&xh)[NCH][8], float (&g)[NCH][8],
+                      float (&sk)[NCH][8], float& s1, float& s2) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nchunk) {
-        float xv[8], dv[8];
-        cvt8(lds128(base + ch * 16), xv);
-        cvt8(lds128(base + kRowBytes + ch * 16), dv);
-        if (skip) cvt8(lds128(base + 2 * kRowBytes + ch * 16), sk[c]);
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunk) {
+          float xv[8], dv[8];
+          cvt8(lds128(base + ch * 16), xv);
+          cvt8(lds128(base + kRowBytes + ch * 16), dv);
+          if (skip) cvt8(lds128(base + 2 * kRowBytes + ch * 16), sk[c]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[c][i] = (xv[i] - mean) * rstd;
-          g[c][i] = dv[i] * gm[c][i];
-          s1 += g[c][i];
-          s2 = fmaf(g[c][i], xh[c][i], s2);
-          ag[c][i] = fmaf(dv[i], xh[c][i], ag[c][i]);
-          ab[c][i] += dv[i];
+          for (int i = 0; i < 8; ++i) {
+            if (!on) dv[i] = 0.f;                      // row beyond M: contributes nothing to the parameter sums
+            xh[c][i] = (xv[i] - mean) * rstd;
+            g[c][i] = dv[i] * gm[c][i];
+            s1 += g[c][i];
+            s2 = fmaf(g[c][i], xh[c][i], s2);
+            ag[c][i] = fmaf(dv[i], xh[c][i], ag[c][i]);
+            ab[c][i] += dv[i];
+          }
         }
       }
-    }
+    };
+    phase1(base_a, ms_a.x, ms_a.y, true, xh_a, g_a, sk_a, s1a, s2a);
+    phase1(base_b, ms_b.x, ms_b.y, has_b, xh_b, g_b, sk_b, s1b, s2b);
     issue(r + kStages * rstride, stage);
-    stage = (stage + 1 == kStages) ? 0 : stage + 1;
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
+    issue(rb + kStages * rstride, stage + 1);
+    stage = (stage + 2 == kStages) ? 0 : stage + 2;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nchunk) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
-        if (skip) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += sk[c][i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ac[c][i] += o[i];
-        store8(dx + (size_t)r * D + ch * 8, o);
-      }
+    for (int o = 16; o > 0; o >>= 1) {                 // four interleaved butterflies
+      s1a += __shfl_xor_sync(0xffffffffu, s1a, o); s2a += __shfl_xor_sync(0xffffffffu, s2a, o);
+      s1b += __shfl_xor_sync(0xffffffffu, s1b, o); s2b += __shfl_xor_sync(0xffffffffu, s2b, o);
     }
+    s1a *= inv_d; s2a *= inv_d; s1b *= inv_d; s2b *= inv_d;
+    auto phase2 = [&](int row, float rstd, float s1, float s2, const float (&xh)[NCH][8], const float (&g)[NCH][8],
+                      const float (&sk)[NCH][8]) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int ch = lane + 32 * c;
+        if (ch < nchunk) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+          if (skip) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += sk[c][i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ac[c][i] += o[i];
+          store8(dx + (size_t)row * D + ch * 8, o);
+        }
+      }
+    };
+    phase2(r, ms_a.y, s1a, s2a, xh_a, g_a, sk_a);
+    if (has_b) phase2(rb, ms_b.y, s1b, s2b, xh_b, g_b, sk_b);
   }
   cp_async_wait<0>();
   if (dgamma == nullptr && dx_colsum == nullptr) return;
@@ -1373,7 +1394,7 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
   const bf16* dy = (const bf16*)dy_bf16;
   const bf16* skip = (const bf16*)skip_bf16;
   if (!x_fp32 && !dx_fp32 && nch <= 2) {
-    constexpr int kSt = 3;
+    constexpr int kSt = 4;
 
     const size_t ring = (size_t)wpb * kSt * 3 * nch * 512;
     const size_t total = ring + smem;
