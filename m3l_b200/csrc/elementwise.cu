@@ -1401,7 +1401,7 @@ extern "C" int m3l_layernorm_bwd(const void* dy_bf16, const int32_t* src_row, co
     static bool configured = false;
     if (!configured) {
       M3L_CUDA(cudaFuncSetAttribute(ln_bwd_pipe_kernel<1, kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-      M3L_CUDA(cudaFuncSetAttribute(ln_bwd_pipe_kernel<2, kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+      M3L_CUDA(cudaFuncSetAttribute(ln_bwd_pipe_kernel<2, kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
     if (nch == 1)
