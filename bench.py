@@ -193,13 +193,12 @@ def dominant_kernel_roofline(peaks):
     # 6460 GB/s = 261 flop/B): the kernel's binding roofline is HBM; the tensor-pipe view is kept beside it.
     bytes_alg = 2.0 * M * K + 2.0 * N * K + 4.0 * N + 2 * 2.0 * M * N
     gbs = bytes_alg / sec / 1e9
-    return {"bound": "hbm", "kernel": "gemm_bf16_kernel<256,GELU_FWD> decoder FF1 (M=49152,N=1024,K=256,+bias, writes "
-                                      "GELU and GELU')",
+    return {"bound": "hbm", "kernel": "gemm_gelu16_kernel decoder FF1 (M=49152,N=1024,K=256,+bias, writes GELU and GELU')",
             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
-            # profiles/r01_ncu_full_gemm_v3.txt (25.77 MB read + 143.43 MB written; the rest of the 201 MB of
-            # outputs was still dirty in the 126 MB L2 when the kernel ended)
-            "traffic": 169.2e6, "algorithmic_bytes": bytes_alg, "us_per_launch": sec * 1e6,
+            # profiles/r01_ncu_full_gemm_v4.txt (gemm_gelu16_kernel: 25.72 MB read + 147.36 MB written; the rest of the
+            # 201 MB of outputs was still dirty in the 126 MB L2 when the kernel ended)
+            "traffic": 173.1e6, "algorithmic_bytes": bytes_alg, "us_per_launch": sec * 1e6,
             "peak_source": peaks["source"] + ", burst",
             "tensor_view": {"achieved": flops / sec / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                             "frac": flops / sec / 1e12 / peaks["tf_burst"], "flop_per_byte": flops / bytes_alg}}
