@@ -512,7 +512,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (want_colsum && active) flush_colsum();
-    tma_wait_group<0>();   // (issuing lane) every store / reduce of this warp has been performed
+    // (issuing lane) every store / reduce of this warp has READ its staging tile; the writes themselves are complete
+    // at grid completion, which is what dependents wait for (griddepcontrol.wait / stream order)
+    tma_wait_group_read<0>();
   }
 
   tc_fence_before_sync();

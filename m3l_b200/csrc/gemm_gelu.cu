@@ -192,7 +192,7 @@ gemm_gelu16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         store_unit(&map_out, stg, lane, hp, n0 + c0, row0);
       }
     }
-    tma_wait_group<0>();        // (issuing lane) every store of this warp has been performed
+    tma_wait_group_read<0>();   // (issuing lane) the staging tile has been read; writes complete with the grid
   }
 
   tc_fence_before_sync();
