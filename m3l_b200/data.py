@@ -22,11 +22,14 @@ def vt_load(x, image_normalization=(0, 1), tactile_normalization=(-1, 1), squeez
         ch = x["tactile"].shape[1]
         assert ch in (3 * frame_stack, 6 * frame_stack, 12 * frame_stack)
         per_frame = ch // frame_stack
-        idx = np.array([i * per_frame + c for i in range(frame_stack) for c in range(3)])
         tac = torch.as_tensor(x["tactile"]).to(torch.float32)
         lo, hi = tactile_normalization
+        # channels {i * per_frame + 3 s + c : i < frame_stack, c < 3} of sensor s (pretrain_utils.py:36-49), taken as a
+        # view + slice (no index tensor: the rollout path replays this inside a CUDA graph)
+        b, _, h, w = tac.shape
+        frames = tac.reshape(b, frame_stack, per_frame, h, w)
         for s in range(per_frame // 3):
-            x[f"tactile{s + 1}"] = (tac[:, torch.as_tensor(idx + 3 * s)] - lo) / (hi - lo)
+            x[f"tactile{s + 1}"] = (frames[:, :, 3 * s:3 * s + 3].reshape(b, 3 * frame_stack, h, w) - lo) / (hi - lo)
         del x["tactile"]
     if squeeze:
         for key in x:

@@ -68,3 +68,21 @@ def test_tie_free_noise_has_no_ties():
     for off in (0, 64, 128):
         s = n[:, off:off + 64].sort(dim=-1).values
         assert not (s[:, 1:] == s[:, :-1]).any()
+
+
+def test_product_vt_load_matches_oracle():
+    """m3l_b200.data.vt_load (pure torch, device agnostic) against the oracle restatement of
+    utils/pretrain_utils.py:7-57 (itself pinned against the reference in test_oracle_vs_reference.py)."""
+    import numpy as np
+    import torch
+    from m3l_b200.data import vt_load
+    from oracle import vtmae_oracle as O
+    rng = np.random.default_rng(0)
+    for sensors in (1, 2, 4):
+        obs = {"image": rng.random((3, 64, 64, 12), dtype=np.float32),
+               "tactile": rng.random((3, 3 * sensors * 4, 32, 32), dtype=np.float32) * 2 - 1}
+        a = vt_load({k: v.copy() for k, v in obs.items()}, frame_stack=4)
+        b = O.vt_load({k: v.copy() for k, v in obs.items()}, frame_stack=4)
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert torch.equal(torch.as_tensor(a[k]), torch.as_tensor(b[k])), k

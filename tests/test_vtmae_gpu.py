@@ -234,6 +234,38 @@ def test_reconstruct_vs_oracle(nt, ratio, ecm):
             assert cos(a, b) >= 0.9995 and (a - b).abs().max() < 5e-2, (k, cos(a, b), float((a - b).abs().max()))
 
 
+def test_mae_extractor_rollout_graph_matches_eager():
+    """Rollout-time inference (torch.no_grad) replays a CUDA graph cached per observation shape: same features as the
+    eager chain, for new observations and after a parameter update, numpy observations included."""
+    from m3l_b200 import MAEExtractor
+    cfg = O.VTMAEConfig(depth=2)
+    sd = O.init_state_dict(cfg, seed=4)
+    gen = torch.Generator().manual_seed(16)
+    mae = build_product(cfg, weights=sd)
+    ext = MAEExtractor(None, mae, cfg.dim, False, cfg.frame_stack).to(DEV)
+
+    def obs(B):
+        return {"image": torch.rand(B, cfg.frame_stack, 64, 64, 3, generator=gen),
+                "tactile": torch.rand(B, cfg.frame_stack, 6, 32, 32, generator=gen) * 2 - 1}
+
+    for B in (2, 5, 2):
+        o = obs(B)
+        with torch.no_grad():
+            got = ext({k: v.numpy() for k, v in o.items()})           # SB3 hands numpy arrays over
+            ext.use_cuda_graph = False
+            want = ext({k: v.to(DEV) for k, v in o.items()})
+            ext.use_cuda_graph = True
+        assert got.shape == (B, cfg.dim) and torch.equal(got, want)
+    with torch.no_grad():
+        for p in ext.parameters():
+            p.mul_(1.01)                                              # e.g. an optimizer step between rollouts
+        o = obs(2)
+        got = ext({k: v.to(DEV) for k, v in o.items()})
+        ext.use_cuda_graph = False
+        want = ext({k: v.to(DEV) for k, v in o.items()})
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("vision_only", [False, True])
 def test_mae_extractor_vs_oracle(vision_only):
     """MAEExtractor.forward (pretrain_models.py:819-841): raw 5-D observations -> (B, dim) features, and the
