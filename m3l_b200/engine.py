@@ -10,6 +10,8 @@ Reference semantics followed (paths relative to /root/reference):
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -50,6 +52,22 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, gview: torch.Tensor) -> None:
     out_f, in_f = gview.shape
     bn, splits = _wgrad_tiling(out_f, in_f, dy.shape[0])
     ops.gemm(dy, x, mn_major=True, out=gview, accumulate=True, splits=splits, bn=bn)
+
+
+@contextlib.contextmanager
+def capture_guard():
+    """Around a CUDA-graph capture: no cyclic-garbage collection inside it.  A stale model that owns captured graphs
+    (e.g. one dropped by the caller but still in a reference cycle) would otherwise be finalised in the middle of the
+    capture, and CUDAGraph.reset() / cudaFree are illegal while a stream is capturing."""
+    gc.collect()
+    torch.cuda.synchronize()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 _SIDE_STREAMS: Dict = {}

@@ -165,23 +165,24 @@ class FusedTrainer:
         self.model.arena.refresh_shadows()
         out = {"xs": sx, "noise": sn, "box": {}}
         counter = ops.LaunchCounter()
-        if self.world == 1:
-            g = torch.cuda.CUDAGraph()
-            with counter, torch.cuda.graph(g):
-                self._phase_a(sx, sn, geo, out["box"])
-                self._phase_b(out["box"])
-                self._phase_c(ranges)
-            out["all"] = g
-        else:
-            ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            pool = torch.cuda.graph_pool_handle()
-            with counter:
-                with torch.cuda.graph(ga, pool=pool):
+        with engine.capture_guard():
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with counter, torch.cuda.graph(g):
                     self._phase_a(sx, sn, geo, out["box"])
-                with torch.cuda.graph(gb, pool=pool):
                     self._phase_b(out["box"])
-                with torch.cuda.graph(gc, pool=pool):
                     self._phase_c(ranges)
-            out.update(a=ga, b=gb, c=gc)
+                out["all"] = g
+            else:
+                ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                pool = torch.cuda.graph_pool_handle()
+                with counter:
+                    with torch.cuda.graph(ga, pool=pool):
+                        self._phase_a(sx, sn, geo, out["box"])
+                    with torch.cuda.graph(gb, pool=pool):
+                        self._phase_b(out["box"])
+                    with torch.cuda.graph(gc, pool=pool):
+                        self._phase_c(ranges)
+                out.update(a=ga, b=gb, c=gc)
         self.kernel_launches_per_step = counter.count
         return out

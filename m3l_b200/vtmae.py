@@ -258,6 +258,7 @@ class VTMAE(nn.Module):
         self.arena: Optional[ParamArena] = None
         self._tables: Dict = {}
         self._trainer = None
+        self.use_cuda_graph = True      # replay mae(x) / .backward() from CUDA graphs (see _MAEGraphFn)
         self.last_masked_indices = self.last_unmasked_indices = None
 
     # ------------------------------------------------------------------------------ plumbing
@@ -286,6 +287,7 @@ class VTMAE(nn.Module):
             self.arena = ParamArena(self._canonical_named_params(), dev, late_names=late)
             self._tables = {}
             self._trainer = None
+            self.__dict__.pop("_mae_graphs", None)      # captured graphs point into the old arena
         self.arena.sync()
         return self.arena
 
@@ -350,7 +352,11 @@ class VTMAE(nn.Module):
         noise = noise.to(device=A.device, dtype=torch.float32).contiguous()
         assert noise.shape == (B, geo.n), f"noise must be ({B}, {geo.n})"
         live = self.live_param_names(geo, True)
-        return _MAEFn.apply(self, xs, noise, geo, tuple(live), *[A.params[k] for k in live])
+        params = [A.params[k] for k in live]
+        if self.use_cuda_graph and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            ent = _graph_entry(self, ("mae", geo.use_vision, geo.nt, B), xs, noise, geo)
+            return _MAEGraphFn.apply(self, ent, geo, tuple(live), *params)
+        return _MAEFn.apply(self, xs, noise, geo, tuple(live), *params)
 
     def get_embeddings(self, x, eval=True, use_vision=True, use_tactile=True):
         """Encoder over all tokens, no masking (pretrain_models.py:588-668) -> (B, N, dim) fp32."""
@@ -511,8 +517,10 @@ class MAEExtractor(_ExtractorBase):
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(obs.items())) + (bool(self.vision_only_control),)
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
-        mae._sync()                                               # bf16 shadows current (outside the graph)
-        self.vit_layer.transformer._own_arena()
+        A = mae._sync()                                           # bf16 shadows current (outside the graph)
+        Av = self.vit_layer.transformer._own_arena()
+        key = key + (id(A), id(Av))                               # a re-created arena invalidates captured pointers
+        ent = cache.get(key)
         if ent is None:
             static_in = {k: v.clone() for k, v in obs.items()}
             s = torch.cuda.Stream()
@@ -522,7 +530,7 @@ class MAEExtractor(_ExtractorBase):
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with engine.capture_guard(), torch.cuda.graph(g):
                 out = self._forward_eager(dict(static_in))
             ent = cache[key] = (g, static_in, out)
         g, static_in, out = ent
@@ -583,6 +591,93 @@ class _ExtractorFn(torch.autograd.Function):
         gm = A.new_grad_buffer()
         engine.embeddings_backward(mae, c, demb, gm)
         return (None, None, None, None, None, None, *[A.view(gm, k) for k in live], *[Av.view(gv, k) for k in vit_names])
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA-graph replay of the autograd path  loss = mae(x); loss.backward()
+# --------------------------------------------------------------------------------------------
+# The reference's learners call the module through autograd (ppo_mae.py:262-263, sac_mae.py:284-291).  Eagerly that is
+# ~165 kernel launches behind Python / ctypes calls: 6.3 ms of host time for 2.3 ms of GPU work at batch 256
+# (tools/eager_latency.py).  Forward and backward are therefore captured once per (modalities, batch) as two CUDA graphs
+# sharing one memory pool (the forward graph's saved activations are the backward graph's inputs) and replayed.
+_MAX_GRAPHS = 4
+
+
+class _GraphEntry:
+    __slots__ = ("fwd", "bwd", "xs", "noise", "loss", "ctx", "gflat", "gout", "gen", "consumed", "masked", "unmasked")
+
+
+def _graph_entry(model, key, xs, noise, geo):
+    cache = model.__dict__.setdefault("_mae_graphs", {})
+    ent = cache.get(key)
+    if ent is None:
+        if len(cache) >= _MAX_GRAPHS:
+            cache.pop(next(iter(cache)))
+        ent = cache[key] = _capture_mae_graphs(model, xs, noise, geo)
+    for k, v in xs.items():
+        ent.xs[k].copy_(v, non_blocking=True)
+    ent.noise.copy_(noise, non_blocking=True)
+    return ent
+
+
+def _capture_mae_graphs(model, xs, noise, geo):
+    A = model.arena
+    ent = _GraphEntry()
+    ent.xs = {k: v.clone() for k, v in xs.items()}
+    ent.noise = noise.clone()
+    ent.gflat = A.new_grad_buffer()
+    ent.gout = torch.ones((), dtype=torch.float32, device=A.device)
+    ent.gen, ent.consumed = 0, True
+
+    def fwd():
+        ent.gflat.zero_()
+        ent.loss, ent.ctx = engine.mae_forward(model, ent.xs, ent.noise, geo, training=True, gflat=ent.gflat)
+        ent.masked, ent.unmasked = model.last_masked_indices, model.last_unmasked_indices
+
+    def bwd():
+        engine.mae_backward_decoder(model, ent.ctx, ent.gflat)
+        engine.mae_backward_encoder(model, ent.ctx, ent.gflat)
+        ent.gflat.mul_(ent.gout)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):                       # warm-up: lazy tables, kernel attributes, allocator
+        fwd()
+        bwd()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    ent.fwd, ent.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with engine.capture_guard():
+        with torch.cuda.graph(ent.fwd, pool=pool):
+            fwd()
+        with torch.cuda.graph(ent.bwd, pool=pool):
+            bwd()
+    return ent
+
+
+class _MAEGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, ent, geo, live, *params):
+        ent.gen += 1
+        ent.consumed = False
+        ent.fwd.replay()
+        model.last_masked_indices, model.last_unmasked_indices = ent.masked, ent.unmasked
+        ctx.model, ctx.ent, ctx.gen, ctx.live = model, ent, ent.gen, live
+        return ent.loss.reshape(()).clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        ent, A = ctx.ent, ctx.model.arena
+        if ctx.gen != ent.gen or ent.consumed:
+            raise M3LError("backward through a CUDA-graph replayed forward whose saved activations were overwritten by a "
+                           "newer forward of the same shape (or a second backward): set model.use_cuda_graph = False "
+                           "for this pattern")
+        ent.consumed = True
+        ent.gout.copy_(gout.reshape(()))
+        ent.bwd.replay()
+        g = ent.gflat.clone()          # the static buffer is zeroed by the next replay; .grad must never alias it
+        return (None, None, None, None, *[A.view(g, k) for k in ctx.live])
 
 
 class _MAEFn(torch.autograd.Function):

@@ -234,6 +234,50 @@ def test_reconstruct_vs_oracle(nt, ratio, ecm):
             assert cos(a, b) >= 0.9995 and (a - b).abs().max() < 5e-2, (k, cos(a, b), float((a - b).abs().max()))
 
 
+def test_autograd_graph_path_matches_eager():
+    """loss = mae(x); loss.backward() replayed from CUDA graphs (the default) against the eager kernel sequence:
+    identical loss, indices and gradients over several calls with fresh inputs, .grad never aliasing the graph's
+    static buffers, and a loud error for the one unsupported pattern (backward of a superseded forward)."""
+    from m3l_b200._lib import M3LError
+    cfg = O.VTMAEConfig(depth=2, decoder_depth=2)
+    sd = O.init_state_dict(cfg, seed=3)
+    mae_g = build_product(cfg, weights=sd)
+    mae_e = build_product(cfg, weights=sd)
+    mae_e.use_cuda_graph = False
+    gen = torch.Generator().manual_seed(77)
+    B = 6
+    kept = None
+    for it in range(3):
+        x = {"image": torch.rand(B, 12, 64, 64, generator=gen), "tactile1": torch.rand(B, 12, 32, 32, generator=gen),
+             "tactile2": torch.rand(B, 12, 32, 32, generator=gen)}
+        noise = O.tie_free_noise(B, 192, gen, [64] * 3)
+        for m in (mae_g, mae_e):
+            m.zero_grad(set_to_none=True)
+        lg = mae_g(to_dev(x), noise=noise.to(DEV)); lg.backward(torch.tensor(0.5 + it, device=DEV))
+        le = mae_e(to_dev(x), noise=noise.to(DEV)); le.backward(torch.tensor(0.5 + it, device=DEV))
+        assert torch.equal(lg.detach(), le.detach())
+        assert torch.equal(mae_g.last_masked_indices, mae_e.last_masked_indices)
+        ge, gg = dict(mae_e.named_parameters()), dict(mae_g.named_parameters())
+        for k, p in ge.items():
+            assert (p.grad is None) == (gg[k].grad is None), k
+            if p.grad is not None:
+                assert torch.allclose(gg[k].grad, p.grad, rtol=2e-3, atol=1e-6), k     # fp32 atomics: order only
+        if kept is None:
+            kept = {k: p.grad.clone() for k, p in gg.items() if p.grad is not None}
+            held = {k: p.grad for k, p in gg.items() if p.grad is not None}
+            for m in (mae_g,):
+                m.zero_grad(set_to_none=True)
+        else:
+            for k in kept:                        # the tensors autograd handed out earlier were not overwritten
+                assert torch.equal(held[k], kept[k]), k
+    x1 = to_dev(x)
+    l1 = mae_g(x1, noise=noise.to(DEV))
+    l2 = mae_g(x1, noise=noise.to(DEV))
+    with pytest.raises(M3LError):
+        l1.backward()
+    l2.backward()
+
+
 def test_mae_extractor_rollout_graph_matches_eager():
     """Rollout-time inference (torch.no_grad) replays a CUDA graph cached per observation shape: same features as the
     eager chain, for new observations and after a parameter update, numpy observations included."""
