@@ -505,9 +505,32 @@ class MAEExtractor(_ExtractorBase):
         mae = self.mae_model
         dev = mae.mask_token.device
         obs = {k: torch.as_tensor(v).to(dev) for k, v in observations.items() if k in ('image', 'tactile')}
-        if not torch.is_grad_enabled() and getattr(self, "use_cuda_graph", True):
-            return self._forward_graph(obs)
+        if getattr(self, "use_cuda_graph", True):
+            if not torch.is_grad_enabled():
+                return self._forward_graph(obs)
+            if any(p.requires_grad for p in self.parameters()):
+                return self._forward_graph_grad(obs)
         return self._forward_eager(obs)
+
+    def _forward_graph_grad(self, obs):
+        """Training-time call (PPO / SAC evaluate the policy on a minibatch and back-propagate through the extractor:
+        ppo_mae.py:280,340): forward and backward replayed from two CUDA graphs sharing one memory pool."""
+        mae = self.mae_model
+        mae.train()                                               # get_embeddings(eval=False) side effect (:590-593)
+        A = mae._sync()
+        Av = self.vit_layer.transformer._own_arena()
+        key = ("grad",) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(obs.items())) + \
+              (bool(self.vision_only_control), id(A), id(Av))
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            ent = cache[key] = _capture_extractor_graphs(self, obs)
+        for k, v in obs.items():
+            ent.xs[k].copy_(v, non_blocking=True)
+        return self.flatten(_ExtractorGraphFn.apply(self, ent, ent.live, ent.vit_names,
+                                                    *[A.params[k] for k in ent.live], *[Av.params[k] for k in ent.vit_names]))
 
     def _forward_graph(self, obs):
         """Rollout-time inference (torch.no_grad): the whole chain — observation reshapes, vt_load, encoder, extra
@@ -517,6 +540,7 @@ class MAEExtractor(_ExtractorBase):
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(obs.items())) + (bool(self.vision_only_control),)
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
+        mae.train()                                               # get_embeddings(eval=False) side effect (:590-593)
         A = mae._sync()                                           # bf16 shadows current (outside the graph)
         Av = self.vit_layer.transformer._own_arena()
         key = key + (id(A), id(Av))                               # a re-created arena invalidates captured pointers
@@ -540,6 +564,15 @@ class MAEExtractor(_ExtractorBase):
         return out.clone()
 
     def _forward_eager(self, obs):
+        xs, geo, B, A, Av = self._prep(obs)
+        live = self.mae_model.live_param_names(geo, False)
+        vit_names = list(Av.names)
+        out = _ExtractorFn.apply(self, xs, geo, B, tuple(live), tuple(vit_names),
+                                 *[A.params[k] for k in live], *[Av.params[k] for k in vit_names])
+        return self.flatten(out)
+
+    def _prep(self, obs):
+        """Observation reshapes (pretrain_models.py:823-827) + vt_load -> (model inputs, geometry, batch, arenas)."""
         from .data import vt_load
         mae = self.mae_model
         if 'image' in obs and obs['image'].dim() == 5:            # (B, F, H, W, 3) -> (B, H, W, 3F)
@@ -556,11 +589,7 @@ class MAEExtractor(_ExtractorBase):
         if tr.p_drop > 0 and tr.training:
             raise M3LError("dropout > 0 in training mode is not supported by the fused kernels")
         Av = tr._own_arena()
-        live = mae.live_param_names(geo, False)
-        vit_names = list(Av.names)
-        out = _ExtractorFn.apply(self, xs, geo, B, tuple(live), tuple(vit_names),
-                                 *[A.params[k] for k in live], *[Av.params[k] for k in vit_names])
-        return self.flatten(out)
+        return xs, geo, B, A, Av
 
 
 class _ExtractorFn(torch.autograd.Function):
@@ -593,6 +622,78 @@ class _ExtractorFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *[A.view(gm, k) for k in live], *[Av.view(gv, k) for k in vit_names])
 
 
+def _capture_extractor_graphs(ext, obs):
+    mae, tr = ext.mae_model, ext.vit_layer.transformer
+    ent = _GraphEntry()
+    ent.xs = {k: v.clone() for k, v in obs.items()}
+    ent.gen, ent.consumed = 0, True
+    xs, geo, B, A, Av = ext._prep(dict(ent.xs))
+    ent.live, ent.vit_names = tuple(mae.live_param_names(geo, False)), tuple(Av.names)
+    ent.gflat, ent.gflat2 = A.new_grad_buffer(), Av.new_grad_buffer()
+    ent.gout = torch.zeros((B, tr.dim), dtype=torch.float32, device=A.device)
+    spec = engine.StackSpec("t", tr.dim, tr.depth, tr.heads, tr.dim_head, tr.mlp_dim)
+
+    def fwd():
+        xs, geo, B, _, _ = ext._prep(dict(ent.xs))
+        emb, c = engine.embeddings_forward(mae, xs, geo, B, training=True)
+        saved = []
+        xe = engine.stack_fwd(Av, spec, emb, B, geo.n, saved)
+        y, st = ops.layernorm_fwd(xe, Av.f32("t.norm.weight"), Av.f32("t.norm.bias"), want_stats=True)
+        ent.loss = ops.token_mean_fwd(y, B, geo.n)
+        ent.ctx = (c, saved, xe, st, B, geo.n)
+
+    def bwd():
+        c, saved, xe, st, B, n = ent.ctx
+        ent.gflat.zero_()
+        ent.gflat2.zero_()
+        Gv = engine.GradView(Av, ent.gflat2)
+        dy = ops.token_mean_bwd(ent.gout, B, n)
+        dxe = ops.layernorm_bwd(dy, xe, st, Av.f32("t.norm.weight"), dgamma=Gv("t.norm.weight"), dbeta=Gv("t.norm.bias"),
+                                dx_colsum=Gv(engine.last_ff_bias(spec)))
+        demb = engine.stack_bwd(Av, Gv, spec, dxe, B, n, saved)
+        engine.embeddings_backward(mae, c, demb, ent.gflat)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fwd()
+        bwd()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    ent.fwd, ent.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with engine.capture_guard():
+        with torch.cuda.graph(ent.fwd, pool=pool):
+            fwd()
+        with torch.cuda.graph(ent.bwd, pool=pool):
+            bwd()
+    return ent
+
+
+class _ExtractorGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ext, ent, live, vit_names, *params):
+        ent.gen += 1
+        ent.consumed = False
+        ent.fwd.replay()
+        ctx.ext, ctx.ent, ctx.gen = ext, ent, ent.gen
+        return ent.loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        ent = ctx.ent
+        if ctx.gen != ent.gen or ent.consumed:
+            raise M3LError("backward through a CUDA-graph replayed extractor forward whose saved activations were "
+                           "overwritten by a newer forward of the same shape (or a second backward): set "
+                           "extractor.use_cuda_graph = False for this pattern")
+        ent.consumed = True
+        ent.gout.copy_(gout)
+        ent.bwd.replay()
+        A, Av = ctx.ext.mae_model.arena, ctx.ext.vit_layer.transformer._arena
+        gm, gv = ent.gflat.clone(), ent.gflat2.clone()    # .grad must never alias the graph's static buffers
+        return (None, None, None, None, *[A.view(gm, k) for k in ent.live], *[Av.view(gv, k) for k in ent.vit_names])
+
+
 # --------------------------------------------------------------------------------------------
 # CUDA-graph replay of the autograd path  loss = mae(x); loss.backward()
 # --------------------------------------------------------------------------------------------
@@ -604,7 +705,8 @@ _MAX_GRAPHS = 4
 
 
 class _GraphEntry:
-    __slots__ = ("fwd", "bwd", "xs", "noise", "loss", "ctx", "gflat", "gout", "gen", "consumed", "masked", "unmasked")
+    __slots__ = ("fwd", "bwd", "xs", "noise", "loss", "ctx", "gflat", "gflat2", "gout", "gen", "consumed", "masked", "unmasked",
+                 "live", "vit_names")
 
 
 def _graph_entry(model, key, xs, noise, geo):

@@ -308,6 +308,21 @@ def test_mae_extractor_rollout_graph_matches_eager():
         ext.use_cuda_graph = False
         want = ext({k: v.to(DEV) for k, v in o.items()})
     assert torch.equal(got, want)
+    # training-time call (gradients through the extractor): graph replay against the eager chain
+    w = torch.randn(4, cfg.dim, generator=gen).to(DEV)
+    grads = []
+    for use_graph in (True, False, True):
+        ext.use_cuda_graph = use_graph
+        ext.zero_grad(set_to_none=True)
+        o = obs(4) if use_graph is True and not grads else o
+        f = ext({k: v.to(DEV) for k, v in o.items()})
+        assert f.requires_grad and mae.training
+        (f * w).sum().backward()
+        grads.append((f.detach().clone(), {k: p.grad.clone() for k, p in ext.named_parameters() if p.grad is not None}))
+    for f, g in grads[1:]:
+        assert torch.equal(f, grads[0][0]) and g.keys() == grads[0][1].keys()
+        for k in g:
+            assert torch.allclose(g[k], grads[0][1][k], rtol=2e-3, atol=1e-6), k
 
 
 @pytest.mark.parametrize("vision_only", [False, True])
