@@ -660,7 +660,7 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const int32_t* __restrict__ src_
       }
     };
     phase1(base_a, ms_a.x, ms_a.y, true, xh_a, g_a, sk_a, s1a, s2a);
-    phase1(base_b, ms_b.x, ms_b.y, has_b, xh_b, g_b, sk_b, s1b, s2b);
+    if (has_b) phase1(base_b, ms_b.x, ms_b.y, true, xh_b, g_b, sk_b, s1b, s2b);   // never touch an unloaded stage (0 * NaN)
     issue(r + kStages * rstride, stage);
     issue(rb + kStages * rstride, stage + 1);
     stage = (stage + 2 == kStages) ? 0 : stage + 2;

@@ -199,6 +199,27 @@ def test_layernorm_fwd_bwd(ops, D, fp32_in):
     assert rel_err(dc, (xr.grad + skip.float()).sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("M", [1, 3, 9, 2049, 4737])
+def test_layernorm_bwd_ragged_rows(ops, M):
+    """Row counts that leave the second row of a warp's two-row iteration (and whole ring stages) unloaded: the
+    parameter-gradient sums must not pick up anything from stale / never-written shared memory (NaN poison first)."""
+    torch.manual_seed(M)
+    D = 256
+    poison = torch.full((148 * 2 * 8 * 4 * 3, D), float("nan"), device=DEV).bfloat16()    # touch lots of memory with NaN
+    del poison
+    x = (torch.randn(M, D, device=DEV) * 2 + 0.5).bfloat16()
+    gamma, beta = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    y, stats = ops.layernorm_fwd(x, gamma, beta)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), gr, br).backward((dy := torch.randn(M, D, device=DEV).bfloat16()).float())
+    dg, db, dc = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    dx = ops.layernorm_bwd(dy, x, stats, gamma, dgamma=dg, dbeta=db, dx_colsum=dc)
+    assert torch.isfinite(dx.float()).all() and torch.isfinite(dg).all() and torch.isfinite(db).all() and torch.isfinite(dc).all()
+    assert rel_err(dx, xr.grad) < 1e-2 and rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+    assert rel_err(dc, xr.grad.sum(0)) < 2e-3 + 1e-2 * (M < 4)
+
+
 def test_layernorm_row_remap_and_adds(ops):
     torch.manual_seed(6)
     M, D = 64, 256
