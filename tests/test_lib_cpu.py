@@ -45,3 +45,23 @@ def test_sass_is_blackwell_native(lib):
     sass = subprocess.run(["cuobjdump", "-sass", str(build.LIB)], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+
+
+def test_single_thread_issue_sites_use_the_uniform_datapath(lib):
+    """Regression guard for the `elect.sync` rule (DESIGN.md §4 'Measured'): no tcgen05.mma / TMA load / TMA store in
+    the built objects may sit inside a VOTEU / ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop, which is what the
+    compiler emits when the issuing thread is selected with `lane == 0` (100-150 clk per instruction)."""
+    import shutil
+    import subprocess
+    from m3l_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    for name in ("gemm", "gemm_gelu", "attention"):
+        obj = build.OBJ / f"{name}.o"
+        assert obj.exists(), obj
+        sass = subprocess.run([cuobjdump, "-sass", str(obj)], capture_output=True, text=True).stdout.splitlines()
+        issue = [i for i, l in enumerate(sass) if re.search(r"\b(UTCHMMA|UTMALDG|UTMASTG|UTMAREDG)\b", l)]
+        assert issue, f"{name}: no tcgen05 / TMA instructions found"
+        bad = [i for i in issue if any("BRA.U.ANY" in l for l in sass[i + 1:i + 4])]
+        assert not bad, f"{name}: {len(bad)} of {len(issue)} MMA / TMA instructions are issued from a waterfall loop"
