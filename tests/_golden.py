@@ -54,3 +54,44 @@ class Golden:
 
     def after(self):
         return {k[6:]: self.t(k) for k in self.z.files if k.startswith("after.")}
+
+
+VTT_DINO_CASES = sorted(p.stem for p in (GOLDEN / "vtt_dino").glob("*.npz"))
+
+
+class VttDinoGolden:
+    """tests/golden/vtt_dino/*.npz (oracle/make_golden_vtt_dino.py): models/VTT.py::VTT.forward_features."""
+
+    def __init__(self, name):
+        from oracle import vtt_dino_oracle as VD
+        self.z = np.load(GOLDEN / "vtt_dino" / f"{name}.npz")
+        cfgd = json.loads(bytes(self.z["config_json"]).decode())
+        for k in ("image_size", "tactile_size"):
+            cfgd[k] = tuple(cfgd[k])
+        self.cfg = VD.VTTDinoConfig(**cfgd)
+        self.batch = int(self.z["batch"])
+
+    def t(self, key):
+        return torch.from_numpy(np.array(self.z[key]))
+
+    def weights(self):
+        return {k[2:]: self.t(k).clone() for k in self.z.files if k.startswith("w.")}
+
+    def inputs(self):
+        return {k[2:]: self.t(k) for k in self.z.files if k.startswith("x.")}
+
+    def masks(self):
+        return [self.t(f"mask.{i}") for i in range(int(self.z["n_masks"]))] or None
+
+    def objective(self, out):
+        w1, w2 = self.t("w1").to(out["x_prenorm"].device), self.t("w2").to(out["x_prenorm"].device)
+        return (out["x_norm_patchtokens"] * w1).sum() + (out["x_norm_regtokens"] ** 2).sum() + 0.5 * (out["x_prenorm"] * w2).sum()
+
+    def grad_present(self):
+        return {k[5:]: bool(self.z[k]) for k in self.z.files if k.startswith("ghas.")}
+
+    def grad_norms(self):
+        return {k[6:]: float(self.z[k]) for k in self.z.files if k.startswith("gnorm.")}
+
+    def full_grads(self):
+        return {k[5:]: self.t(k) for k in self.z.files if k.startswith("grad.")}

@@ -3,7 +3,7 @@ import pytest
 import torch
 
 from oracle import vtmae_oracle as O
-from tests._golden import CASES, Golden
+from tests._golden import CASES, VTT_DINO_CASES, Golden, VttDinoGolden
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -86,3 +86,28 @@ def test_product_vt_load_matches_oracle():
         assert sorted(a) == sorted(b)
         for k in a:
             assert torch.equal(torch.as_tensor(a[k]), torch.as_tensor(b[k])), k
+
+
+
+@pytest.mark.parametrize("name", VTT_DINO_CASES)
+def test_vtt_dino_oracle_matches_reference_golden(name):
+    """oracle/vtt_dino_oracle.py against outputs of the unmodified models/VTT.py::VTT frozen by
+    oracle/make_golden_vtt_dino.py (runs anywhere: the GPU box has no /root/reference)."""
+    from oracle import vtt_dino_oracle as VD
+    g = VttDinoGolden(name)
+    sd = g.weights()
+    for k in sd:
+        if sd[k].dtype.is_floating_point and k != "pos_embed.frequency_bands":
+            sd[k].requires_grad_(True)
+    out = VD.forward_features(sd, g.cfg, g.inputs(), g.masks())
+    for k in ("x_norm_regtokens", "x_norm_patchtokens", "x_prenorm"):
+        assert torch.equal(out[k].detach(), g.t("out." + k)), k
+    g.objective(out).backward()
+    for k, has in g.grad_present().items():
+        gr = sd[k].grad
+        assert (gr is not None and float(gr.abs().max()) > 0) == has, k
+    for k, n in g.grad_norms().items():
+        if n > 0:
+            assert abs(float(sd[k].grad.double().norm()) - n) <= 1e-5 * n, k
+    for k, gr in g.full_grads().items():
+        assert torch.allclose(sd[k].grad, gr, rtol=1e-5, atol=1e-7), k

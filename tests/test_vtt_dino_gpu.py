@@ -79,3 +79,38 @@ def test_forward_returns_patch_tokens_and_fails_on_cpu():
     with torch.no_grad():
         y = m({k: v.to(DEV) for k, v in x.items()})
     assert y.shape == (2, 192, 256)
+
+
+from tests._golden import VTT_DINO_CASES, VttDinoGolden   # noqa: E402
+
+
+@pytest.mark.parametrize("name", VTT_DINO_CASES)
+def test_forward_features_vs_reference_golden(name):
+    """The kernel path against outputs / gradients of the UNMODIFIED reference models/VTT.py::VTT frozen in
+    tests/golden/vtt_dino/ (oracle/make_golden_vtt_dino.py)."""
+    from m3l_b200.vtt import VTT
+    g = VttDinoGolden(name)
+    cfg = g.cfg
+    m = VTT(image_size=cfg.image_size, tactile_size=cfg.tactile_size, image_patch_size=cfg.image_patch_size,
+            tactile_patch_size=cfg.tactile_patch_size, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim,
+            num_tactiles=cfg.num_tactiles, image_channels=cfg.image_channels, tactile_channels=cfg.tactile_channels,
+            dim_head=cfg.dim_head, num_register_tokens=cfg.num_register_tokens, pos_embed_fn="sinusoidal")
+    m.load_state_dict(g.weights(), strict=True)
+    m = m.to(DEV)
+    masks = g.masks()
+    out = m.forward_features({k: v.to(DEV) for k, v in g.inputs().items()}, [mk.to(DEV) for mk in masks] if masks else None)
+    for k in ("x_norm_regtokens", "x_norm_patchtokens", "x_prenorm"):
+        ref = g.t("out." + k)
+        assert out[k].shape == ref.shape
+        if ref.numel():
+            assert cos(out[k], ref) >= 0.9995, (k, cos(out[k], ref))
+    g.objective(out).backward()
+    named = dict(m.named_parameters())
+    for k, has in g.grad_present().items():
+        got = named[k].grad
+        assert (got is not None and float(got.abs().max()) > 0) == has, k
+    for k, n in g.grad_norms().items():
+        if n > 1e-6:
+            assert abs(float(named[k].grad.double().norm()) - n) <= 3e-2 * n, (k, float(named[k].grad.double().norm()), n)
+    for k, gr in g.full_grads().items():
+        assert cos(named[k].grad, gr) >= 0.999, (k, cos(named[k].grad, gr))
