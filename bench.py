@@ -89,11 +89,6 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def canonical_cfg():
-    from oracle import vtmae_oracle as O  # config dataclass only (geometry constants)
-    return O.VTMAEConfig()
-
-
 def build_model(device):
     import torch
     from m3l_b200 import VTT, VTMAE
