@@ -111,3 +111,24 @@ def test_vtt_dino_oracle_matches_reference_golden(name):
             assert abs(float(sd[k].grad.double().norm()) - n) <= 1e-5 * n, k
     for k, gr in g.full_grads().items():
         assert torch.allclose(sd[k].grad, gr, rtol=1e-5, atol=1e-7), k
+
+
+def test_product_geometry_matches_oracle_mask_counts():
+    """Host logic of the product (engine.make_geometry: the Python-float truncations of pretrain_models.py:223-227 and
+    the per-modality rule of reconstruct(), :425,433) against the oracle over a sweep of ratios and token grids."""
+    from types import SimpleNamespace
+    from m3l_b200 import engine
+    from oracle import vtmae_oracle as O
+    for n_img, n_tac, nt in ((64, 64, 2), (64, 64, 0), (16, 16, 2), (25, 25, 2), (64, 16, 1), (36, 64, 3)):
+        for r in (0.05, 0.3, 0.5, 0.75, 0.8, 0.9, 0.95, 0.99):
+            cfg = SimpleNamespace(num_tactiles=nt, n_img=n_img, n_tac=n_tac, masking_ratio=r)
+            for use_vision, use_tactile in ((True, True), (True, False), (False, True)):
+                if (not use_tactile or nt == 0) and not use_vision:
+                    continue
+                g = engine.make_geometry(cfg, use_vision, use_tactile)
+                ni = n_img if use_vision else 0
+                ntt = nt * n_tac if (use_tactile and nt) else 0
+                assert (g.nm_img, g.nm_tac) == O.mask_counts(r, ni, ntt, nt), (n_img, n_tac, nt, r, use_vision, use_tactile)
+                assert g.n == ni + ntt and g.nv == g.n - g.nm
+                gr = engine.make_geometry(cfg, use_vision, use_tactile, reconstruct_ratio=r)
+                assert (gr.nm_img, gr.nm_tac) == O.mask_counts_reconstruct(r, ni, ntt, nt)
