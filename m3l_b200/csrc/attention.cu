@@ -657,11 +657,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       for (int i = 0; i < p.q_tiles; ++i) {
         const int grow = i * 128 + row;
         d[i] = 0.f; l[i] = 0.f;
-#ifdef M3L_EXP_NOSTATS
-        if (grow < 0) {
-#else
         if (grow < n) {
-#endif
           l[i] = p.lse[((size_t)b * p.heads + h) * n + grow];     // raw: scaled at use, so the load stays in flight
           if (p.delta != nullptr) {
             d[i] = p.delta[((size_t)b * n + grow) * p.heads + h];
