@@ -367,7 +367,19 @@ class VTMAE(nn.Module):
         A = self._sync()
         xs, geo, B = self._prep_inputs(x, use_vision, use_tactile)
         live = self.live_param_names(geo, False)
-        return _EmbFn.apply(self, xs, geo, B, tuple(live), *[A.params[k] for k in live])
+        params = [A.params[k] for k in live]
+        if self.use_cuda_graph and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            cache = self.__dict__.setdefault("_mae_graphs", {})
+            key = ("emb", geo.use_vision, geo.nt, B)
+            ent = cache.get(key)
+            if ent is None:
+                if len(cache) >= _MAX_GRAPHS:
+                    cache.pop(next(iter(cache)))
+                ent = cache[key] = _capture_emb_graphs(self, xs, geo, B)
+            for k, v in xs.items():
+                ent.xs[k].copy_(v, non_blocking=True)
+            return _EmbGraphFn.apply(self, ent, tuple(live), *params)
+        return _EmbFn.apply(self, xs, geo, B, tuple(live), *params)
 
     @torch.no_grad()
     def reconstruct(self, x, mask_ratio=None, use_vision=True, use_tactile=True, noise=None):
@@ -780,6 +792,62 @@ class _MAEGraphFn(torch.autograd.Function):
         ent.bwd.replay()
         g = ent.gflat.clone()          # the static buffer is zeroed by the next replay; .grad must never alias it
         return (None, None, None, None, *[A.view(g, k) for k in ctx.live])
+
+
+def _capture_emb_graphs(model, xs, geo, B):
+    """Forward / backward graphs of get_embeddings (no-mask encoder pass), same scheme as _capture_mae_graphs."""
+    A = model.arena
+    ent = _GraphEntry()
+    ent.xs = {k: v.clone() for k, v in xs.items()}
+    ent.gflat = A.new_grad_buffer()
+    ent.gout = torch.zeros((B * geo.n, model.cfg.dim), dtype=torch.bfloat16, device=A.device)
+    ent.gen, ent.consumed = 0, True
+
+    def fwd():
+        out, ent.ctx = engine.embeddings_forward(model, ent.xs, geo, B, training=True)
+        ent.loss = out.float().reshape(B, geo.n, model.cfg.dim)
+
+    def bwd():
+        ent.gflat.zero_()
+        engine.embeddings_backward(model, ent.ctx, ent.gout, ent.gflat)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fwd()
+        bwd()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    ent.fwd, ent.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with engine.capture_guard():
+        with torch.cuda.graph(ent.fwd, pool=pool):
+            fwd()
+        with torch.cuda.graph(ent.bwd, pool=pool):
+            bwd()
+    return ent
+
+
+class _EmbGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, ent, live, *params):
+        ent.gen += 1
+        ent.consumed = False
+        ent.fwd.replay()
+        ctx.model, ctx.ent, ctx.gen, ctx.live = model, ent, ent.gen, live
+        return ent.loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        ent, A = ctx.ent, ctx.model.arena
+        if ctx.gen != ent.gen or ent.consumed:
+            raise M3LError("backward through a CUDA-graph replayed get_embeddings whose saved activations were overwritten "
+                           "by a newer call of the same shape (or a second backward): set model.use_cuda_graph = False")
+        ent.consumed = True
+        ent.gout.copy_(gout.reshape(ent.gout.shape))
+        ent.bwd.replay()
+        g = ent.gflat.clone()
+        return (None, None, None, *[A.view(g, k) for k in ctx.live])
 
 
 class _MAEFn(torch.autograd.Function):
