@@ -53,6 +53,7 @@ typedef struct m3l_gemm_args {
   int32_t ld_aux;
   float alpha;        /* must be 1 */
   float* colsum_out;  /* fp32 [n] or NULL: += column sums of the bf16 output (fused bias gradient) */
+  void* out2;         /* bf16 [m, ldo] or NULL: a second copy of the output (act 0, residual given) */
   const void* dot_side; /* bf16 [m, ld_dot] or NULL (bf16 output, no residual / act; n % 64 == 0): */
   int32_t ld_dot;       /*   dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]        */
   float* dot_out;       /* fp32 [m, n/64]: with out = dO and dot_side = O this is FlashAttention's delta */
@@ -60,6 +61,36 @@ typedef struct m3l_gemm_args {
 
 int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Fused pre-norm feed-forward block, forward (dim == 256, hidden a multiple of 128 up to 1024):
+ *     out = x + W2 GELU(W1 LayerNorm(x) + b1) + b2
+ * One kernel for vit_pytorch's `x = ff(x) + x` (FeedForward.net = LayerNorm, Linear, GELU, Linear;
+ * pretrain_models.py:113,784 through vit-pytorch 1.6.4): the [rows, hidden] activation stays in
+ * tensor memory.  Optional training outputs (what the backward pass reads): stats (mean, rstd per
+ * row), xn_out = LayerNorm(x), h_out = GELU(pre), gp_out = GELU'(pre) (h_out and gp_out together).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct m3l_ln_mlp_args {
+  const void* x;      /* bf16 [rows, dim] */
+  int32_t rows, dim, hidden;
+  const float* gamma; /* [dim] LayerNorm weight */
+  const float* beta;  /* [dim] LayerNorm bias */
+  float eps;
+  const void* w1;     /* bf16 [hidden, dim] */
+  const float* b1;    /* [hidden] */
+  const void* w2;     /* bf16 [dim, hidden] */
+  const float* b2;    /* [dim] */
+  void* out;          /* bf16 [rows, dim]; out == x updates the residual stream in place */
+  int32_t out_has_x;  /* non-zero: out (!= x) already holds a copy of x, e.g. written by the producing GEMM
+                         (m3l_gemm_args.out2); then, as in the in-place case, the block output is added to out
+                         with TMA reduce-adds and x is not fetched a second time */
+  float* stats;       /* fp32 [rows, 2] or NULL */
+  void* xn_out;       /* bf16 [rows, dim] or NULL */
+  void* h_out;        /* bf16 [rows, hidden] or NULL */
+  void* gp_out;       /* bf16 [rows, hidden] or NULL */
+} m3l_ln_mlp_args;
+
+int m3l_ln_mlp_fwd(const m3l_ln_mlp_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mask sampling: per sample and per token segment (image, tactile1, tactile2, ...) the ascending
@@ -214,17 +245,23 @@ int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* do
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer over flat fp32 arenas: clip_grad_norm_(params, max_norm) + AdamW.step()
- * (pretrain_models.py:670-676,707-711; torch.optim.AdamW defaults).  `state` is 3 doubles on the
+ * (pretrain_models.py:670-676,707-711; torch.optim.AdamW defaults).  `state` is 8 doubles on the
  * device: [0] step counter, [1] sum of squares of all gradients (zero it, then call
- * m3l_grad_sumsq once per live range), [2] total gradient norm (written by step_begin).
+ * m3l_grad_sumsq once per live range), [2] total gradient norm, [3] 1 - beta1^step,
+ * [4] sqrt(1 - beta2^step) ([2..4] written by step_begin, the bias corrections in double like the
+ * Python scalars of torch.optim.AdamW).
  * Sequence per step: sumsq(ranges...) -> step_begin -> clip_adamw(ranges...).  Parameters whose
  * gradient is None in the reference are simply left out of the ranges.
+ * hyper_dev (optional): device array of 6 floats [lr, beta1, beta2, eps, weight_decay, max_norm]
+ * that overrides the scalar arguments at RUN time, so a captured CUDA graph follows
+ * optimizer.param_groups (learning-rate schedules) without being re-captured.
  * ---------------------------------------------------------------------------------------- */
 int m3l_grad_sumsq(const float* grads, size_t count, double* state, void* stream);
-int m3l_optimizer_step_begin(double* state, void* stream);
+int m3l_optimizer_step_begin(double* state, float beta1, float beta2, const float* hyper_dev, void* stream);
 int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t count,
                    const double* state, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, float max_norm, int write_clipped_grad, void* stream);
+                   float weight_decay, float max_norm, int write_clipped_grad, const float* hyper_dev,
+                   void* stream);
 
 /* bf16 shadow copies of the fp32 master weights consumed by the GEMMs: a flat cast, and transposed
  * copies (dst[c, r] = src[r, c]) of a table of matrices for the dgrad products. */

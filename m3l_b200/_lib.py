@@ -28,7 +28,17 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p),
         ("ld_aux", C.c_int32), ("alpha", C.c_float), ("colsum_out", C.c_void_p),
-        ("dot_side", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
+        ("out2", C.c_void_p), ("dot_side", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
+    ]
+
+
+class LnMlpArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("rows", C.c_int32), ("dim", C.c_int32), ("hidden", C.c_int32),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("out", C.c_void_p), ("out_has_x", C.c_int32), ("stats", C.c_void_p), ("xn_out", C.c_void_p),
+        ("h_out", C.c_void_p), ("gp_out", C.c_void_p),
     ]
 
 
@@ -95,7 +105,7 @@ class MatrixDesc(C.Structure):
 
 # every symbol include/m3l_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "m3l_last_error", "m3l_gemm_bf16", "m3l_mask_indices", "m3l_patch_layernorm", "m3l_layernorm_fwd",
+    "m3l_last_error", "m3l_gemm_bf16", "m3l_ln_mlp_fwd", "m3l_mask_indices", "m3l_patch_layernorm", "m3l_layernorm_fwd",
     "m3l_layernorm_bwd", "m3l_decoder_assemble_fwd", "m3l_decoder_assemble_bwd", "m3l_rowclass_sum",
     "m3l_mse_loss", "m3l_colsum", "m3l_ln_param_grad", "m3l_attention_fwd", "m3l_attention_bwd",
     "m3l_grad_sumsq", "m3l_optimizer_step_begin", "m3l_clip_adamw", "m3l_cast_bf16",

@@ -22,10 +22,18 @@ LIB = LIBDIR / "libm3l_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
+    "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+# --use_fast_math only where the approximate exp2 / reciprocal are the point (softmax exponentials and the GELU
+# epilogues of the tensor-core kernels).  LayerNorm statistics, the MSE loss, the gradient norm and AdamW
+# (elementwise.cu, optim.cu) are compiled with IEEE division / sqrt and without flush-to-zero.
+FAST_MATH_SOURCES = {"gemm.cu", "gemm_gelu.cu", "attention.cu", "rowblock.cu"}
+
+
+def flags_for(src: Path) -> list[str]:
+    return NVCC_FLAGS + (["--use_fast_math"] if src.name in FAST_MATH_SOURCES else [])
 
 
 def _sources() -> list[Path]:
@@ -38,7 +46,7 @@ def _deps_hash(src: Path) -> str:
     for hdr in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) +
                       list((ROOT.parent / "include").glob("*.h"))):
         h.update(hdr.read_bytes())
-    h.update(" ".join(NVCC_FLAGS + ARCH_FLAGS).encode())
+    h.update(" ".join(flags_for(src) + ARCH_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -48,7 +56,7 @@ def _compile(src: Path, verbose: bool) -> Path:
     digest = _deps_hash(src)
     if obj.exists() and stamp.exists() and stamp.read_text() == digest:
         return obj
-    cmd = [NVCC, *ARCH_FLAGS, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [NVCC, *ARCH_FLAGS, *flags_for(src), "-c", str(src), "-o", str(obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = OBJ / (src.stem + ".ptxas.log")
     log.write_text(res.stderr)

@@ -169,7 +169,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
-    if (EPI == EPI_GELU_FWD) tma_prefetch_desc(&map_aux);
+    if (EPI == EPI_GELU_FWD || (EPI == EPI_BF16 && p.out2 != nullptr)) tma_prefetch_desc(&map_aux);
     if (EPI == EPI_GELU_BWD || EPI == EPI_BF16) tma_prefetch_desc(&map_side);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&bars->full[s], 1);
@@ -475,6 +475,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
             if (elect_one()) {
               tma_store_2d(&map_out, sb, gcol, row0);
+              if (EPI == EPI_BF16 && p.out2 != nullptr) tma_store_2d(&map_aux, sb, gcol, row0);   // second copy of the output
               tma_commit_group();
             }
             if (want_colsum) add_colsum(sb, row0, r);
@@ -597,6 +598,8 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
                   ((p.aux_in == nullptr && p.aux_out == nullptr) || p.ld_aux % 8 == 0),
               "gemm: output / residual / aux leading dimensions must be multiples of 8");
   M3L_REQUIRE((p.dot_out == nullptr) == (p.dot_side == nullptr), "gemm: dot_side and dot_out go together");
+  M3L_REQUIRE(p.out2 == nullptr || (p.out_mode == 0 && p.act == 0 && p.residual != nullptr && p.aux_out == nullptr),
+              "gemm: out2 needs the bf16 output mode with a residual and no activation");
   M3L_REQUIRE(p.act >= 0 && p.act <= 3 && (p.act != 3 || p.out_mode == 0), "gemm: act=%d unsupported here", p.act);
   M3L_REQUIRE(p.dot_out == nullptr || (p.out_mode == 0 && p.act == 0 && p.residual == nullptr && p.N % 64 == 0 &&
                                        p.ld_dot % 8 == 0 && !p.a_mn_major),
@@ -623,6 +626,7 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   plan->map_aux = plan->map_out;
   plan->map_side = plan->map_out;
   if (p.aux_out != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.aux_out, p.M, p.N, p.ld_aux, 32))) return s;
+  if (p.out2 != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.out2, p.M, p.N, p.ldo, 32))) return s;
   if (p.act == 2) {
     if ((s = make_tmap_2d_bf16(&plan->map_side, p.aux_in, p.M, p.N, p.ld_aux, 32))) return s;
   } else if (p.residual != nullptr) {
@@ -684,7 +688,7 @@ extern "C" int m3l_gemm_bf16(const m3l_gemm_args* a, void* stream) {
   g.out = a->out; g.ldo = a->ldo; g.out_mode = a->out_mode;
   g.bias = a->bias; g.residual = (const m3l::bf16*)a->residual; g.ldr = a->ldr;
   g.act = a->act; g.aux_out = (m3l::bf16*)a->aux_out; g.aux_in = (const m3l::bf16*)a->aux_in;
-  g.ld_aux = a->ld_aux; g.alpha = a->alpha; g.colsum_out = a->colsum_out;
+  g.ld_aux = a->ld_aux; g.alpha = a->alpha; g.colsum_out = a->colsum_out; g.out2 = (m3l::bf16*)a->out2;
   g.dot_side = (const m3l::bf16*)a->dot_side; g.ld_dot = a->ld_dot; g.dot_out = a->dot_out;
   m3l::GemmPlan plan;
   int s = m3l::gemm_make_plan(&plan, g, a->bn);

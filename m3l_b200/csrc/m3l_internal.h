@@ -26,6 +26,7 @@ struct GemmArgs {
   int ld_aux = 0;
   float alpha = 1.0f;
   float* colsum_out = nullptr;  // [N] fp32: += column sums of the (bf16) output, e.g. the bias gradient
+  bf16* out2 = nullptr;             // [M, ldo] bf16: second copy of the output (EPI_BF16 with a residual)
   const bf16* dot_side = nullptr;   // [M, ld_dot] bf16: dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]
   int ld_dot = 0;
   float* dot_out = nullptr;         // [M, N/64] fp32
@@ -33,7 +34,7 @@ struct GemmArgs {
 
 struct GemmPlan {
   CUtensorMap map_a, map_b;
-  CUtensorMap map_out, map_aux, map_side;   // epilogue tiles: output, second output (GELU'), side operand
+  CUtensorMap map_out, map_aux, map_side;   // epilogue tiles: output, second output (GELU' / out2), side operand
   GemmArgs args;
   int bn = 0;
   int grid = 0;

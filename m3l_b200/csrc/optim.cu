@@ -39,27 +39,35 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __re
   }
 }
 
-// state[0] = step counter (as double), state[1] = sum of squares of all grads, state[2] = total norm (out)
-__global__ void step_begin_kernel(double* state) {
+// state[0] = step counter (as double), state[1] = sum of squares of all grads, state[2] = total norm (out),
+// state[3] = 1 - beta1^step, state[4] = sqrt(1 - beta2^step): the bias corrections, in double like the Python
+// scalars torch.optim.AdamW computes them in (an fp32 powf per thread is ~1e-4 off for small steps).
+// hyper (optional, device): [lr, beta1, beta2, eps, weight_decay, max_norm] — read at run time so that a captured
+// CUDA graph follows optimizer.param_groups without being re-captured.
+__global__ void step_begin_kernel(double* state, float beta1, float beta2, const float* __restrict__ hyper) {
   pdl_wait();
   pdl_trigger();
+  if (hyper != nullptr) { beta1 = hyper[1]; beta2 = hyper[2]; }
   state[0] += 1.0;
   state[2] = sqrt(state[1]);
+  state[3] = 1.0 - pow((double)beta1, state[0]);
+  state[4] = sqrt(1.0 - pow((double)beta2, state[0]));
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n, const double* __restrict__ state, float lr,
                              float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                             int write_clipped_grad) {
+                             int write_clipped_grad, const float* __restrict__ hyper) {
   pdl_wait();
   pdl_trigger();
-  const float step = (float)state[0];
+  if (hyper != nullptr) {
+    lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; weight_decay = hyper[4]; max_norm = hyper[5];
+  }
   const float total = (float)state[2];
   float coef = 1.0f;
   if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (total + 1e-6f));
-  const float bc1 = 1.0f - powf(beta1, step);
-  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, step));
-  const float step_size = lr / bc1;
+  const float bc2_sqrt = (float)state[4];
+  const float step_size = (float)((double)lr / state[3]);
   const float decay = 1.0f - lr * weight_decay;
   const size_t n4 = n >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -157,23 +165,24 @@ extern "C" int m3l_grad_sumsq(const float* grads, size_t count, double* state, v
   return M3L_OK;
 }
 
-extern "C" int m3l_optimizer_step_begin(double* state, void* stream) {
+extern "C" int m3l_optimizer_step_begin(double* state, float beta1, float beta2, const float* hyper_dev, void* stream) {
   M3L_REQUIRE(state, "optimizer_step_begin: null pointer");
-  M3L_CUDA(launch_kernel(step_begin_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state));
+  M3L_CUDA(launch_kernel(step_begin_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state, beta1, beta2, hyper_dev));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }
 
 extern "C" int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t count,
                               const double* state, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, float max_norm, int write_clipped_grad, void* stream) {
+                              float weight_decay, float max_norm, int write_clipped_grad, const float* hyper_dev,
+                              void* stream) {
   M3L_REQUIRE(params && grads && exp_avg && exp_avg_sq && state, "clip_adamw: null pointer");
   M3L_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
               "clip_adamw: arenas must be 16-byte aligned");
   if (count == 0) return M3L_OK;
   M3L_CUDA(launch_kernel(adamw_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, 
       params, grads, exp_avg, exp_avg_sq, count, state, lr, beta1, beta2, eps, weight_decay, max_norm,
-      write_clipped_grad));
+      write_clipped_grad, hyper_dev));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

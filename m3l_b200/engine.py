@@ -20,7 +20,11 @@ import torch
 from . import ops
 from .arena import ParamArena
 
+import os
+
 _SM_COUNT = 148
+# M3L_FUSED_MLP=0: the unfused LayerNorm / FF1+GELU / FF2 kernels instead of csrc/rowblock.cu (A/B measurements)
+_FUSED_MLP = os.environ.get("M3L_FUSED_MLP", "1") != "0"
 
 
 @dataclass
@@ -169,12 +173,28 @@ def stack_fwd(A: ParamArena, spec: StackSpec, x: torch.Tensor, B: int, n: int, s
                                      want_stats=saved is not None)
         qkv = ops.gemm(xn1, A.bf(pa + ".to_qkv.weight"))
         o, lse = ops.attention_fwd(qkv, B, n, spec.heads, spec.dim_head, scale)
-        x_mid = ops.gemm(o, A.bf(pa + ".to_out.0.weight"), bias=A.f32(pa + ".to_out.0.bias"), residual=x)
-        xn2, st2 = ops.layernorm_fwd(x_mid, A.f32(pf + ".net.0.weight"), A.f32(pf + ".net.0.bias"),
-                                     want_stats=saved is not None)
-        pre = torch.empty((M, spec.mlp_dim), dtype=torch.bfloat16, device=x.device) if saved is not None else None
-        h = ops.gemm(xn2, A.bf(pf + ".net.1.weight"), bias=A.f32(pf + ".net.1.bias"), act=ops.GELU_FWD, aux_out=pre)
-        x_out = ops.gemm(h, A.bf(pf + ".net.4.weight"), bias=A.f32(pf + ".net.4.bias"), residual=x_mid)
+        fused = _FUSED_MLP and ops.ln_mlp_supported(spec.dim, spec.mlp_dim)
+        # training keeps x_mid for the backward pass, so the attention-output GEMM writes its result twice (x_mid and
+        # the buffer the fused feed-forward block then accumulates into); inference updates x_mid in place
+        x_out = torch.empty_like(x) if (fused and saved is not None) else None
+        x_mid = ops.gemm(o, A.bf(pa + ".to_out.0.weight"), bias=A.f32(pa + ".to_out.0.bias"), residual=x, out2=x_out)
+        if fused:
+            # LayerNorm -> Linear -> GELU -> Linear -> + residual in ONE kernel; the [M, mlp_dim] hidden stays in
+            # tensor memory (training additionally stores what the backward pass reads)
+            r = ops.ln_mlp_fwd(x_mid, A.f32(pf + ".net.0.weight"), A.f32(pf + ".net.0.bias"),
+                               A.bf(pf + ".net.1.weight"), A.f32(pf + ".net.1.bias"),
+                               A.bf(pf + ".net.4.weight"), A.f32(pf + ".net.4.bias"), save=saved is not None,
+                               out=x_out if saved is not None else x_mid, out_has_x=saved is not None)
+            if saved is not None:
+                x_out, st2, xn2, h, pre = r
+            else:
+                x_out, st2, xn2, h, pre = r, None, None, None, None
+        else:
+            xn2, st2 = ops.layernorm_fwd(x_mid, A.f32(pf + ".net.0.weight"), A.f32(pf + ".net.0.bias"),
+                                         want_stats=saved is not None)
+            pre = torch.empty((M, spec.mlp_dim), dtype=torch.bfloat16, device=x.device) if saved is not None else None
+            h = ops.gemm(xn2, A.bf(pf + ".net.1.weight"), bias=A.f32(pf + ".net.1.bias"), act=ops.GELU_FWD, aux_out=pre)
+            x_out = ops.gemm(h, A.bf(pf + ".net.4.weight"), bias=A.f32(pf + ".net.4.bias"), residual=x_mid)
         if saved is not None:
             saved.append((x, xn1, st1, qkv, o, lse, x_mid, xn2, st2, pre, h))
         x = x_out
@@ -634,6 +654,11 @@ def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
         dd = ops.decoder_assemble_bwd(dz, ctx["slots"], B, geo.n, geo.nv, dmask_token=G("mask_token"),
                                       dadd1=G("decoder_pos_emb.weight")[:geo.n])
     ctx["dd"] = dd
+    if model.has_enc_to_dec:
+        # enc_to_dec's parameter gradients belong to the FIRST all-reduce bucket (dp.DECODER_SIDE_PREFIXES), so they
+        # must be final when this phase ends; only the dgrad through it is left to the encoder phase
+        ops.colsum(dd, G("enc_to_dec.bias"))
+        wgrad(dd, ctx["enc_out"], G("enc_to_dec.weight"))
 
 
 def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
@@ -642,8 +667,6 @@ def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
     geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
     dd = ctx["dd"]
     if model.has_enc_to_dec:
-        ops.colsum(dd, G("enc_to_dec.bias"))
-        wgrad(dd, ctx["enc_out"], G("enc_to_dec.weight"))
         denc = ops.gemm(dd, A.bf_t("enc_to_dec.weight"))
     else:
         denc = dd

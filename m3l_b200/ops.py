@@ -44,7 +44,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None,
          alpha: float = 1.0, colsum_out: Optional[torch.Tensor] = None,
-         dot_side: Optional[torch.Tensor] = None, dot_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         dot_side: Optional[torch.Tensor] = None, dot_out: Optional[torch.Tensor] = None,
+         out2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[m, n] = epilogue(alpha * sum_k A[m, k] B[n, k]).
 
     mn_major=False: a is [M, K], b is [N, K] (nn.Linear forward: x @ W.T).
@@ -84,11 +85,52 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
     args.ld_aux = aux.stride(0) if aux is not None else 0
     args.alpha = alpha
     args.colsum_out = ptr(colsum_out)
+    if out2 is not None:
+        assert out2.dtype == torch.bfloat16 and out2.shape == out.shape and out2.stride() == out.stride()
+        args.out2 = ptr(out2)
     if dot_side is not None:
         assert dot_side.dtype == torch.bfloat16 and dot_side.stride(1) == 1 and dot_side.shape == (M, N)
         assert dot_out is not None and dot_out.dtype == torch.float32 and dot_out.is_contiguous() and dot_out.shape == (M, N // 64)
         args.dot_side, args.ld_dot, args.dot_out = ptr(dot_side), dot_side.stride(0), ptr(dot_out)
     check(_lib.load().m3l_gemm_bf16(C.byref(args), current_stream()), "m3l_gemm_bf16")
+    return out
+
+
+def ln_mlp_supported(dim: int, hidden: int) -> bool:
+    """Shapes the fused feed-forward block kernel is built for (csrc/rowblock.cu)."""
+    return dim == 256 and hidden % 128 == 0 and 128 <= hidden <= 1024
+
+
+def ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, *, save: bool = False, eps: float = 1e-5, out=None,
+               out_has_x: bool = False):
+    """out = x + W2 GELU(W1 LayerNorm(x) + b1) + b2 in one kernel (x bf16 [M, 256]; w1 [hidden, 256], w2 [256, hidden] bf16).
+    out=x updates the residual stream in place; out_has_x=True says `out` already holds a copy of x (gemm(out2=...)): in
+    both cases the block output is reduce-added to out and x is read once.
+    save=True additionally returns what the backward pass reads: (out, stats, xn, h, gelu_grad)."""
+    _req_cuda(x, gamma, beta, w1, b1, w2, b2, out)
+    M, D = x.shape
+    hidden = w1.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
+    assert w1.shape == (hidden, D) and w2.shape == (D, hidden) and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    if out is None:
+        assert not out_has_x
+        out = torch.empty_like(x)
+    assert out.shape == x.shape and out.dtype == torch.bfloat16 and out.is_contiguous()
+    a = _lib.LnMlpArgs()
+    a.x, a.rows, a.dim, a.hidden = ptr(x), M, D, hidden
+    a.gamma, a.beta, a.eps = ptr(gamma), ptr(beta), eps
+    a.w1, a.b1, a.w2, a.b2 = ptr(w1), ptr(b1), ptr(w2), ptr(b2)
+    a.out, a.out_has_x = ptr(out), int(out_has_x)
+    stats = xn = h = gp = None
+    if save:
+        stats = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+        xn = torch.empty_like(x)
+        h = torch.empty((M, hidden), dtype=torch.bfloat16, device=x.device)
+        gp = torch.empty_like(h)
+        a.stats, a.xn_out, a.h_out, a.gp_out = ptr(stats), ptr(xn), ptr(h), ptr(gp)
+    check(_lib.load().m3l_ln_mlp_fwd(C.byref(a), current_stream()), "m3l_ln_mlp_fwd")
+    if save:
+        return out, stats, xn, h, gp
     return out
 
 
@@ -338,16 +380,22 @@ def grad_sumsq(grads, state):
           "m3l_grad_sumsq")
 
 
-def optimizer_step_begin(state):
-    check(_lib.load().m3l_optimizer_step_begin(ptr(state), current_stream()), "m3l_optimizer_step_begin")
+OPT_STATE_DOUBLES = 8     # step, sumsq, total norm, 1 - beta1^t, sqrt(1 - beta2^t), spare
+
+
+def optimizer_step_begin(state, betas=(0.9, 0.999), hyper=None):
+    assert state.numel() >= 5 and state.dtype == torch.float64
+    check(_lib.load().m3l_optimizer_step_begin(ptr(state), C.c_float(betas[0]), C.c_float(betas[1]), ptr(hyper),
+                                               current_stream()), "m3l_optimizer_step_begin")
 
 
 def clip_adamw(params, grads, exp_avg, exp_avg_sq, state, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-               max_norm=0.5, write_clipped_grad=True):
+               max_norm=0.5, write_clipped_grad=True, hyper=None):
+    """hyper: optional device fp32 [6] = [lr, beta1, beta2, eps, weight_decay, max_norm] read at run time (graph replay)."""
     check(_lib.load().m3l_clip_adamw(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),
                                      C.c_size_t(params.numel()), ptr(state), C.c_float(lr), C.c_float(betas[0]),
                                      C.c_float(betas[1]), C.c_float(eps), C.c_float(weight_decay),
-                                     C.c_float(max_norm), int(write_clipped_grad), current_stream()),
+                                     C.c_float(max_norm), int(write_clipped_grad), ptr(hyper), current_stream()),
           "m3l_clip_adamw")
 
 

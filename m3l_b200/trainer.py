@@ -18,7 +18,13 @@ from ._lib import M3LError
 
 
 class FusedAdamW:
-    """Minimal optimizer facade (param_groups / state_dict) over the trainer's flat moment arenas."""
+    """Minimal optimizer facade (param_groups / state_dict) over the trainer's flat moment arenas.
+
+    Differences from torch.optim.AdamW, by construction of the flat-arena step: ONE step counter serves every
+    parameter (torch keeps one per parameter, which only differs for parameters that receive a gradient in some
+    steps and not in others, e.g. alternating use_tactile); zero_grad() always zero-fills (the gradient arena is a
+    persistent buffer, `set_to_none` is accepted and ignored).  lr / betas / eps / weight_decay may be changed
+    through param_groups at any time: they are read from a device buffer at run time, also under graph replay."""
 
     def __init__(self, trainer, lr, betas, eps, weight_decay):
         self._t = trainer
@@ -40,6 +46,8 @@ class FusedAdamW:
 
 
 class FusedTrainer:
+    _MAX_GRAPHS = 4      # captured (modalities, batch) shapes kept alive; oldest evicted first
+
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=0.5,
                  process_group=None, use_cuda_graph=True):
         self.model = model
@@ -48,7 +56,9 @@ class FusedTrainer:
         self.gflat = torch.zeros(A.total, dtype=torch.float32, device=dev)
         self.m = torch.zeros_like(self.gflat)
         self.v = torch.zeros_like(self.gflat)
-        self.state = torch.zeros(3, dtype=torch.float64, device=dev)  # step, sumsq, total norm
+        self.state = torch.zeros(ops.OPT_STATE_DOUBLES, dtype=torch.float64, device=dev)  # step, sumsq, norm, bias corrections
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)   # lr, beta1, beta2, eps, weight_decay, max_norm
+        self._hyper_host = None
         self.max_norm = max_norm
         self.pg = process_group
         self.world = 1
@@ -80,15 +90,26 @@ class FusedTrainer:
     def _phase_b(self, box):
         engine.mae_backward_encoder(self.model, box["ctx"], self.gflat)
 
+    def _push_hyper(self):
+        """Optimizer hyper-parameters -> device buffer (only when they changed): the kernels read them at run time,
+        so captured graphs follow param_groups (LR schedules) without re-capture."""
+        g = self.opt.param_groups[0]
+        vals = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                float(self.max_norm if self.max_norm is not None else 0.0))
+        if vals != self._hyper_host:
+            self.hyper[:6].copy_(torch.tensor(vals, dtype=torch.float32))
+            self._hyper_host = vals
+
     def _phase_c(self, ranges):
         A = self.model.arena
         g = self.opt.param_groups[0]
         for s, e in ranges:
             ops.grad_sumsq(self.gflat[s:e], self.state)
-        ops.optimizer_step_begin(self.state)
+        ops.optimizer_step_begin(self.state, g["betas"], hyper=self.hyper)
         for s, e in ranges:
             ops.clip_adamw(A.flat[s:e], self.gflat[s:e], self.m[s:e], self.v[s:e], self.state, lr=g["lr"],
-                           betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], max_norm=self.max_norm)
+                           betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], max_norm=self.max_norm,
+                           hyper=self.hyper)
         A.refresh_shadows()
 
     def _allreduce(self, ranges, after_event):
@@ -109,7 +130,7 @@ class FusedTrainer:
             p = A.params[k]
             if p.grad is None or p.grad.data_ptr() != A.view(self.gflat, k).data_ptr():
                 p.grad = A.view(self.gflat, k)
-        lr = self.opt.param_groups[0]["lr"]
+        self._push_hyper()
         if not self.use_graph:
             box = {}
             self._phase_a(xs, noise, geo, box)
@@ -124,9 +145,11 @@ class FusedTrainer:
             self._phase_c(ranges)
             A._version_seen = A.version()
             return box["loss"].reshape(())
-        key = (geo.use_vision, geo.nt, B, lr)
+        key = (geo.use_vision, geo.nt, B)
         g = self._graphs.get(key)
         if g is None:
+            while len(self._graphs) >= self._MAX_GRAPHS:       # each capture owns a full activation pool
+                self._graphs.pop(next(iter(self._graphs)))
             g = self._capture(xs, noise, geo, ranges)
             self._graphs[key] = g
         for k, v in xs.items():

@@ -52,7 +52,9 @@ def _worker(rank, world, port, out):
     lt = loss.detach().clone()
     dist.all_reduce(lt)
     if rank == 0:
-        out.put((order, flat, lt / world))
+        # plain numpy through the queue: a torch tensor would travel as a shared-memory file descriptor that the
+        # parent can only receive while this process is still alive (EOFError in recvfds otherwise)
+        out.put((order, flat.numpy().copy(), (lt / world).numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,6 +68,7 @@ def test_two_rank_gradient_average_equals_global_batch():
     for p in procs:
         p.start()
     order, flat, loss = out.get(timeout=240)
+    flat, loss = torch.from_numpy(flat), torch.from_numpy(loss)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -57,7 +57,7 @@ def test_single_thread_issue_sites_use_the_uniform_datapath(lib):
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not Path(cuobjdump).exists():
         pytest.skip("cuobjdump not available")
-    for name in ("gemm", "gemm_gelu", "attention"):
+    for name in ("gemm", "gemm_gelu", "attention", "rowblock"):
         obj = build.OBJ / f"{name}.o"
         assert obj.exists(), obj
         sass = subprocess.run([cuobjdump, "-sass", str(obj)], capture_output=True, text=True).stdout.splitlines()

@@ -56,6 +56,9 @@ def test_gemm_epilogues(ops):
     z = a.float() @ b.float().T
     out = ops.gemm(a, b, bias=bias, residual=res)
     assert rel_err(out, z + bias + res.float()) < 1e-2
+    twin = torch.zeros_like(out)
+    out_b = ops.gemm(a, b, bias=bias, residual=res, out2=twin)       # second copy of the output
+    assert torch.equal(out_b, out) and torch.equal(twin, out)
     dgelu = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     h = ops.gemm(a, b, bias=bias, act=ops.GELU_FWD, aux_out=dgelu)
     zz = (z + bias).requires_grad_(True)
@@ -122,6 +125,81 @@ def test_gemm_gelu_fwd_16_warp_kernel(ops, M, N, K):
 
 
 # ------------------------------------------------------------------------------- mask indices
+# The weight-stationary variants the benchmark shape (B = 256 per GPU) selects: gemm_bf16_kernel<256,0,0,0,1> (decoder
+# QKV, M = 49152), <256,0,0,3,1> / <128,0,0,3,1> (to_pixels / to_tactiles, fp32 epilogue, M = 15360 / 31232).
+@pytest.mark.parametrize("M,N,K,f32", [(49152, 768, 256, False), (15360, 768, 256, True), (31232, 192, 256, True),
+                                       (49152, 256, 256, False)])
+def test_gemm_weight_stationary_variants_at_bench_shape(ops, M, N, K, f32):
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) * 0.06).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    out = ops.gemm(a, b, bias=bias, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    ref = a.float() @ b.float().T + bias
+    assert rel_err(out, ref) < (1e-5 if f32 else 1e-2)
+    # every 128-row tile is right, not only the largest element
+    blk = (out.float() - ref).abs().reshape(M // 128, -1).amax(1)
+    assert blk.max().item() < (1e-4 if f32 else 6e-2) * ref.abs().max().item()
+
+
+def _ln_mlp_reference(x, gamma, beta, w1, b1, w2, b2):
+    """fp32 statement of x + W2 GELU(W1 LN(x) + b1) + b2 with the kernel's bf16 rounding points."""
+    xf = x.float()
+    mean = xf.mean(1, keepdim=True)
+    var = ((xf - mean) ** 2).mean(1, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    xn = ((xf - mean) * rstd * gamma + beta).bfloat16()
+    pre = (xn.float() @ w1.float().T + b1).requires_grad_(True)
+    hf = F.gelu(pre)
+    hf.sum().backward()
+    h = hf.detach().bfloat16()
+    out = xf + h.float() @ w2.float().T + b2
+    return out, torch.cat([mean, rstd], 1), xn, h, pre.grad
+
+
+@pytest.mark.parametrize("M,hidden", [(128, 128), (128, 1024), (777, 512), (2560, 512), (49152, 1024), (148 * 128 * 2 + 5, 256)])
+def test_ln_mlp_fused_block(ops, M, hidden):
+    torch.manual_seed(5)
+    D = 256
+    x = (torch.randn(M, D, device=DEV) * 1.5 + 0.3).bfloat16()
+    gamma = 1 + 0.2 * torch.randn(D, device=DEV)
+    beta = 0.1 * torch.randn(D, device=DEV)
+    w1 = (torch.randn(hidden, D, device=DEV) * 0.08).bfloat16()
+    b1 = 0.5 * torch.randn(hidden, device=DEV)
+    w2 = (torch.randn(D, hidden, device=DEV) * 0.05).bfloat16()
+    b2 = 0.3 * torch.randn(D, device=DEV)
+    ref_out, ref_stats, ref_xn, ref_h, ref_gp = _ln_mlp_reference(x, gamma, beta, w1, b1, w2, b2)
+    out = ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2)
+    assert rel_err(out, ref_out) < 1e-2
+    blk = (out.float() - ref_out).abs().amax(1)
+    assert blk.max().item() < 6e-2 * ref_out.abs().max().item()
+    out2, stats, xn, h, gp = ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, save=True)
+    assert rel_err(out2, ref_out) < 1e-2
+    assert rel_err(stats, ref_stats) < 1e-4
+    assert rel_err(xn, ref_xn) < 1e-2 and rel_err(h, ref_h) < 1e-2 and rel_err(gp, ref_gp) < 1e-2
+    # the two variants compute the same block
+    assert rel_err(out2, out) < 1e-2
+    # accumulate modes: in place on the residual stream, and into a buffer that already holds x (reduce-add epilogue)
+    xi = x.clone()
+    o3 = ops.ln_mlp_fwd(xi, gamma, beta, w1, b1, w2, b2, out=xi)
+    assert o3.data_ptr() == xi.data_ptr() and rel_err(xi, ref_out) < 1e-2
+    assert (xi.float() - ref_out).abs().amax(1).max().item() < 6e-2 * ref_out.abs().max().item()
+    buf = x.clone()
+    o4, stats4, xn4, h4, gp4 = ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, save=True, out=buf, out_has_x=True)
+    assert rel_err(o4, ref_out) < 1e-2 and torch.equal(stats4, stats) and torch.equal(xn4, xn)
+    assert torch.equal(h4, h) and torch.equal(gp4, gp)
+
+
+def test_ln_mlp_rejects_unsupported_shapes(ops):
+    from m3l_b200._lib import M3LError
+    x = torch.zeros(128, 384, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(M3LError):
+        ops.ln_mlp_fwd(x, torch.ones(384, device=DEV), torch.zeros(384, device=DEV),
+                       torch.zeros(768, 384, device=DEV, dtype=torch.bfloat16), torch.zeros(768, device=DEV),
+                       torch.zeros(384, 768, device=DEV, dtype=torch.bfloat16), torch.zeros(384, device=DEV))
+    assert not ops.ln_mlp_supported(384, 768) and ops.ln_mlp_supported(256, 1024)
+
+
 @pytest.mark.parametrize("B,segs", [(37, [(0, 64, 60), (64, 64, 61), (128, 64, 61)]), (5, [(0, 64, 60)]),
                                     (9, [(0, 25, 20), (25, 25, 20)]), (3, [(0, 300, 17)])])
 def test_mask_indices_bit_exact(ops, B, segs):
@@ -450,7 +528,7 @@ def test_clip_adamw_matches_torch(ops):
     p_ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.AdamW([p_ref], lr=1e-3)
     m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
-    state = torch.zeros(3, dtype=torch.float64, device=DEV)
+    state = torch.zeros(ops.OPT_STATE_DOUBLES, dtype=torch.float64, device=DEV)
     for it in range(3):
         g = torch.randn(n, device=DEV) * (3.0 if it < 2 else 1e-4)  # clip active, then inactive
         p_ref.grad = g.clone()
@@ -465,6 +543,19 @@ def test_clip_adamw_matches_torch(ops):
         assert rel_err(gg, p_ref.grad) < 1e-5
         assert rel_err(p, p_ref.data) < 1e-5
     assert state[0].item() == 3.0
+    # hyper-parameters read from a device buffer at run time (what a captured graph does) give the same step as scalars
+    hyper = torch.tensor([2e-3, 0.8, 0.95, 1e-7, 0.1, 0.25, 0, 0], device=DEV)
+    opt2 = torch.optim.AdamW([p_ref], lr=2e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.1)
+    opt2.load_state_dict({"state": opt.state_dict()["state"], "param_groups": opt2.state_dict()["param_groups"]})
+    g = torch.randn(n, device=DEV)
+    p_ref.grad = g.clone()
+    torch.nn.utils.clip_grad_norm_([p_ref], 0.25)
+    opt2.step()
+    state[1] = 0
+    ops.grad_sumsq(g, state)
+    ops.optimizer_step_begin(state, (0.0, 0.0), hyper=hyper)          # the scalar arguments are ignored
+    ops.clip_adamw(p, g, m, v, state, lr=123.0, max_norm=99.0, hyper=hyper)
+    assert rel_err(p, p_ref.data) < 1e-5 and state[0].item() == 4.0
 
 
 def test_cast_and_transpose(ops):

@@ -11,7 +11,7 @@ out.mkdir(parents=True, exist_ok=True)
 objs = []
 for src in B._sources():
     o = out / (src.stem + ".o")
-    cmd = [B.NVCC, *B.ARCH_FLAGS, *B.NVCC_FLAGS, *defs, "-c", str(src), "-o", str(o)]
+    cmd = [B.NVCC, *B.ARCH_FLAGS, *B.flags_for(src), *defs, "-c", str(src), "-o", str(o)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.exit(r.stderr)
