@@ -49,7 +49,7 @@ struct Cfg {
   static constexpr int kSlots = SAVE ? 3 : 4;
   static constexpr int kGeluStg = SAVE ? kGeluWarps * 2048 : 0;     // one 32 x 32 bf16 unit per GELU warp
   static constexpr int kSmem = 1024 + kABytes + kSlots * kSlotBytes + kRowWarps * 2 * kStgUnit + kGeluStg +
-                               kMaxHidden * 4 + 2 * kD * 4 + 512;
+                               kMaxHidden * 4 + 3 * kD * 4 + 512;
 };
 
 struct alignas(8) Bars {
@@ -80,6 +80,7 @@ struct Args {
   float* stats;          // [M, 2] or null
   int want_xn;           // store LN(x)
   int out_has_x;         // out already holds x (in place, or pre-copied): the block output is ADDED to it
+  bf16* out;
 };
 
 // ---- TS-mode product (A operand in TMEM: lane = row, bf16 pairs packed per 32-bit column) and TMEM stores
@@ -105,40 +106,40 @@ M3L_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
 }
 M3L_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ---- exact-erf GELU with ONE MUFU per element -------------------------------------------------------
-// Phi(x) = 1/2 + copysign(1/2, x) (1 - erfc(|x| / sqrt 2)),  erfc(z) = exp2(z P(z)):  z P(z) is the degree-7
-// weighted-minimax fit of log2(erfc(z)) on [0, 4.3] (|erfc error| <= 1.6e-7 in fp32, measured against scipy;
-// the Abramowitz-Stegun form used elsewhere needs a reciprocal as well).  Below the coefficients are those of
-// P in the variable a = min(|x|, 6.08) (the 1/sqrt(2) is folded in); beyond 6.08 Phi is 0 / 1 to fp32 precision.
-constexpr float kE1 = -1.627913732f * 0.70710678118654752f;
-constexpr float kE2 = -0.9183286465f * 0.5f;
-constexpr float kE3 = -0.1489636613f * 0.35355339059327376f;
-constexpr float kE4 = 0.0294525041f * 0.25f;
-constexpr float kE5 = -0.002302231466f * 0.17677669529663687f;
-constexpr float kE6 = -0.0004615745302f * 0.125f;
-constexpr float kE7 = 0.000100221133f * 0.08838834764831843f;
-constexpr float kClamp = 6.08f;
+// ---- exact-erf GELU with ONE MUFU and 8 packed FMA-pipe instructions per PAIR of elements ------------------
+//   GELU(x) = x Phi(x) = max(x, 0) - |x| * (erfc(|x| / sqrt 2) / 2)
+// erfc(z) / 2 = exp2(P(z)): P is the degree-6 weighted-minimax fit of log2(erfc(z) / 2) on [0, 4.3]
+// (|GELU error| <= 6e-7 in fp32 against scipy, relative accuracy kept in the negative tail; the Abramowitz-Stegun
+// form used by the unfused epilogues needs a reciprocal as well).  The polynomial is evaluated in the variable
+// na = max(-|x|, -6.08) (1/sqrt 2 and the sign folded into the coefficients); beyond 6.08 Phi is 0 / 1 in fp32.
+// The first version (Phi = 1/2 + copysign(1/2, x)(1 - erfc)) spent 13 packed FMA-pipe instructions per pair and the
+// 16 GELU warps needed 2400 clk per 128-column chunk against 2048 clk of tensor work.
+constexpr float kE1 = 1.1511168561f, kE2 = -4.5908273735e-01f, kE3 = 5.2926736750e-02f, kE4 = 7.7240424434e-03f,
+                kE5 = 6.4775743001e-04f, kE6 = 1.7755137836e-05f;
+constexpr float kClamp = -6.08f;
 
 // GELU(x) of two pre-activations (packed fp32 arithmetic); if WANT_GRAD also GELU'(x) = Phi(x) + x phi(x)
 template <bool WANT_GRAD>
 M3L_DEVINL void gelu2(uint32_t x0u, uint32_t x1u, f32x2& gelu, f32x2& dgelu) {
-  const f32x2 x = f2_packu(x0u, x1u);
-  const f32x2 a = f2_pack(fminf(fabsf(__uint_as_float(x0u)), kClamp), fminf(fabsf(__uint_as_float(x1u)), kClamp));
-  const f32x2 s = f2_packu((x0u & 0x80000000u) | 0x3f000000u, (x1u & 0x80000000u) | 0x3f000000u);   // copysign(0.5, x)
-  f32x2 t = f2_fma(f2_splat(kE7), a, f2_splat(kE6));
-  t = f2_fma(t, a, f2_splat(kE5));
-  t = f2_fma(t, a, f2_splat(kE4));
-  t = f2_fma(t, a, f2_splat(kE3));
-  t = f2_fma(t, a, f2_splat(kE2));
-  t = f2_fma(t, a, f2_splat(kE1));
-  const f32x2 pw = f2_mul(t, a);
+  const float x0 = __uint_as_float(x0u), x1 = __uint_as_float(x1u);
+  const f32x2 na = f2_pack(fmaxf(-fabsf(x0), kClamp), fmaxf(-fabsf(x1), kClamp));
+  const f32x2 relu = f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  f32x2 t = f2_fma(f2_splat(kE6), na, f2_splat(kE5));
+  t = f2_fma(t, na, f2_splat(kE4));
+  t = f2_fma(t, na, f2_splat(kE3));
+  t = f2_fma(t, na, f2_splat(kE2));
+  t = f2_fma(t, na, f2_splat(kE1));
+  const f32x2 pw = f2_fma(t, na, f2_splat(-1.0f));
   float p0, p1;
   f2_unpack(pw, p0, p1);
-  const f32x2 e = f2_pack(exp2f(p0), exp2f(p1));                     // erfc(|x| / sqrt 2), MUFU.EX2 x 2
-  const f32x2 om = f2_fma(e, f2_splat(-1.0f), f2_splat(1.0f));       // erf(|x| / sqrt 2)
-  const f32x2 cdf = f2_fma(s, om, f2_splat(0.5f));
-  gelu = f2_mul(x, cdf);
+  const f32x2 eh = f2_pack(exp2f(p0), exp2f(p1));                    // erfc(|x| / sqrt 2) / 2 = Phi(-|x|), MUFU.EX2 x 2
+  gelu = f2_fma(na, eh, relu);
   if (WANT_GRAD) {
+    // Phi(x) = x >= 0 ? 1 - eh : eh = c0 + sg * eh
+    const uint32_t c0a = (uint32_t)((int32_t)(~x0u) >> 31) & 0x3f800000u, c0b = (uint32_t)((int32_t)(~x1u) >> 31) & 0x3f800000u;
+    const f32x2 sg = f2_packu((x0u & 0x80000000u) ^ 0xbf800000u, (x1u & 0x80000000u) ^ 0xbf800000u);
+    const f32x2 cdf = f2_fma(sg, eh, f2_packu(c0a, c0b));
+    const f32x2 x = f2_packu(x0u, x1u);
     const f32x2 xx = f2_mul(f2_mul(x, x), f2_splat(-0.5f * 1.4426950408889634f));
     float q0, q1;
     f2_unpack(xx, q0, q1);
@@ -169,6 +170,11 @@ M3L_DEVINL void rb_store_unit(const CUtensorMap* map, uint32_t stg, int lane, co
 M3L_DEVINL uint4 rb_lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+M3L_DEVINL float4 rb_lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 M3L_DEVINL void rb_sts128(uint32_t addr, uint4 v) {
@@ -203,7 +209,12 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   float* s_b1 = reinterpret_cast<float*>(gelu_stg + C::kGeluStg);
   float* s_gamma = s_b1 + kMaxHidden;
   float* s_beta = s_gamma + kD;
-  Bars* bars = reinterpret_cast<Bars*>(s_beta + kD);
+  float* s_b2 = s_beta + kD;
+  Bars* bars = reinterpret_cast<Bars*>(s_b2 + kD);
+  // bias / LayerNorm parameters are READ through 32-bit shared-state-space addresses (ld.shared): through the float*
+  // above the compiler emits generic LD.E, which goes down the global-memory path of the LSU ("lg" throttle stalls)
+  const uint32_t s_b1_u32 = smem_u32(s_b1), s_gamma_u32 = smem_u32(s_gamma), s_beta_u32 = smem_u32(s_beta),
+                 s_b2_u32 = smem_u32(s_b2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + kBM - 1) / kBM;
@@ -250,6 +261,7 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (threadIdx.x < kD) {
     s_gamma[threadIdx.x] = p.gamma[threadIdx.x];
     s_beta[threadIdx.x] = p.beta[threadIdx.x];
+    s_b2[threadIdx.x] = p.b2[threadIdx.x];
   }
   __syncthreads();
   pdl_trigger();
@@ -387,7 +399,7 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       const int row0 = m0 + quad * 32;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 256;
       if (p.out_has_x) {
-        // ---- out += acc2 + b2 by TMA reduce-add (bf16): no residual fetch on the path that frees acc2
+        // ---- out += acc2 + b2 with bf16 vector reductions: no residual fetch on the path that frees acc2
         mbar_wait(&bars->acc2_full, i & 1);
         tc_fence_after_sync();
         if (rw == 0 && lane == 0) RB_EV(2, i * 4 + 2);
@@ -404,23 +416,20 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           uint32_t w[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + r * 32 + j));
+            const float4 b = rb_lds_f4(s_b2_u32 + (r * 32 + j) * 4);
             w[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y);
             w[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
           }
-          const uint32_t sb = stg + (g_round & 1) * kStgUnit;
-          if (elect_one()) tma_wait_group_read<1>();    // the reduce issued from this buffer two rounds ago has read it
-          __syncwarp();
+          // 16-byte bf16 reductions from registers (REDG.ADD.BF16x8): thread = row, 64 contiguous bytes per round.
+          // (Staging through shared memory + TMA reduce-add cost ~1000 clk per round here: the bulk group's
+          // "read done" comes back slowly and only two 2 KB buffers fit beside the weight ring.)
+          if (row0 + lane < p.M) {
+            bf16* dst = p.out + (size_t)(row0 + lane) * kD + r * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t addr = sb + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-            rb_sts128(addr, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (elect_one()) {
-            tma_reduce_add_2d(&map_out, sb, r * 32, row0);
-            tma_commit_group();
+            for (int j = 0; j < 4; ++j)
+              asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8 * j), "r"(w[4 * j]),
+                           "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                           : "memory");
           }
         }
         if (rw == 0 && lane == 0) RB_EV(2, i * 4 + 3);
@@ -453,7 +462,7 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + r * 32 + j));
+          const float4 b = rb_lds_f4(s_b2_u32 + (r * 32 + j) * 4);
           v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
           v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
           v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
@@ -496,65 +505,79 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int part = gw >> 2;                         // 32-column part of the 128-column chunk
     const uint32_t stg = smem_u32(gelu_stg + gw * 2048);
     const uint32_t a_u32 = smem_u32(a_tile);
-    // LayerNorm in place on the smem tile: warp gw owns rows gw*8 .. +8, EIGHT lanes per row (lane sub holds the
-    // 16-byte chunk `sub` of each of the row's four k-blocks = 32 values), so the two reductions are 3 shuffles each
-    // and four rows are in flight per instruction.  (The first version ran this on the 4 row warps, one row per warp
-    // instruction with 5 + 5 dependent shuffles: 10.5 k clk per tile, all of it a bubble in front of the first product.)
+    // LayerNorm in place on the smem tile: warp gw owns rows gw*8 .. +8; a lane holds ONE 16-byte chunk of a row
+    // (k-block lane >> 3, chunk lane & 7), so gamma / beta are 16 registers re-read once per tile, and four rows are
+    // in flight per iteration (one pass: sum and sum of squares, 5 butterfly stages for the eight partials).
+    // History: on the 4 row warps, one row at a time with 5 + 5 dependent shuffles, this took 10.5 k clk per tile; with
+    // 8 lanes per row (3-stage butterflies) 7 k clk, because every lane then re-read 64 gamma / beta floats per
+    // iteration: 4 k shared-memory wavefronts per tile, the LSU pipe was the limit.
     auto layer_norm_tile = [&](int i) {
       const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * kBM;
+      const int kb = lane >> 3, jc = lane & 7;
+      f32x2 gg[4], bb[4];
+      {
+        const float4 g0 = rb_lds_f4(s_gamma_u32 + (kb * 64 + jc * 8) * 4);
+        const float4 g1 = rb_lds_f4(s_gamma_u32 + (kb * 64 + jc * 8 + 4) * 4);
+        const float4 b0 = rb_lds_f4(s_beta_u32 + (kb * 64 + jc * 8) * 4);
+        const float4 b1 = rb_lds_f4(s_beta_u32 + (kb * 64 + jc * 8 + 4) * 4);
+        gg[0] = f2_pack(g0.x, g0.y); gg[1] = f2_pack(g0.z, g0.w); gg[2] = f2_pack(g1.x, g1.y); gg[3] = f2_pack(g1.z, g1.w);
+        bb[0] = f2_pack(b0.x, b0.y); bb[1] = f2_pack(b0.z, b0.w); bb[2] = f2_pack(b1.x, b1.y); bb[3] = f2_pack(b1.z, b1.w);
+      }
       mbar_wait(&bars->a_loaded, i & 1);
       if (gw == 0 && lane == 0) RB_EV(2, i * 4);
-      const int sub = lane & 7;
 #pragma unroll 1
       for (int it = 0; it < 2; ++it) {
-        const int row = gw * 8 + it * 4 + (lane >> 3);
-        const uint32_t base = a_u32 + row * 128 + ((sub ^ (row & 7)) << 4);
-        // one pass over the row: sum and sum of squares in packed fp32 (bf16 inputs, fp32 accumulation over 256
-        // values: var = E[x^2] - mean^2 loses ~mean^2 / var ulps, far below the bf16 output rounding), then
-        // y = (x * rstd - mean * rstd) * gamma + beta as two packed FMAs per pair
+        const int r0 = gw * 8 + it * 4;
+        uint32_t addr[4];
         f32x2 v[4][4];
-        f32x2 s2 = f2_splat(0.f), q2 = f2_splat(0.f);
+        float sum[4], sq[4];
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint4 u = rb_lds128(base + kb * kKbBytes);
+        for (int rr = 0; rr < 4; ++rr) {
+          const int row = r0 + rr;
+          addr[rr] = a_u32 + kb * kKbBytes + row * 128 + ((jc ^ (row & 7)) << 4);
+          const uint4 u = rb_lds128(addr[rr]);
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          f32x2 s2 = f2_splat(0.f), q2 = f2_splat(0.f);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[kb][e] = f2_packu(w[e] << 16, w[e] & 0xffff0000u);      // bf16 pair -> fp32 pair (exact)
-            s2 = f2_add(s2, v[kb][e]);
-            q2 = f2_fma(v[kb][e], v[kb][e], q2);
+            v[rr][e] = f2_packu(w[e] << 16, w[e] & 0xffff0000u);      // bf16 pair -> fp32 pair (exact)
+            s2 = f2_add(s2, v[rr][e]);
+            q2 = f2_fma(v[rr][e], v[rr][e], q2);
+          }
+          float sa, sb, qa, qb;
+          f2_unpack(s2, sa, sb);
+          f2_unpack(q2, qa, qb);
+          sum[rr] = sa + sb;
+          sq[rr] = qa + qb;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            sum[rr] += __shfl_xor_sync(0xffffffffu, sum[rr], o);
+            sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
           }
         }
-        float sa, sb, qa, qb;
-        f2_unpack(s2, sa, sb);
-        f2_unpack(q2, qa, qb);
-        float sum = sa + sb, sq = qa + qb;
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4); sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float mean = sum * (1.0f / kD);
-        const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / kD)), 0.f);
-        const float rstd = rsqrtf(var + p.eps);
-        if (p.stats != nullptr && sub == 0 && m0 + row < p.M)
-          *reinterpret_cast<float2*>(p.stats + 2 * (size_t)(m0 + row)) = make_float2(mean, rstd);
-        const f32x2 r2 = f2_splat(rstd), nm2 = f2_splat(-mean * rstd);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + kb * 64 + sub * 8);
-          const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + kb * 64 + sub * 8 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(s_beta + kb * 64 + sub * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_beta + kb * 64 + sub * 8 + 4);
-          const f32x2 gg[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
-          const f32x2 bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+        for (int rr = 0; rr < 4; ++rr) {
+          const int row = r0 + rr;
+          const float mean = sum[rr] * (1.0f / kD);
+          // var = E[x^2] - mean^2 (bf16 inputs, fp32 sums over 256 values: the cancellation costs ~mean^2 / var ulps,
+          // far below the bf16 rounding of the output)
+          const float var = fmaxf(fmaf(-mean, mean, sq[rr] * (1.0f / kD)), 0.f);
+          const float rstd = rsqrtf(var + p.eps);
+          if (p.stats != nullptr && lane == 0 && m0 + row < p.M)
+            *reinterpret_cast<float2*>(p.stats + 2 * (size_t)(m0 + row)) = make_float2(mean, rstd);
+          const f32x2 r2 = f2_splat(rstd), nm2 = f2_splat(-mean * rstd);
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const f32x2 y = f2_fma(f2_fma(v[kb][e], r2, nm2), gg[e], bb[e]);
+            const f32x2 y = f2_fma(f2_fma(v[rr][e], r2, nm2), gg[e], bb[e]);
             float y0, y1;
             f2_unpack(y, y0, y1);
             o[e] = pack_bf16x2(y0, y1);
           }
-          rb_sts128(base + kb * kKbBytes, make_uint4(o[0], o[1], o[2], o[3]));
+          rb_sts128(addr[rr], make_uint4(o[0], o[1], o[2], o[3]));
         }
       }
       fence_proxy_async_smem();       // the normalised rows are read by tcgen05.mma / TMA (async proxy)
@@ -590,22 +613,26 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         if (gw == 0 && lane == 0) RB_EV(3, k * 4 + 1);
-        const float* bias = s_b1 + pc * kCH + part * 32;
+        const uint32_t bias = s_b1_u32 + (pc * kCH + part * 32) * 4;
         uint32_t hp[16], gp[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 b2 = *reinterpret_cast<const float2*>(bias + 2 * j);
-          const f32x2 x = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_pack(b2.x, b2.y));
+        for (int j = 0; j < 16; j += 2) {
+          const float4 b4 = rb_lds_f4(bias + 8 * j);      // all lanes read the same address: one broadcast wavefront
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+          const int j2 = j + jj;
+          const f32x2 x = f2_add(f2_packu(v[2 * j2], v[2 * j2 + 1]), jj == 0 ? f2_pack(b4.x, b4.y) : f2_pack(b4.z, b4.w));
           uint32_t x0, x1;
           f2_unpacku(x, x0, x1);
           f32x2 hh, gg;
           gelu2<SAVE>(x0, x1, hh, gg);
           float a0, a1;
           f2_unpack(hh, a0, a1);
-          hp[j] = pack_bf16x2(a0, a1);
+          hp[j2] = pack_bf16x2(a0, a1);
           if (SAVE) {
             f2_unpack(gg, a0, a1);
-            gp[j] = pack_bf16x2(a0, a1);
+            gp[j2] = pack_bf16x2(a0, a1);
+          }
           }
         }
         // hidden chunk -> TMEM, over the accumulator columns this warp has just read: column part*32 + j holds
@@ -661,6 +688,7 @@ int launch(const m3l_ln_mlp_args* a, cudaStream_t stream) {
   p.b1 = a->b1; p.b2 = a->b2;
   p.stats = a->stats;
   p.want_xn = a->xn_out != nullptr ? 1 : 0;
+  p.out = (bf16*)a->out;
   p.out_has_x = (a->out == a->x || a->out_has_x) ? 1 : 0;
   auto kern = ln_mlp_fwd_kernel<SAVE>;
   static bool configured = false;
