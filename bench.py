@@ -100,6 +100,23 @@ def build_model(device):
     return mae.to(device)
 
 
+def synth_obs(B, seed, pinned=True, u8_frames=False):
+    """One rollout-buffer batch as the reference's learners hold it (ppo_mae.py:236-262): image frames
+    [B, F, 64, 64, 3] in [0, 1] and tactile maps [B, F, 6, 32, 32] in [-1, 1], fp32 (u8_frames: the compact storage
+    variant, uint8 frames scaled by 1/255 on the device), plus the mask noise."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, 4, 64, 64, 3, generator=g)
+    if u8_frames:
+        img = (img * 255).to(torch.uint8)
+    obs = {"image": img, "tactile": torch.rand(B, 4, 6, 32, 32, generator=g) * 2 - 1}
+    noise = torch.rand(B, 192, generator=g)
+    if pinned:
+        obs = {k: v.pin_memory() for k, v in obs.items()}
+        noise = noise.pin_memory()
+    return obs, noise
+
+
 def synth_batch(B, seed, pinned=False):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -170,33 +187,114 @@ def time_kernel(fn, iters=10):
     return s.elapsed_time(e) / iters * 1e-3  # seconds
 
 
-def dominant_kernel_roofline(peaks):
-    """Live CUDA-event timing of the dominant kernel (the tcgen05 GEMM on the decoder feed-forward
-    shape M=49152, N=1024, K=256: 25.8 GFLOP per launch) on the current stream."""
+def _flush_l2():
     import torch
-    from m3l_b200 import ops
-    M, N, K = BATCH_PER_GPU * 192, 1024, 256
-    a = torch.randn(M, K, device="cuda").bfloat16()
-    b = torch.randn(N, K, device="cuda").bfloat16()
-    bias = torch.randn(N, device="cuda")
-    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    pre = torch.empty_like(out)
-    sec = time_kernel(lambda: ops.gemm(a, b, out=out, bias=bias, act=ops.GELU_FWD, aux_out=pre))
-    flops = 2.0 * M * N * K
-    # algorithmic HBM bytes per launch: A (M x K bf16) + W (N x K bf16) + bias + the two bf16 outputs
-    # (GELU(pre) and GELU'(pre), both M x N) = 227.0 MB -> 113.8 flop/B, below the ridge (burst 1684 TF/s /
-    # 6460 GB/s = 261 flop/B): the kernel's binding roofline is HBM; the tensor-pipe view is kept beside it.
-    bytes_alg = 2.0 * M * K + 2.0 * N * K + 4.0 * N + 2 * 2.0 * M * N
-    gbs = bytes_alg / sec / 1e9
-    return {"bound": "hbm", "kernel": "gemm_gelu16_kernel decoder FF1 (M=49152,N=1024,K=256,+bias, writes GELU and GELU')",
-            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
-            # profiles/r01_ncu_full_gemm_v4.txt (gemm_gelu16_kernel: 25.72 MB read + 147.36 MB written; the rest of the
-            # 201 MB of outputs was still dirty in the 126 MB L2 when the kernel ended)
-            "traffic": 173.1e6, "algorithmic_bytes": bytes_alg, "us_per_launch": sec * 1e6,
-            "peak_source": peaks["source"] + ", burst",
-            "tensor_view": {"achieved": flops / sec / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                            "frac": flops / sec / 1e12 / peaks["tf_burst"], "flop_per_byte": flops / bytes_alg}}
+    global _FLUSH
+    try:
+        _FLUSH.zero_()
+    except NameError:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        _FLUSH.zero_()
+
+
+def time_kernel_cold(fn, iters=8):
+    """Median CUDA-event time of one launch with the L2 flushed (256 MB write) before every launch."""
+    import torch
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(iters):
+        _flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r02_ncu_top_kernels.txt); None where no capture of that kernel is committed
+NCU_TRAFFIC = {}
+try:
+    NCU_TRAFFIC = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text())
+except Exception:
+    pass
+
+
+def per_kernel_roofline(peaks, ms_per_step):
+    """Live CUDA-event timings (L2 flushed before every launch) of the kernels that make up most of the step, each at
+    its benchmark shape (B = 256: M = 49152 decoder rows), against the roofline SURVEY.md section 8(d) assigns: the
+    tensor pipe (measured burst bf16 peak) for every dense contraction, HBM for gather / norm / loss / optimizer
+    kernels.  `launches` = launches of that shape per step; share = launches * us / step time.  The entries are sorted
+    by share; `roofline` in the JSON line is the first one."""
+    import torch
+    from m3l_b200 import ops, engine
+    dev = "cuda"
+    B, n, D, H, heads = BATCH_PER_GPU, 192, 256, 1024, 4
+    M = B * n
+    bf = lambda *shape: (torch.randn(*shape, device=dev) * 0.5).bfloat16()
+    x, dy = bf(M, D), bf(M, D)
+    h, dh = bf(M, H), bf(M, H)
+    w1, w2 = bf(H, D) * 0.1, bf(D, H) * 0.1
+    wqkv, wo = bf(3 * D, D) * 0.1, bf(D, D) * 0.1
+    qkv = bf(M, 3 * D)
+    gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    b1, b2 = torch.zeros(H, device=dev), torch.zeros(D, device=dev)
+    gW = torch.zeros(H, D, device=dev)
+    gW2 = torch.zeros(D, H, device=dev)
+    gQ = torch.zeros(3 * D, D, device=dev)
+    o, lse = ops.attention_fwd(qkv, B, n, heads, 64, 0.125)
+    delta = torch.zeros(M, heads, device=dev)
+    st = torch.zeros(M, 2, device=dev); st[:, 1] = 1
+    xo = x.clone()
+    tf, hb = peaks["tf_burst"], peaks["hbm_gbs"]
+    rows = []
+
+    def add(name, fn, launches, flops=None, nbytes=None, key=None):
+        sec = time_kernel_cold(fn)
+        ent = {"kernel": name, "us_per_launch": sec * 1e6, "launches_per_step": launches,
+               "us_per_step": sec * 1e6 * launches, "share_of_step": sec * 1e3 * launches / ms_per_step}
+        if flops is not None:
+            ent.update(bound="tensor", achieved=flops / sec / 1e12, peak=tf, unit="TFLOP/s", frac=flops / sec / 1e12 / tf,
+                       algorithmic_flop=flops)
+        else:
+            ent.update(bound="hbm", achieved=nbytes / sec / 1e9, peak=hb, unit="GB/s", frac=nbytes / sec / 1e9 / hb,
+                       algorithmic_bytes=nbytes)
+        ent["traffic"] = NCU_TRAFFIC.get(key or name.split()[0])
+        rows.append(ent)
+
+    # weight gradients of the decoder feed-forward (dW[1024,256] = dpre^T xn and dW[256,1024] = dx^T h): 6 per step
+    add("gemm_bf16_kernel<256,1,1,4,0> wgrad dW1 = dpre^T[1024 x 49152] xn[49152 x 256]", lambda: engine.wgrad(dh, x, gW), 3,
+        flops=2.0 * M * H * D, key="wgrad_ff")
+    add("gemm_bf16_kernel<256,1,1,4,0> wgrad dW2 = dx^T[256 x 49152] h[49152 x 1024]", lambda: engine.wgrad(dy, h, gW2), 3,
+        flops=2.0 * M * H * D, key="wgrad_ff2")
+    add("gemm_bf16_kernel<256,1,1,4,0> wgrad dWqkv = dqkv^T[768 x 49152] xn[49152 x 256]", lambda: engine.wgrad(qkv, x, gQ), 3,
+        flops=2.0 * M * 3 * D * D, key="wgrad_qkv")
+    add("ln_mlp_fwd_kernel<1> fused LayerNorm+FF1+GELU+FF2+residual (training: stores h, GELU')",
+        lambda: ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, save=True, out=xo, out_has_x=True), 3,
+        flops=4.0 * M * H * D, key="ln_mlp_fwd_save")
+    add("attn_bwd_kernel (B=256, n=192, 4 heads x 64)",
+        lambda: ops.attention_bwd(qkv, o, dy, lse, B, n, heads, 64, 0.125, delta=delta), 3,
+        flops=10.0 * n * n * 64 * B * heads, key="attn_bwd")
+    add("attn_fwd_kernel (B=256, n=192, 4 heads x 64)", lambda: ops.attention_fwd(qkv, B, n, heads, 64, 0.125), 3,
+        flops=4.0 * n * n * 64 * B * heads, key="attn_fwd")
+    gp = h.clone()
+    add("gemm_bf16_kernel<256,0,0,2,0> dgrad dpre = (dx W2) * GELU' [49152 x 1024, K=256]",
+        lambda: ops.gemm(dy, w2.t().contiguous(), act=ops.GELU_BWD, aux_in=gp), 3, flops=2.0 * M * H * D, key="dgrad_ff2")
+    w1t = w1.t().contiguous()
+    add("gemm_bf16_kernel<256,0,0,0,0> dgrad dxn = dpre W1 [49152 x 256, K=1024]", lambda: ops.gemm(dh, w1t), 3,
+        flops=2.0 * M * H * D, key="dgrad_ff1")
+    add("gemm_bf16_kernel<256,0,0,0,1> QKV projection [49152 x 768, K=256]", lambda: ops.gemm(x, wqkv), 3,
+        flops=2.0 * M * 3 * D * D, key="qkv_fwd")
+    add("gemm_bf16_kernel<256,0,0,0,0> attention out-projection + residual [49152 x 256, K=256]",
+        lambda: ops.gemm(x, wo, bias=b2, residual=dy), 3, flops=2.0 * M * D * D, key="out_proj")
+    add("ln_bwd_pipe_kernel LayerNorm backward + residual-gradient add [49152 x 256]",
+        lambda: ops.layernorm_bwd(dy, x, st, gamma, skip=dy), 6, nbytes=4.0 * M * D * 2 + M * 8, key="ln_bwd")
+    add("ln_fwd_pipe_kernel LayerNorm forward [49152 x 256]", lambda: ops.layernorm_fwd(x, gamma, beta), 3,
+        nbytes=2.0 * M * D * 2 + M * 8, key="ln_fwd")
+    rows.sort(key=lambda r: -r["share_of_step"])
+    return rows
 
 
 def run_gpu_arm(args):
@@ -259,76 +357,121 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    # ---- end to end: pinned host inputs, H2D every step (prefetched one step ahead on a copy
-    #      stream), D2H read of the loss every step ------------------------------------------
-    copy_stream = torch.cuda.Stream()
-    stage = [({k: torch.empty_like(v, device=dev) for k, v in host[0][0].items()}, torch.empty(B, 192, device=dev))
-             for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---- sustained: the same loop for >= args.sustain_seconds (the 20-step figure above is a burst of ~50 ms)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / ms_per_step) + 1)
+        barrier()
+        with ClockSampler(local) as clocks_sus:
+            s.record()
+            for i in range(n_sus):
+                x, n = devb[i % nbuf]
+                trainer.step(x, noise=n)
+            e.record()
+            barrier()
+        t = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sustained = {"steps": n_sus, "seconds": float(t.item()) * 1e-3, "ms_per_step": float(t.item()) / n_sus,
+                     "value": B * world * n_sus / (float(t.item()) * 1e-3), "clocks": clocks_sus.summary()}
 
-    def prefetch(i):
-        slot = i % 2
-        x, n = host[i % nbuf]
-        copy_stream.wait_event(consumed[slot])
-        with torch.cuda.stream(copy_stream):
-            for k, v in x.items():
-                stage[slot][0][k].copy_(v, non_blocking=True)
-            stage[slot][1].copy_(n, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    for ev in consumed:
-        ev.record()
-    h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4
-    e2e_steps = args.steps
-    # H2D alone (reported next to e2e: the floor the PCIe link sets for a step)
-    barrier()
-    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    hs.record(copy_stream)
-    for i in range(4):
-        prefetch(i)
-        consumed[i % 2].record(copy_stream)
-    he.record(copy_stream)
-    barrier()
-    h2d_ms = hs.elapsed_time(he) / 4
-    for ev in consumed:
-        ev.record()
-    # every step's loss is copied D2H into pinned memory on the compute stream and READ by the host one
-    # step later (after its event), so the host never drains the GPU queue; all K losses are read
-    # inside the timed region
-    loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
-    loss_ev = [torch.cuda.Event() for _ in range(e2e_steps)]
-    barrier()
-    t0 = time.perf_counter()
-    s.record()
-    prefetch(0)
-    losses = []
-    for i in range(e2e_steps):
-        slot = i % 2
-        if i + 1 < e2e_steps:
-            prefetch(i + 1)
-        torch.cuda.current_stream().wait_event(ready[slot])
-        l = trainer.step(stage[slot][0], noise=stage[slot][1])
-        consumed[slot].record()
-        loss_host[i:i + 1].copy_(l.reshape(1), non_blocking=True)     # D2H of the step result
-        loss_ev[i].record()
-        if i > 0:
-            loss_ev[i - 1].synchronize()
-            losses.append(float(loss_host[i - 1]))
-    loss_ev[e2e_steps - 1].synchronize()
-    losses.append(float(loss_host[e2e_steps - 1]))
-    e.record()
-    barrier()
-    assert len(losses) == e2e_steps and all(x == x for x in losses)
-    ms_e2e = s.elapsed_time(e)
-    t = torch.tensor([ms_e2e], device=dev)
+    # ---- replicas: after the timed loops every rank must hold bit-identical parameters
+    replicas_identical = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * e2e_steps / (float(t.item()) * 1e-3)
-    wall_e2e = time.perf_counter() - t0
+        flat = mae.arena.flat
+        chk = torch.stack([flat.view(torch.int32).to(torch.int64).sum(), (flat.view(torch.int32).to(torch.int64) ** 2 % 1000003).sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = all(torch.equal(c, allc[0]) for c in allc)
+
+    # ---- end to end through the reference-facing call: a pinned HOST rollout batch (raw observations, as the
+    #      reference's learners hold them) -> H2D every step (prefetched one step ahead on a copy stream) ->
+    #      vt_load (lazy: fused into the patch-gather kernels) -> train step -> D2H read of the loss every step
+    from m3l_b200.data import vt_load_lazy
+    copy_stream = torch.cuda.Stream()
+
+    def e2e_run(u8_frames):
+        hostb = [synth_obs(B, 4321 + rank * 100 + i, pinned=True, u8_frames=u8_frames) for i in range(nbuf)]
+        stage = [({k: torch.empty_like(v, device=dev) for k, v in hostb[0][0].items()}, torch.empty(B, 192, device=dev))
+                 for _ in range(2)]
+        views = [vt_load_lazy(st[0], frame_stack=4) for st in stage]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            slot = i % 2
+            x, n = hostb[i % nbuf]
+            copy_stream.wait_event(consumed[slot])
+            with torch.cuda.stream(copy_stream):
+                for k, v in x.items():
+                    stage[slot][0][k].copy_(v, non_blocking=True)
+                stage[slot][1].copy_(n, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        for ev in consumed:
+            ev.record()
+        h2d = sum(v.numel() * v.element_size() for v in hostb[0][0].values()) + hostb[0][1].numel() * 4
+        # H2D alone (reported next to e2e: the floor the PCIe link sets for a step)
+        barrier()
+        hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hs.record(copy_stream)
+        for i in range(4):
+            prefetch(i)
+            consumed[i % 2].record(copy_stream)
+        he.record(copy_stream)
+        barrier()
+        h2d_ms = hs.elapsed_time(he) / 4
+        for ev in consumed:
+            ev.record()
+        for i in range(2):                                 # graph capture for this input form happens outside the timing
+            prefetch(i)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            trainer.step(views[i % 2], noise=stage[i % 2][1])
+            consumed[i % 2].record()
+        # every step's loss is copied D2H into pinned memory on the compute stream and READ by the host one
+        # step later (after its event), so the host never drains the GPU queue; all K losses are read
+        # inside the timed region
+        k_steps = args.steps
+        loss_host = torch.empty(k_steps, dtype=torch.float32).pin_memory()
+        loss_ev = [torch.cuda.Event() for _ in range(k_steps)]
+        barrier()
+        t0 = time.perf_counter()
+        s.record()
+        prefetch(0)
+        losses = []
+        for i in range(k_steps):
+            slot = i % 2
+            if i + 1 < k_steps:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            l = trainer.step(views[slot], noise=stage[slot][1])
+            consumed[slot].record()
+            loss_host[i:i + 1].copy_(l.reshape(1), non_blocking=True)     # D2H of the step result
+            loss_ev[i].record()
+            if i > 0:
+                loss_ev[i - 1].synchronize()
+                losses.append(float(loss_host[i - 1]))
+        loss_ev[k_steps - 1].synchronize()
+        losses.append(float(loss_host[k_steps - 1]))
+        e.record()
+        barrier()
+        assert len(losses) == k_steps and all(x == x for x in losses)
+        t = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"value": B * world * k_steps / (float(t.item()) * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "h2d_ms_per_step_alone": h2d_ms, "wall_s": time.perf_counter() - t0}
+
+    e2e = e2e_run(False)
+    e2e["note"] = ("pinned host rollout batch (raw fp32 observations: image [B,4,64,64,3], tactile [B,4,6,32,32]) -> H2D "
+                   "prefetched one step ahead on a copy stream -> vt_load fused into the patch-gather kernels -> train step; "
+                   "every step's loss copied D2H to pinned memory and read by the host one step later")
+    e2e_u8 = e2e_run(True)
+    e2e_u8["note"] = "same, with the image frames stored as uint8 in the host buffer (scaled by 1/255 inside the gather kernels)"
 
     if rank == 0:
-        roof = dominant_kernel_roofline(peaks)
+        table = per_kernel_roofline(peaks, ms_per_step)
+        roof = dict(table[0], peak_source=peaks["source"] + ", burst (kernel timed alone, L2 flushed)")
         step_tflops = value / world * FLOPS_PER_SAMPLE / 1e12
         # CPU baseline: rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1; the driver's reference arm times it)
         cpu_sps, cpu_ms, cores = cpu_reference_run(steps=30, warmup=3) if world == 1 else (None, None, None)
@@ -342,17 +485,20 @@ def run_gpu_arm(args):
                              "activations through HBM, far above the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(trainer.use_graph), "loss_last_step": loss_val},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "note": "pinned host batch -> H2D prefetched one step ahead on a copy stream; every step's loss "
-                            "copied D2H to pinned memory and read by the host one step later",
-                    "h2d_ms_per_step_alone": h2d_ms, "wall_s": wall_e2e},
+            "e2e": e2e,
+            "e2e_uint8_frames": e2e_u8,
+            "sustained": sustained,
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "roofline": roof,
+            "per_kernel": [{k: r[k] for k in ("kernel", "us_per_launch", "launches_per_step", "us_per_step", "share_of_step",
+                                                "bound", "achieved", "peak", "unit", "frac", "traffic")} for r in table],
             "step_tensor_utilisation": {"achieved": step_tflops, "unit": "TFLOP/s (3404.7 MFLOP/sample x samples/s/GPU)",
                                         "peak": peaks["tf_sustained"], "frac": step_tflops / peaks["tf_sustained"],
                                         "peak_source": peaks["source"] + ", sustained"},
         }
+        if replicas_identical is not None:
+            line["replicas_identical"] = replicas_identical
         if cpu_sps is not None:
             line["cpu_baseline"] = {"value": cpu_sps, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"batch 32 slice of the workload, fp32 torch CPU oracle, 30 timed steps, "
@@ -371,6 +517,8 @@ def main():
     ap.add_argument("--impl", default="m3l_b200", choices=["m3l_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly (for ncu launch lists)")
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (no e2e / CPU baseline legs)")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0,
+                    help="also time the device-resident loop for at least this long (0 disables)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

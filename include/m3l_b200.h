@@ -127,9 +127,24 @@ int m3l_mask_indices(const float* noise, int batch, int n_total, const m3l_mask_
  * (pretrain_models.py:768,775); token_base = global index of the modality's first token.
  * ---------------------------------------------------------------------------------------- */
 typedef struct m3l_patch_source {
-  const float* src[4];
+  const void* src[4]; /* layout 0: fp32 [batch, channels, height, width] maps, one per sensor.
+                         layout 1: base pointer of each sensor's first element in the RAW observation tensor */
   int32_t channels, height, width, patch_h, patch_w;
   int32_t token_base;
+  /* layout 1 fuses utils/pretrain_utils.py:7-57 (vt_load: NHWC -> NCHW, per-sensor channel de-interleave,
+   * (x - lo) / (hi - lo)) and the 5-D frame-stack reshape (models/pretrain_models.py:823-827, ppo_mae.py:236-242)
+   * into the patch loads: map element (b, c, y, x) with c = f * chan_group + ch is read from
+   *     src[s][b*stride_b + f*stride_f + ch*stride_ch + y*stride_y + x*stride_x]        (strides in elements)
+   * and normalised as (raw - norm_lo) / norm_span in fp32; dtype 1 = uint8 frames, raw = value / 255 first.
+   * E.g. images [B, F, H, W, 3]: chan_group 3, stride_f H*W*3, stride_ch 1, stride_y W*3, stride_x 3;
+   * tactile [B, F, 3*sensors, h, w], sensor s: src[s] = base + 3*s*h*w, chan_group 3, stride_f 3*sensors*h*w,
+   * stride_ch h*w, stride_y w, stride_x 1, norm_lo -1, norm_span 2. */
+  int32_t layout;     /* 0 or 1 */
+  int32_t dtype;      /* layout 1: 0 fp32, 1 uint8 */
+  int64_t stride_b;
+  int32_t chan_group;
+  int32_t stride_f, stride_ch, stride_y, stride_x;
+  float norm_lo, norm_span;
 } m3l_patch_source;
 
 /* Fused patchify + row gather + LayerNorm(patch_dim) -> bf16 rows [batch*ncols, P]
@@ -186,6 +201,11 @@ int m3l_rowclass_sum(const void* dx_bf16, int batch, int n_visible, int dim,
 int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0,
                  int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
                  float* dpred_colsum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* vt_load as a kernel of its own (utils/pretrain_utils.py:7-57): raw observation (layout 1 source) of sensor
+ * `sensor` -> fp32 [batch, channels, height, width] contiguous, for callers that need the maps materialised
+ * (the EarlyCNN conv stem, reconstruct()); the masked-autoencoder step itself reads raw observations directly. */
+int m3l_vt_load(const m3l_patch_source* src, int batch, int sensor, float* out_nchw, void* stream);
 
 /* out[n] += sum_m x[m, n] (bias gradients). */
 int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);

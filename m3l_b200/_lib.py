@@ -95,7 +95,11 @@ class MaskSegments(C.Structure):
 class PatchSource(C.Structure):
     _fields_ = [("src", C.c_void_p * 4), ("channels", C.c_int32), ("height", C.c_int32),
                 ("width", C.c_int32), ("patch_h", C.c_int32), ("patch_w", C.c_int32),
-                ("token_base", C.c_int32)]
+                ("token_base", C.c_int32),
+                # layout 1: raw-observation addressing (vt_load fused into the patch loads; include/m3l_b200.h)
+                ("layout", C.c_int32), ("dtype", C.c_int32), ("stride_b", C.c_int64), ("chan_group", C.c_int32),
+                ("stride_f", C.c_int32), ("stride_ch", C.c_int32), ("stride_y", C.c_int32), ("stride_x", C.c_int32),
+                ("norm_lo", C.c_float), ("norm_span", C.c_float)]
 
 
 class MatrixDesc(C.Structure):
@@ -110,5 +114,5 @@ EXPORTED_SYMBOLS = (
     "m3l_mse_loss", "m3l_colsum", "m3l_ln_param_grad", "m3l_attention_fwd", "m3l_attention_bwd",
     "m3l_grad_sumsq", "m3l_optimizer_step_begin", "m3l_clip_adamw", "m3l_cast_bf16",
     "m3l_transpose_cast_bf16", "m3l_token_mean_fwd", "m3l_token_mean_bwd",
-    "m3l_im2col", "m3l_col2im_relu", "m3l_token_finish", "m3l_token_finish_bwd",
+    "m3l_im2col", "m3l_col2im_relu", "m3l_token_finish", "m3l_token_finish_bwd", "m3l_vt_load",
 )

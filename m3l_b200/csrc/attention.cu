@@ -720,10 +720,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
           const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
           const bool cols_any = key0 < n;
+          // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
+          // wait: behind it the LDL latency sat on the producers' critical path (r01_ncu_attention_hot_lines_v5.txt)
+          const float dl = delta[i], lg = l2[i] * kLog2e;
           mbar_wait(&bars->sdp_full, g & 1);
           tc_fence_after_sync();
           PF(1)
-          const float dl = delta[i], lg = l2[i] * kLog2e;
           // P / dS of this thread's (row, 64-key half): TMEM -> registers first, so that the S / dP
           // columns can be handed back to the tensor core (next step's products) before the math
           uint32_t pw[32], dw[32];

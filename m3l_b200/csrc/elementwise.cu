@@ -66,12 +66,20 @@ __global__ void mask_indices_kernel(const float* __restrict__ noise, int n_total
 // patch addressing shared by the gather kernels
 // ------------------------------------------------------------------------------------------
 struct PatchSrc {
-  const float* src[4];   // per sensor [B, C, H, W] fp32 (image: one entry)
+  const float* src[4];   // per sensor [B, C, H, W] fp32 (image: one entry); layout 1: raw observation base pointers
   int C, H, W, ph, pw;   // channels, height, width, patch height / width
   int gw;                // patches per row (W / pw)
   int n_per_src;         // patches per source (gh * gw)
   int tok_base;          // global token index of this modality's first token
   int P;                 // ph * pw * C
+  // layout 1: the maps are read straight from the RAW observation tensors (vt_load and the 5-D frame-stack reshape
+  // fused into the patch loads: utils/pretrain_utils.py:7-57, models/pretrain_models.py:823-827):
+  //   element (b, c, y, x), c = f * cg + ch, lives at  b*sb + f*sf + ch*sch + y*sy + x*sx  (elements) and is
+  //   normalised as (raw - lo) / span  (uint8 sources: raw / 255 first)
+  int layout, u8;
+  long long sb;
+  int cg, sf, sch, sy, sx;
+  float lo, span;
 };
 
 M3L_DEVINL const float* patch_origin(const PatchSrc& ps, int b, int tok, int* sensor) {
@@ -109,6 +117,116 @@ M3L_DEVINL void load_patch_smem(const PatchSrc& ps, const float* origin, float* 
       for (int p2 = 0; p2 < ps.pw; ++p2) dst[p2 * ps.C] = src[p2];
     }
   }
+}
+
+// ---- layout 1 (raw observations) ------------------------------------------------------------------------
+// normalisation exactly as the reference computes it: (x - lo) / (hi - lo) in fp32 with IEEE division (this file is
+// compiled without fast-math); uint8 frames are x / 255 first
+M3L_DEVINL float raw_norm(const PatchSrc& ps, float v) { return (v - ps.lo) / ps.span; }
+M3L_DEVINL float raw_norm_u8(const PatchSrc& ps, unsigned int v) { return ((float)v / 255.0f - ps.lo) / ps.span; }
+
+// element offset of the patch origin (b, token) in the raw tensor of its sensor
+M3L_DEVINL long long raw_origin(const PatchSrc& ps, int b, int tok, int* sensor) {
+  const int t = tok - ps.tok_base;
+  const int s = t / ps.n_per_src;
+  const int tl = t - s * ps.n_per_src;
+  const int hh = tl / ps.gw, ww = tl - hh * ps.gw;
+  *sensor = s;
+  return (long long)b * ps.sb + (long long)hh * ps.ph * ps.sy + (long long)ww * ps.pw * ps.sx;
+}
+
+// Gathers one patch from a raw observation tensor into `dst` in destination order (p1, p2, c), patch row p1 at
+// dst + p1 * pitch; `nthr` cooperating threads, this one is `t`.  Work is split into runs that are CONTIGUOUS in the
+// source so that each thread issues wide loads:
+//   sx == 1            (channel planes, e.g. the tactile maps [B, F, 6, h, w]): run = (c, p1), pw elements along x
+//   sch == 1, sx == cg (interleaved frames, e.g. images [B, F, H, W, 3]):       run = (f, p1), pw * cg elements (x, ch)
+//   otherwise          (e.g. NHWC with all stacked channels contiguous [B, H, W, C]): run = (p1, p2), C elements
+template <typename T>
+M3L_DEVINL void gather_patch_raw(const PatchSrc& ps, const T* base, float* dst, int pitch, int t, int nthr) {
+  const int C = ps.C, pw = ps.pw, cg = ps.cg;
+  auto cvt = [&](T v) -> float {
+    if constexpr (sizeof(T) == 1) return raw_norm_u8(ps, (unsigned int)v); else return raw_norm(ps, (float)v);
+  };
+  if (ps.sx == 1) {
+    const int rows = C * ps.ph;
+    for (int i = t; i < rows; i += nthr) {
+      const int p1 = i / C, c = i - p1 * C;
+      const int f = c / cg, ch = c - f * cg;
+      const T* src = base + (long long)f * ps.sf + (long long)ch * ps.sch + (long long)p1 * ps.sy;
+      float* d = dst + p1 * pitch + c;
+      if constexpr (sizeof(T) == 4) {
+        if ((pw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          for (int p2 = 0; p2 < pw; p2 += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + p2));
+            d[(p2 + 0) * C] = raw_norm(ps, v.x); d[(p2 + 1) * C] = raw_norm(ps, v.y);
+            d[(p2 + 2) * C] = raw_norm(ps, v.z); d[(p2 + 3) * C] = raw_norm(ps, v.w);
+          }
+          continue;
+        }
+      }
+      for (int p2 = 0; p2 < pw; ++p2) d[p2 * C] = cvt(src[p2]);
+    }
+  } else if (ps.sch == 1 && ps.sx == cg) {
+    const int F = C / cg, rows = F * ps.ph, run = pw * cg;
+    for (int i = t; i < rows; i += nthr) {
+      const int p1 = i / F, f = i - p1 * F;
+      const T* src = base + (long long)f * ps.sf + (long long)p1 * ps.sy;
+      float* d = dst + p1 * pitch + f * cg;
+      // destination of run element q = p2 * cg + ch is d[p2 * C + ch]
+      if constexpr (sizeof(T) == 4) {
+        if ((run & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          int p2 = 0, ch = 0;
+          for (int q = 0; q < run; q += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + q));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              d[p2 * C + ch] = raw_norm(ps, vv[e]);
+              if (++ch == cg) { ch = 0; ++p2; }
+            }
+          }
+          continue;
+        }
+      } else {
+        if ((run & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+          int p2 = 0, ch = 0;
+          for (int q = 0; q < run; q += 4) {
+            const unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(src + q));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              d[p2 * C + ch] = raw_norm_u8(ps, (w >> (8 * e)) & 0xffu);
+              if (++ch == cg) { ch = 0; ++p2; }
+            }
+          }
+          continue;
+        }
+      }
+      int p2 = 0, ch = 0;
+      for (int q = 0; q < run; ++q) {
+        d[p2 * C + ch] = cvt(src[q]);
+        if (++ch == cg) { ch = 0; ++p2; }
+      }
+    }
+  } else {
+    const int rows = ps.ph * pw;
+    for (int i = t; i < rows; i += nthr) {
+      const int p1 = i / pw, p2 = i - p1 * pw;
+      const T* src = base + (long long)p1 * ps.sy + (long long)p2 * ps.sx;
+      float* d = dst + p1 * pitch + p2 * C;
+      for (int c = 0; c < C; ++c) {
+        const int f = c / cg, ch = c - f * cg;
+        d[c] = cvt(src[(long long)f * ps.sf + (long long)ch * ps.sch]);
+      }
+    }
+  }
+}
+
+// layout-dispatching gather used by the patch kernels (t / nthr as above)
+M3L_DEVINL void gather_patch(const PatchSrc& ps, int b, int tok, float* dst, int pitch, int t, int nthr) {
+  int sensor;
+  const long long off = raw_origin(ps, b, tok, &sensor);
+  if (ps.u8) gather_patch_raw(ps, reinterpret_cast<const unsigned char*>(ps.src[sensor]) + off, dst, pitch, t, nthr);
+  else gather_patch_raw(ps, ps.src[sensor] + off, dst, pitch, t, nthr);
 }
 
 // Two-stage column reduction without contended atomics (same-sector fp32 atomics serialise at
@@ -181,10 +299,14 @@ __global__ void patch_ln_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx
   const int r = blockIdx.x;
   const int b = r / ncols, jj = r - b * ncols;
   const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
-  int sensor;
-  const float* origin = patch_origin(ps, b, tok, &sensor);
   const int P = ps.P;
-  load_patch_smem(ps, origin, patch);
+  if (ps.layout == 0) {
+    int sensor;
+    const float* origin = patch_origin(ps, b, tok, &sensor);
+    load_patch_smem(ps, origin, patch);
+  } else {
+    gather_patch(ps, b, tok, patch, ps.pw * ps.C, threadIdx.x, blockDim.x);
+  }
   __syncthreads();
   float s = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) s += patch[i];
@@ -901,8 +1023,8 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
   for (int r = blockIdx.x * nwarps + warp; r < rows; r += gridDim.x * nwarps) {
     const int b = r / ncols, jj = r - b * ncols;
     const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
-    int sensor;
-    const float* origin = patch_origin(ps, b, tok, &sensor);
+    int sensor = 0;
+    const float* origin = ps.layout == 0 ? patch_origin(ps, b, tok, &sensor) : nullptr;
     // the predictions of this row are requested BEFORE the target gather so that both global round trips
     // overlap (they used to be exposed back to back, one row at a time per warp)
     const float* prow = pred + (size_t)r * P;
@@ -912,7 +1034,8 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
       const int e = t * 128 + lane * 4;
       if (e < P) pvr[t] = __ldcs(reinterpret_cast<const float4*>(prow + e));
     }
-    for (int i = lane; i < src_rows; i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
+    if (ps.layout != 0) gather_patch(ps, b, tok, patch, pitch, lane, 32);     // raw observations (vt_load fused)
+    for (int i = lane; i < (ps.layout == 0 ? src_rows : 0); i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
       const int p1 = i / ps.C, c = i - p1 * ps.C;
       const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
       float* dst = patch + p1 * pitch + c;
@@ -1260,13 +1383,50 @@ token_finish_bwd_kernel(const bf16* __restrict__ dx0, int B, int rows_per_sample
 
 PatchSrc make_patch_src(const m3l_patch_source* s) {
   PatchSrc ps;
-  for (int i = 0; i < 4; ++i) ps.src[i] = s->src[i];
+  for (int i = 0; i < 4; ++i) ps.src[i] = static_cast<const float*>(s->src[i]);
   ps.C = s->channels; ps.H = s->height; ps.W = s->width; ps.ph = s->patch_h; ps.pw = s->patch_w;
   ps.gw = s->width / s->patch_w;
   ps.n_per_src = (s->height / s->patch_h) * ps.gw;
   ps.tok_base = s->token_base;
   ps.P = s->patch_h * s->patch_w * s->channels;
+  ps.layout = s->layout; ps.u8 = s->dtype == 1 ? 1 : 0;
+  ps.sb = s->stride_b; ps.cg = s->chan_group > 0 ? s->chan_group : 1;
+  ps.sf = s->stride_f; ps.sch = s->stride_ch; ps.sy = s->stride_y; ps.sx = s->stride_x;
+  ps.lo = s->norm_lo; ps.span = s->norm_span;
   return ps;
+}
+
+int check_patch_src(const m3l_patch_source* s, const char* what) {
+  M3L_REQUIRE(s->layout == 0 || s->layout == 1, "%s: patch source layout %d unknown", what, s->layout);
+  if (s->layout == 1) {
+    M3L_REQUIRE(s->dtype == 0 || s->dtype == 1, "%s: raw observation dtype %d unknown (0 fp32, 1 uint8)", what, s->dtype);
+    M3L_REQUIRE(s->chan_group >= 1 && s->channels % s->chan_group == 0, "%s: channels %d not a multiple of the channel group %d",
+                what, s->channels, s->chan_group);
+    M3L_REQUIRE(s->norm_span != 0.f, "%s: normalisation span must be non-zero", what);
+  } else {
+    M3L_REQUIRE(s->dtype == 0, "%s: layout 0 takes fp32 maps", what);
+  }
+  return M3L_OK;
+}
+
+// vt_load as a kernel of its own (callers that need the maps materialised: the conv stem, reconstruct()):
+// out[b, c, y, x] fp32 NCHW contiguous <- raw observation (layout 1 addressing), one thread per output element
+__global__ void __launch_bounds__(256)
+vt_load_kernel(PatchSrc ps, int sensor, long long total, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const long long plane = (long long)ps.H * ps.W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long bc = i / plane;
+    const int yx = (int)(i - bc * plane);
+    const int y = yx / ps.W, x = yx - y * ps.W;
+    const int b = (int)(bc / ps.C), c = (int)(bc - (long long)b * ps.C);
+    const int f = c / ps.cg, ch = c - f * ps.cg;
+    const long long off = (long long)b * ps.sb + (long long)f * ps.sf + (long long)ch * ps.sch + (long long)y * ps.sy +
+                          (long long)x * ps.sx;
+    out[i] = ps.u8 ? raw_norm_u8(ps, reinterpret_cast<const unsigned char*>(ps.src[sensor])[off])
+                   : raw_norm(ps, ps.src[sensor][off]);
+  }
 }
 
 int ln_grid(int M, int warps_per_block) {
@@ -1311,6 +1471,7 @@ extern "C" int m3l_patch_layernorm(const m3l_patch_source* src, int batch, const
                                    void* out_bf16, void* xhat_bf16, void* stream) {
   M3L_REQUIRE(src && gamma && beta && out_bf16, "patch_layernorm: null pointer");
   if (batch * ncols == 0) return M3L_OK;
+  { const int s_ = check_patch_src(src, "patch_layernorm"); if (s_) return s_; }
   PatchSrc ps = make_patch_src(src);
   M3L_REQUIRE(ps.P * sizeof(float) <= 48 * 1024, "patch_layernorm: patch dim %d too large", ps.P);
   M3L_CUDA(launch_kernel(patch_ln_kernel, dim3(batch * ncols), dim3(128), ps.P * sizeof(float), (cudaStream_t)stream, 
@@ -1488,6 +1649,7 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
                             float* dpred_colsum, void* workspace, size_t workspace_bytes, void* stream) {
   M3L_REQUIRE(src && pred && dpred_bf16 && loss_acc, "mse_loss: null pointer");
   if (batch * ncols == 0) return M3L_OK;
+  { const int s_ = check_patch_src(src, "mse_loss"); if (s_) return s_; }
   PatchSrc ps = make_patch_src(src);
   const int rowlen = ps.pw * ps.C;
   M3L_REQUIRE(ps.P % 4 == 0 && rowlen % 4 == 0, "mse_loss: patch dim %d / row %d must be multiples of 4", ps.P, rowlen);
@@ -1630,6 +1792,22 @@ extern "C" int m3l_token_finish_bwd(const void* dx0_bf16, int batch, int rows_pe
   M3L_CUDA(launch_kernel(token_finish_bwd_kernel, dim3(ln_grid(batch * n_mod, 8)), dim3(256), 0, (cudaStream_t)stream,
                          (const bf16*)dx0_bf16, batch, rows_per_sample, n_total, slot_of_token, tok_base, n_mod, n_per, dim,
                          (bf16*)dtok_bf16));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_vt_load(const m3l_patch_source* src, int batch, int sensor, float* out_nchw, void* stream) {
+  M3L_REQUIRE(src && out_nchw, "vt_load: null pointer");
+  M3L_REQUIRE(src->layout == 1, "vt_load: the source must be a raw observation (layout 1)");
+  M3L_REQUIRE(sensor >= 0 && sensor < 4 && src->src[sensor] != nullptr, "vt_load: bad sensor index %d", sensor);
+  { const int s_ = check_patch_src(src, "vt_load"); if (s_) return s_; }
+  if (batch == 0) return M3L_OK;
+  PatchSrc ps = make_patch_src(src);
+  const long long total = (long long)batch * ps.C * ps.H * ps.W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  M3L_CUDA(launch_kernel(vt_load_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, ps, sensor, total, out_nchw));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -397,10 +397,11 @@ def _modalities(model, geo, x):
     """(key, prefix, maps, H, W, n_per_source, tok_base) of the modalities present."""
     e = model.encoder
     out = []
+    mat = lambda t: t.materialize() if hasattr(t, "materialize") else t      # the conv stem reads NCHW maps
     if geo.use_vision:
-        out.append(("image", "early_conv_vision", [x["image"]], e.image_height, e.image_width, geo.n_img, 0))
+        out.append(("image", "early_conv_vision", [mat(x["image"])], e.image_height, e.image_width, geo.n_img, 0))
     if geo.nt:
-        out.append(("tactile", "early_conv_tactile", [x[f"tactile{i + 1}"] for i in range(geo.nt)],
+        out.append(("tactile", "early_conv_tactile", [mat(x[f"tactile{i + 1}"]) for i in range(geo.nt)],
                     e.tactile_height, e.tactile_width, geo.n_tac, geo.n_img))
     return out
 

@@ -168,16 +168,39 @@ def mask_indices(noise: torch.Tensor, segs, want_slots: bool = True, extra: bool
 
 
 def make_patch_source(maps, patch_h: int, patch_w: int, token_base: int):
-    """maps: list of fp32 NCHW tensors of one modality (same shape)."""
+    """maps: list of fp32 NCHW tensors of one modality (same shape), or of data.RawMap views into raw observation
+    tensors (vt_load fused into the patch loads: `layout 1` of m3l_patch_source)."""
+    from .data import RawMap
     ps = _lib.PatchSource()
     assert 1 <= len(maps) <= 4
-    for i, m in enumerate(maps):
-        assert m.dtype == torch.float32 and m.is_contiguous() and m.is_cuda and m.shape == maps[0].shape
-        ps.src[i] = m.data_ptr()
-    _, ps.channels, ps.height, ps.width = maps[0].shape
+    if isinstance(maps[0], RawMap):
+        m0 = maps[0]
+        for i, m in enumerate(maps):
+            assert isinstance(m, RawMap) and m.is_cuda and m.shape == m0.shape and m.t.dtype == m0.t.dtype
+            assert (m.sb, m.cg, m.sf, m.sch, m.sy, m.sx, m.lo, m.span) == (m0.sb, m0.cg, m0.sf, m0.sch, m0.sy, m0.sx, m0.lo, m0.span)
+            ps.src[i] = m.data_ptr()
+        _, ps.channels, ps.height, ps.width = m0.shape
+        ps.layout, ps.dtype = 1, (1 if m0.t.dtype == torch.uint8 else 0)
+        ps.stride_b, ps.chan_group = m0.sb, m0.cg
+        ps.stride_f, ps.stride_ch, ps.stride_y, ps.stride_x = m0.sf, m0.sch, m0.sy, m0.sx
+        ps.norm_lo, ps.norm_span = m0.lo, m0.span
+    else:
+        for i, m in enumerate(maps):
+            assert m.dtype == torch.float32 and m.is_contiguous() and m.is_cuda and m.shape == maps[0].shape
+            ps.src[i] = m.data_ptr()
+        _, ps.channels, ps.height, ps.width = maps[0].shape
     ps.patch_h, ps.patch_w, ps.token_base = patch_h, patch_w, token_base
     ps._keepalive = maps
     return ps
+
+
+def vt_load_map(raw) -> torch.Tensor:
+    """data.RawMap -> fp32 [B, C, H, W] contiguous (utils/pretrain_utils.py:7-57 as one kernel)."""
+    ps = make_patch_source([raw], 1, 1, 0)
+    B = raw.shape[0]
+    out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    check(_lib.load().m3l_vt_load(C.byref(ps), B, 0, ptr(out), current_stream()), "m3l_vt_load")
+    return out
 
 
 def patch_layernorm(ps, batch: int, ncols: int, gamma, beta, tok_idx=None, col0: int = 0, want_xhat=True,

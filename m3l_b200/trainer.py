@@ -15,6 +15,7 @@ import torch
 
 from . import dp, engine, ops
 from ._lib import M3LError
+from .data import clone_inputs, copy_inputs, input_signature
 
 
 class FusedAdamW:
@@ -145,15 +146,14 @@ class FusedTrainer:
             self._phase_c(ranges)
             A._version_seen = A.version()
             return box["loss"].reshape(())
-        key = (geo.use_vision, geo.nt, B)
+        key = (geo.use_vision, geo.nt, B, input_signature(xs))
         g = self._graphs.get(key)
         if g is None:
             while len(self._graphs) >= self._MAX_GRAPHS:       # each capture owns a full activation pool
                 self._graphs.pop(next(iter(self._graphs)))
             g = self._capture(xs, noise, geo, ranges)
             self._graphs[key] = g
-        for k, v in xs.items():
-            g["xs"][k].copy_(v, non_blocking=True)
+        copy_inputs(g["xs"], xs)
         g["noise"].copy_(noise, non_blocking=True)
         if self.world == 1:
             g["all"].replay()
@@ -171,7 +171,7 @@ class FusedTrainer:
 
     def _capture(self, xs, noise, geo, ranges):
         """Warm-up once eagerly (lazy kernel attributes, allocator), then capture."""
-        sx = {k: v.clone() for k, v in xs.items()}
+        sx = clone_inputs(xs)
         sn = noise.clone()
         # eager warm-up on a side stream must not advance the optimizer: snapshot & restore state
         snap = (self.model.arena.flat.clone(), self.m.clone(), self.v.clone(), self.state.clone())

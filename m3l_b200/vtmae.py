@@ -12,6 +12,7 @@ draws the reference takes from torch.rand (image, tactile1, tactile2 order; pret
 from __future__ import annotations
 
 import math
+import weakref
 import random
 from types import SimpleNamespace
 from typing import Dict, Optional
@@ -23,6 +24,7 @@ from torch import nn
 from . import engine, ops
 from ._lib import M3LError
 from .arena import ParamArena
+from .data import RawMap, clone_inputs, copy_inputs, input_signature, vt_load_lazy
 
 
 def pair(t):
@@ -178,6 +180,11 @@ class VTT(nn.Module):
         self.dropout = nn.Dropout(emb_dropout)
         self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
         self.to_latent = nn.Identity()
+
+
+def _as_map(t):
+    """fp32 NCHW tensor of a model input (materialises a raw-observation view: m3l_vt_load kernel)."""
+    return t.materialize() if isinstance(t, RawMap) else t
 
 
 def _sincos_2d(nx: int, ny: int, gen_channels: int, out_channels: int) -> torch.Tensor:
@@ -338,7 +345,8 @@ class VTMAE(nn.Module):
             t = x[k]
             if not t.is_cuda:
                 raise M3LError(f"input '{k}' is not on a CUDA device (no CPU fallback)")
-            xs[k] = t.detach().to(torch.float32).contiguous()
+            # data.RawMap: a view into the raw observation tensor; vt_load happens inside the patch-gather kernels
+            xs[k] = t if isinstance(t, RawMap) else t.detach().to(torch.float32).contiguous()
         B = xs[keys[0]].shape[0]
         return xs, geo, B
 
@@ -354,8 +362,13 @@ class VTMAE(nn.Module):
         live = self.live_param_names(geo, True)
         params = [A.params[k] for k in live]
         if self.use_cuda_graph and torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            ent = _graph_entry(self, ("mae", geo.use_vision, geo.nt, B), xs, noise, geo)
-            return _MAEGraphFn.apply(self, ent, geo, tuple(live), *params)
+            key = ("mae", geo.use_vision, geo.nt, B, input_signature(xs))
+            # The graph entry owns ONE set of saved activations.  If the previous replayed forward of this shape has
+            # not been back-propagated yet (two forwards before a backward: SAC with a shared extractor, gradient
+            # accumulation over two losses), this call takes the eager autograd path, which owns its activations.
+            if _entry_free(self.__dict__.get("_mae_graphs", {}).get(key)):
+                ent = _graph_entry(self, key, xs, noise, geo)
+                return _MAEGraphFn.apply(self, ent, geo, tuple(live), *params)
         return _MAEFn.apply(self, xs, noise, geo, tuple(live), *params)
 
     def get_embeddings(self, x, eval=True, use_vision=True, use_tactile=True):
@@ -370,15 +383,15 @@ class VTMAE(nn.Module):
         params = [A.params[k] for k in live]
         if self.use_cuda_graph and torch.is_grad_enabled() and any(p.requires_grad for p in params):
             cache = self.__dict__.setdefault("_mae_graphs", {})
-            key = ("emb", geo.use_vision, geo.nt, B)
+            key = ("emb", geo.use_vision, geo.nt, B, input_signature(xs))
             ent = cache.get(key)
-            if ent is None:
-                if len(cache) >= _MAX_GRAPHS:
-                    cache.pop(next(iter(cache)))
-                ent = cache[key] = _capture_emb_graphs(self, xs, geo, B)
-            for k, v in xs.items():
-                ent.xs[k].copy_(v, non_blocking=True)
-            return _EmbGraphFn.apply(self, ent, tuple(live), *params)
+            if _entry_free(ent):                  # else: previous forward not back-propagated yet -> eager path
+                if ent is None:
+                    if len(cache) >= _MAX_GRAPHS:
+                        cache.pop(next(iter(cache)))
+                    ent = cache[key] = _capture_emb_graphs(self, xs, geo, B)
+                copy_inputs(ent.xs, xs)
+                return _EmbGraphFn.apply(self, ent, tuple(live), *params)
         return _EmbFn.apply(self, xs, geo, B, tuple(live), *params)
 
     @torch.no_grad()
@@ -404,7 +417,7 @@ class VTMAE(nn.Module):
         out = {}
         if geo.use_vision:
             gh, gw = e.image_height // self.ph_img, e.image_width // self.pw_img
-            patches = self.image_to_patch(xs['image'])
+            patches = self.image_to_patch(_as_map(xs['image']))
             mi = masked[:, :geo.nm_img]
             vis, rec = patches.clone(), patches.clone()
             vis[br, mi] = 0.5
@@ -420,7 +433,7 @@ class VTMAE(nn.Module):
             out['image_rec'], out['image_masked'] = unp(rec), unp(vis)
         if geo.nt:
             gh, gw = e.tactile_height // self.ph_tac, e.tactile_width // self.pw_tac
-            patches = torch.cat([self.tactile_to_patch(xs[f'tactile{i + 1}']) for i in range(geo.nt)], dim=1)
+            patches = torch.cat([self.tactile_to_patch(_as_map(xs[f'tactile{i + 1}'])) for i in range(geo.nt)], dim=1)
             mt = masked[:, geo.nm_img:] - geo.n_img
             vis, rec = patches.clone(), patches.clone()
             vis[br, mt] = float('inf')
@@ -454,7 +467,6 @@ class VTMAE(nn.Module):
 
     def train_iterations(self, iterations, replay_buffer, no_tactile=False):
         """pretrain_models.py:679-715 (host-side batch assembly kept as in the reference)."""
-        from .data import vt_load
         if len(replay_buffer) < self.batch_size:
             print("Not enough samples in replay buffer")
             return
@@ -470,8 +482,8 @@ class VTMAE(nn.Module):
                 new_x['image'] = new_x['image'].reshape((new_x['image'].shape[0], new_x['image'].shape[1], new_x['image'].shape[2], -1))
             if 'tactile' in new_x:
                 new_x['tactile'] = new_x['tactile'].reshape((new_x['tactile'].shape[0], -1, new_x['tactile'].shape[3], new_x['tactile'].shape[4]))
-            xd = vt_load(new_x, frame_stack=self.frame_stack)
-            xd = {k: v.to(self.mask_token.device, non_blocking=True) for k, v in xd.items()}
+            # raw batch -> device; vt_load itself (layout, de-interleave, normalisation) runs inside the patch gathers
+            xd = vt_load_lazy(new_x, frame_stack=self.frame_stack, device=self.mask_token.device)
             self.train_step(xd)
         self.eval()
 
@@ -535,6 +547,8 @@ class MAEExtractor(_ExtractorBase):
               (bool(self.vision_only_control), id(A), id(Av))
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
+        if not _entry_free(ent):                  # previous forward of this shape not back-propagated yet
+            return self._forward_eager(obs)
         if ent is None:
             if len(cache) >= 8:
                 cache.pop(next(iter(cache)))
@@ -585,15 +599,13 @@ class MAEExtractor(_ExtractorBase):
 
     def _prep(self, obs):
         """Observation reshapes (pretrain_models.py:823-827) + vt_load -> (model inputs, geometry, batch, arenas)."""
-        from .data import vt_load
         mae = self.mae_model
-        if 'image' in obs and obs['image'].dim() == 5:            # (B, F, H, W, 3) -> (B, H, W, 3F)
-            im = obs['image'].permute(0, 2, 3, 1, 4)
-            obs['image'] = im.reshape(im.shape[0], im.shape[1], im.shape[2], -1)
-        if 'tactile' in obs and obs['tactile'].dim() == 5:        # (B, F, 6, h, w) -> (B, 6F, h, w)
-            t = obs['tactile']
-            obs['tactile'] = t.reshape(t.shape[0], -1, t.shape[3], t.shape[4])
-        vt = vt_load(obs, frame_stack=self.frame_stack)
+        # The 5-D frame-stack reshapes (:823-827) and vt_load are not executed: the observation tensors stay as the
+        # rollout buffer holds them and the patch-gather kernels read them in place (data.RawMap, layout 1).
+        if mae.early_conv_masking:
+            vt = {k: v.materialize() for k, v in vt_load_lazy(obs, frame_stack=self.frame_stack).items()}
+        else:
+            vt = vt_load_lazy(obs, frame_stack=self.frame_stack)
         mae.train()                                               # get_embeddings(eval=False) side effect (:590-593)
         A = mae._sync()
         xs, geo, B = mae._prep_inputs(vt, True, not self.vision_only_control)
@@ -638,7 +650,7 @@ def _capture_extractor_graphs(ext, obs):
     mae, tr = ext.mae_model, ext.vit_layer.transformer
     ent = _GraphEntry()
     ent.xs = {k: v.clone() for k, v in obs.items()}
-    ent.gen, ent.consumed = 0, True
+    ent.gen, ent.consumed, ent.node = 0, True, None
     xs, geo, B, A, Av = ext._prep(dict(ent.xs))
     ent.live, ent.vit_names = tuple(mae.live_param_names(geo, False)), tuple(Av.names)
     ent.gflat, ent.gflat2 = A.new_grad_buffer(), Av.new_grad_buffer()
@@ -687,6 +699,7 @@ class _ExtractorGraphFn(torch.autograd.Function):
     def forward(ctx, ext, ent, live, vit_names, *params):
         ent.gen += 1
         ent.consumed = False
+        ent.node = _weak(ctx)
         ent.fwd.replay()
         ctx.ext, ctx.ent, ctx.gen = ext, ent, ent.gen
         return ent.loss.clone()
@@ -716,9 +729,25 @@ class _ExtractorGraphFn(torch.autograd.Function):
 _MAX_GRAPHS = 4
 
 
+def _weak(node):
+    try:
+        return weakref.ref(node)
+    except TypeError:                        # not weak-referenceable: treat the forward as outstanding until consumed
+        return lambda: True
+
+
+def _entry_free(ent) -> bool:
+    """True when a graph entry may be replayed: none captured yet, or its last forward was consumed by a backward /
+    its autograd node is gone (result discarded, e.g. an evaluation-only call under enable_grad)."""
+    if ent is None or ent.consumed:
+        return True
+    node = ent.node() if ent.node is not None else None
+    return node is None
+
+
 class _GraphEntry:
     __slots__ = ("fwd", "bwd", "xs", "noise", "loss", "ctx", "gflat", "gflat2", "gout", "gen", "consumed", "masked", "unmasked",
-                 "live", "vit_names")
+                 "live", "vit_names", "node")
 
 
 def _graph_entry(model, key, xs, noise, geo):
@@ -728,8 +757,7 @@ def _graph_entry(model, key, xs, noise, geo):
         if len(cache) >= _MAX_GRAPHS:
             cache.pop(next(iter(cache)))
         ent = cache[key] = _capture_mae_graphs(model, xs, noise, geo)
-    for k, v in xs.items():
-        ent.xs[k].copy_(v, non_blocking=True)
+    copy_inputs(ent.xs, xs)
     ent.noise.copy_(noise, non_blocking=True)
     return ent
 
@@ -737,11 +765,11 @@ def _graph_entry(model, key, xs, noise, geo):
 def _capture_mae_graphs(model, xs, noise, geo):
     A = model.arena
     ent = _GraphEntry()
-    ent.xs = {k: v.clone() for k, v in xs.items()}
+    ent.xs = clone_inputs(xs)
     ent.noise = noise.clone()
     ent.gflat = A.new_grad_buffer()
     ent.gout = torch.ones((), dtype=torch.float32, device=A.device)
-    ent.gen, ent.consumed = 0, True
+    ent.gen, ent.consumed, ent.node = 0, True, None
 
     def fwd():
         ent.gflat.zero_()
@@ -775,8 +803,9 @@ class _MAEGraphFn(torch.autograd.Function):
     def forward(ctx, model, ent, geo, live, *params):
         ent.gen += 1
         ent.consumed = False
+        ent.node = _weak(ctx)
         ent.fwd.replay()
-        model.last_masked_indices, model.last_unmasked_indices = ent.masked, ent.unmasked
+        model.last_masked_indices, model.last_unmasked_indices = ent.masked.clone(), ent.unmasked.clone()
         ctx.model, ctx.ent, ctx.gen, ctx.live = model, ent, ent.gen, live
         return ent.loss.reshape(()).clone()
 
@@ -798,10 +827,10 @@ def _capture_emb_graphs(model, xs, geo, B):
     """Forward / backward graphs of get_embeddings (no-mask encoder pass), same scheme as _capture_mae_graphs."""
     A = model.arena
     ent = _GraphEntry()
-    ent.xs = {k: v.clone() for k, v in xs.items()}
+    ent.xs = clone_inputs(xs)
     ent.gflat = A.new_grad_buffer()
     ent.gout = torch.zeros((B * geo.n, model.cfg.dim), dtype=torch.bfloat16, device=A.device)
-    ent.gen, ent.consumed = 0, True
+    ent.gen, ent.consumed, ent.node = 0, True, None
 
     def fwd():
         out, ent.ctx = engine.embeddings_forward(model, ent.xs, geo, B, training=True)
@@ -833,6 +862,7 @@ class _EmbGraphFn(torch.autograd.Function):
     def forward(ctx, model, ent, live, *params):
         ent.gen += 1
         ent.consumed = False
+        ent.node = _weak(ctx)
         ent.fwd.replay()
         ctx.model, ctx.ent, ctx.gen, ctx.live = model, ent, ent.gen, live
         return ent.loss.clone()
