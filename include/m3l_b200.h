@@ -202,6 +202,20 @@ int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_t* tok_idx,
                  int ncols, const float* pred, float weight, void* dpred_bf16, float* loss_acc,
                  float* dpred_colsum, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Plain patchify + row gather (no LayerNorm) -> bf16 rows [batch*ncols, ld], (p1, p2, c) order, columns [P, ld)
+ * zero-filled: the input of a ViT patch embedding whose first layer is Conv2d(kernel = stride = patch), here the
+ * frozen DINOv2 ViT-S/14 image branch of the DINO-tac-MAE variant (/root/reference/train_dino_tac_mae.py:29,
+ * models/pretrain_models_dino_cat_mae.py:884-889). */
+int m3l_patchify(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0, int ncols,
+                 void* out_bf16, int ld, void* stream);
+
+/* dst[b*n_total + tok_idx[b*idx_ld + j]] += src[b*ncols + j] over bf16 rows of `dim` elements (distinct tokens per
+ * sample).  Joint MAE + policy-feature step (/root/reference/models/ppo_mae.py:260-263,280): the masked encoder's
+ * input is a row gather of the full embedded token sequence the feature extractor also consumes; this adds the
+ * gather's gradient into the full-sequence gradient so the patch embedding is back-propagated once. */
+int m3l_row_scatter_add(const void* src_bf16, int batch, int ncols, const int32_t* tok_idx, int idx_ld, int n_total,
+                        int dim, void* dst_bf16, void* stream);
+
 /* vt_load as a kernel of its own (utils/pretrain_utils.py:7-57): raw observation (layout 1 source) of sensor
  * `sensor` -> fp32 [batch, channels, height, width] contiguous, for callers that need the maps materialised
  * (the EarlyCNN conv stem, reconstruct()); the masked-autoencoder step itself reads raw observations directly. */

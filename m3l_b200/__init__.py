@@ -12,6 +12,9 @@ def __getattr__(name):
     if name in ("VTT", "VTMAE", "EarlyCNN", "Transformer", "MAEExtractor", "pair"):
         from . import vtmae
         return getattr(vtmae, name)
+    if name in ("DinoV2", "DinoCatMAEExtractor"):
+        from . import dinov2
+        return getattr(dinov2, name)
     if name == "VTTDino":
         from .vtt import VTT as VTTDino
         return VTTDino

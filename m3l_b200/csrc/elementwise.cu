@@ -325,6 +325,37 @@ __global__ void patch_ln_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx
 }
 
 // ------------------------------------------------------------------------------------------
+// 2b. plain patchify (no LayerNorm): row r = (b, jj) <- patch of token tok_idx[b, col0 + jj] (or tok_base + jj) in
+//     (p1, p2, c) order as bf16, row pitch `ld` >= P, columns [P, ld) zero (K padding for the GEMM that follows).
+//     The patch embedding of a ViT whose first layer is Conv2d(kernel = stride = patch), e.g. the frozen DINOv2
+//     image branch (train_dino_tac_mae.py:29; weights permuted once to this K order).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+patchify_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols,
+                bf16* __restrict__ out, int ld) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float patch[];   // P floats
+  const int r = blockIdx.x;
+  const int b = r / ncols, jj = r - b * ncols;
+  const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+  const int P = ps.P;
+  if (ps.layout == 0) {
+    int sensor;
+    const float* origin = patch_origin(ps, b, tok, &sensor);
+    load_patch_smem(ps, origin, patch);
+  } else {
+    gather_patch(ps, b, tok, patch, ps.pw * ps.C, threadIdx.x, blockDim.x);
+  }
+  __syncthreads();
+  bf16* orow = out + (size_t)r * ld;
+  for (int i = threadIdx.x * 2; i < ld; i += blockDim.x * 2) {
+    const float v0 = i < P ? patch[i] : 0.f, v1 = i + 1 < P ? patch[i + 1] : 0.f;
+    *reinterpret_cast<uint32_t*>(orow + i) = pack_bf16x2(v0, v1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // generic warp-per-row LayerNorm helpers (D multiple of 8, D <= 1024); lane owns 8-element chunks
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxChunks = 4;  // D <= 32 * 8 * 4 = 1024
@@ -1358,6 +1389,31 @@ token_finish_kernel(const bf16* __restrict__ x, int B, int n_per, const int32_t*
   }
 }
 
+// dst[b*n_total + tok_idx[b, j]] += src[b*ncols + j]  (bf16 rows; the tokens of one sample are distinct, so no two
+// source rows hit the same destination row): adds the gradient of a row gather (the masked encoder's visible tokens)
+// into the gradient of the full token sequence it was taken from (joint MAE + policy-feature step)
+__global__ void __launch_bounds__(256)
+row_scatter_add_kernel(const bf16* __restrict__ src, int B, int ncols, const int32_t* __restrict__ tok_idx, int idx_ld,
+                       int n_total, int D, bf16* __restrict__ dst) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int nchunk = D >> 3;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B * ncols; r += gridDim.x * wpb) {
+    const int b = r / ncols, jj = r - b * ncols;
+    const int tok = tok_idx[(size_t)b * idx_ld + jj];
+    bf16* d = dst + ((size_t)b * n_total + tok) * D;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      float v[8], a[8];
+      load8<bf16>(d + ch * 8, v);
+      load8<bf16>(src + (size_t)r * D + ch * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += a[i];
+      store8(d + ch * 8, v);
+    }
+  }
+}
+
 // backward of the token gather: dtok[src(b, tl)] = slot >= 0 ? dx0[b*rows_per_sample + slot] : 0,
 //   slot = slot_of_token ? slot_of_token[b*n_total + tok_base + tl] : tok_base + tl   (src() as above)
 __global__ void __launch_bounds__(256)
@@ -1808,6 +1864,31 @@ extern "C" int m3l_vt_load(const m3l_patch_source* src, int batch, int sensor, f
   const long long cap = (long long)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
   M3L_CUDA(launch_kernel(vt_load_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, ps, sensor, total, out_nchw));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_patchify(const m3l_patch_source* src, int batch, const int64_t* tok_idx, int idx_ld, int col0, int ncols,
+                            void* out_bf16, int ld, void* stream) {
+  M3L_REQUIRE(src && out_bf16, "patchify: null pointer");
+  if (batch * ncols == 0) return M3L_OK;
+  { const int s_ = check_patch_src(src, "patchify"); if (s_) return s_; }
+  PatchSrc ps = make_patch_src(src);
+  M3L_REQUIRE(ld >= ps.P && ld % 8 == 0, "patchify: row pitch %d must be a multiple of 8 and >= the patch dim %d", ld, ps.P);
+  M3L_REQUIRE(ps.P * sizeof(float) <= 48 * 1024, "patchify: patch dim %d too large", ps.P);
+  M3L_CUDA(launch_kernel(patchify_kernel, dim3(batch * ncols), dim3(128), ps.P * sizeof(float), (cudaStream_t)stream,
+                         ps, tok_idx, idx_ld, col0, ncols, (bf16*)out_bf16, ld));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_row_scatter_add(const void* src_bf16, int batch, int ncols, const int32_t* tok_idx, int idx_ld, int n_total,
+                                   int dim, void* dst_bf16, void* stream) {
+  M3L_REQUIRE(src_bf16 && tok_idx && dst_bf16, "row_scatter_add: null pointer");
+  M3L_REQUIRE(dim % 8 == 0, "row_scatter_add: dim %d must be a multiple of 8", dim);
+  if (batch * ncols == 0) return M3L_OK;
+  M3L_CUDA(launch_kernel(row_scatter_add_kernel, dim3(ln_grid(batch * ncols, 8)), dim3(256), 0, (cudaStream_t)stream,
+                         (const bf16*)src_bf16, batch, ncols, tok_idx, idx_ld, n_total, dim, (bf16*)dst_bf16));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

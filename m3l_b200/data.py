@@ -29,8 +29,11 @@ class RawMap:
 
     __slots__ = ("t", "shape", "offset", "sb", "cg", "sf", "sch", "sy", "sx", "lo", "span")
 
-    def __init__(self, t, shape, offset, sb, cg, sf, sch, sy, sx, lo, span):
-        assert t.is_contiguous() and t.dtype in (torch.float32, torch.uint8), "raw observations must be contiguous fp32 / uint8"
+    def __init__(self, t, shape, offset, sb, cg, sf, sch, sy, sx, lo, span, strided_view=False):
+        # strided_view: `t` is itself a strided view whose data_ptr() is the origin (offset 0); such maps cannot serve
+        # as static graph inputs (clone_inputs) and are only built by callers that read them immediately
+        assert (strided_view or t.is_contiguous()) and t.dtype in (torch.float32, torch.uint8), \
+            "raw observations must be contiguous fp32 / uint8"
         self.t, self.shape, self.offset = t, tuple(shape), int(offset)
         self.sb, self.cg, self.sf, self.sch, self.sy, self.sx = int(sb), int(cg), int(sf), int(sch), int(sy), int(sx)
         self.lo, self.span = float(lo), float(span)

@@ -216,6 +216,18 @@ def patch_layernorm(ps, batch: int, ncols: int, gamma, beta, tok_idx=None, col0:
     return out, xhat
 
 
+def patchify(ps, batch: int, ncols: int, *, ld: int = 0, tok_idx=None, col0: int = 0):
+    """Patch rows bf16 [batch*ncols, ld] in (p1, p2, c) order, zero-padded to the row pitch ld (default: P rounded up to 8)."""
+    P = ps.patch_h * ps.patch_w * ps.channels
+    ld = ld or (P + 7) // 8 * 8
+    dev = ps._keepalive[0].device
+    out = torch.empty((batch * ncols, ld), dtype=torch.bfloat16, device=dev)
+    idx_ld = tok_idx.stride(0) if tok_idx is not None else 0
+    check(_lib.load().m3l_patchify(C.byref(ps), batch, ptr(tok_idx), idx_ld, col0, ncols, ptr(out), ld, current_stream()),
+          "m3l_patchify")
+    return out
+
+
 def layernorm_fwd(x, gamma, beta, *, out=None, out_rows=None, stats=None, want_stats=True, dst_row=None,
                   add0=None, add0_row=None, add1=None, add1_row=None, eps: float = 1e-5):
     _req_cuda(x, gamma, beta)
@@ -346,6 +358,16 @@ def token_finish_bwd(dx0, batch, rows_per_sample, n_total, tok_base, n_mod, n_pe
     check(_lib.load().m3l_token_finish_bwd(ptr(dx0), batch, rows_per_sample, n_total, ptr(slot_of_token), tok_base, n_mod,
                                            n_per, dx0.shape[1], ptr(dtok), current_stream()), "m3l_token_finish_bwd")
     return dtok
+
+
+def row_scatter_add(src, tok_idx, batch, n_total, dst):
+    """dst[b*n_total + tok_idx[b, j]] += src[b*ncols + j]  (bf16 rows; tok_idx int32 [batch, ncols], distinct per sample)."""
+    _req_cuda(src, tok_idx, dst)
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
+    assert tok_idx.dtype == torch.int32 and tok_idx.shape[0] == batch and src.shape[0] == batch * tok_idx.shape[1]
+    check(_lib.load().m3l_row_scatter_add(ptr(src), batch, tok_idx.shape[1], ptr(tok_idx), tok_idx.stride(0), n_total,
+                                          src.shape[1], ptr(dst), current_stream()), "m3l_row_scatter_add")
+    return dst
 
 
 def token_mean_fwd(x, batch, n_tokens):
