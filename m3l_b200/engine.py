@@ -551,10 +551,14 @@ def _embed_bwd(model, A, G, geo, tabs, dx0, B, masked: bool, saved: dict):
 # masked-autoencoder forward / backward
 # --------------------------------------------------------------------------------------------
 def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geometry, training: bool,
-                gflat: Optional[torch.Tensor] = None, capture: Optional[dict] = None):
+                gflat: Optional[torch.Tensor] = None, capture: Optional[dict] = None,
+                tokens_all: Optional[torch.Tensor] = None):
     """Returns (loss_acc fp32[1], ctx).  ctx holds what mae_backward needs (None if not training).
     gflat: the (zeroed) flat gradient buffer the backward pass will use; when given, the MSE kernel
-    already accumulates the head bias gradients (column sums of dpred) into it."""
+    already accumulates the head bias gradients (column sums of dpred) into it.
+    tokens_all: the embedded token sequence of ALL tokens [B*n, dim] (joint step: computed once for this pass and for
+    the feature extractor); the masked encoder's input is then a row gather of it and the embedding's backward is left
+    to the caller (mae_backward_encoder returns the gradient w.r.t. the gathered rows)."""
     cfg, A = model.cfg, model.arena
     dev = A.device
     B = noise.shape[0]
@@ -564,7 +568,12 @@ def mae_forward(model, x: Dict[str, torch.Tensor], noise: torch.Tensor, geo: Geo
     model.last_masked_indices, model.last_unmasked_indices = masked, unmasked
     emb_saved = {"unmasked32": unmasked32} if training else None
     ecm = cfg.early_conv_masking
-    if ecm:
+    if tokens_all is not None:
+        x0 = torch.empty((B * geo.nv, cfg.dim), dtype=torch.bfloat16, device=dev)
+        ops.token_finish(tokens_all, B, geo.n, geo.nv, 0, x0, tok_idx=unmasked32)        # tokens[b, visible] (:256)
+        if training:
+            emb_saved["shared"] = True
+    elif ecm:
         x0 = _embed_fwd_ecm(model, A, geo, tabs, x, B, True, emb_saved, unmasked32=unmasked32)
     else:
         x0 = _embed_fwd(model, A, geo, tabs, x, B, unmasked, True, emb_saved, unmasked32=unmasked32)
@@ -675,10 +684,13 @@ def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
                             dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
                             dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
+    if ctx["emb"].get("shared"):
+        return dx0                       # joint step: the caller adds it into the full-sequence gradient
     if cfg.early_conv_masking:
         _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, True, ctx["emb"], slots=ctx["slots"])
     else:
         _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
+    return None
 
 
 # --------------------------------------------------------------------------------------------
@@ -696,11 +708,13 @@ def embeddings_forward(model, x, geo: Geometry, B: int, training: bool):
     xe = stack_fwd(A, model.enc_spec, x0, B, geo.n, enc_saved)
     out, st = ops.layernorm_fwd(xe, A.f32("encoder.transformer.norm.weight"), A.f32("encoder.transformer.norm.bias"),
                                 want_stats=training)
-    ctx = dict(geo=geo, B=B, tabs=tabs, emb=emb_saved, enc=enc_saved, xe=xe, st=st) if training else None
+    ctx = dict(geo=geo, B=B, tabs=tabs, emb=emb_saved, enc=enc_saved, xe=xe, st=st, tokens_all=x0) if training else None
     return out, ctx
 
 
-def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor):
+def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor, extra_token_grad=None):
+    """extra_token_grad: optional (dx_rows bf16 [B*k, dim], tok_idx int32 [B, k]) added into the gradient of the embedded
+    token sequence before the embedding's backward (the masked-autoencoder branch of the joint step)."""
     A = model.arena
     G = GradView(A, gflat)
     geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
@@ -708,6 +722,8 @@ def embeddings_backward(model, ctx, dout: torch.Tensor, gflat: torch.Tensor):
                             dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
                             dx_colsum=G(last_ff_bias(model.enc_spec)))
     dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.n, ctx["enc"])
+    if extra_token_grad is not None:
+        ops.row_scatter_add(extra_token_grad[0], extra_token_grad[1], B, geo.n, dx0)
     if model.cfg.early_conv_masking:
         _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, False, ctx["emb"])
     else:

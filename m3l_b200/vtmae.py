@@ -529,12 +529,57 @@ class MAEExtractor(_ExtractorBase):
         mae = self.mae_model
         dev = mae.mask_token.device
         obs = {k: torch.as_tensor(v).to(dev) for k, v in observations.items() if k in ('image', 'tactile')}
+        cached = self.__dict__.get("_joint_feats")
+        if cached is not None:                                    # features of joint_mae_loss() on these very observations
+            self._joint_feats = None
+            if cached[0] == _obs_key(obs) and torch.is_grad_enabled():
+                return self.flatten(cached[1])
         if getattr(self, "use_cuda_graph", True):
             if not torch.is_grad_enabled():
                 return self._forward_graph(obs)
             if any(p.requires_grad for p in self.parameters()):
                 return self._forward_graph_grad(obs)
         return self._forward_eager(obs)
+
+    def joint_mae_loss(self, observations, noise=None):
+        """The two passes a PPO / SAC minibatch makes over the SAME observations (ppo_mae.py:255-283: `mae(x)` with
+        backward, then `evaluate_actions` -> this extractor with backward) as ONE pass: the patch embedding of all tokens
+        is computed once, the masked encoder reads its visible rows from it, and in the backward pass the two gradients
+        meet before a single embedding backward.  Returns the MAE loss; the extractor features of the same pass are
+        handed out by the next `forward(observations)` on these observations (the call `evaluate_actions` makes), both
+        attached to one autograd node, so `(ppo_loss + mae_loss).backward()` replays one backward graph.
+        Falls back to `mae(vt_load(obs))` when the extractor uses a different token set (vision_only_control)."""
+        mae = self.mae_model
+        dev = mae.mask_token.device
+        obs = {k: torch.as_tensor(v).to(dev) for k, v in observations.items() if k in ('image', 'tactile')}
+        if self.vision_only_control or not torch.is_grad_enabled():
+            return mae(vt_load_lazy(obs, frame_stack=self.frame_stack), noise=noise)
+        mae.train()
+        A = mae._sync()
+        Av = self.vit_layer.transformer._own_arena()
+        xs, geo, B, _, _ = self._prep(dict(obs))
+        if noise is None:
+            noise = torch.rand(B, geo.n, device=dev)
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        key = ("joint",) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(obs.items())) + (id(A), id(Av))
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if not _entry_free(ent):
+            ent_fn, args = _JointFn, (self, xs, noise, geo, B)
+        else:
+            if ent is None:
+                if len(cache) >= 8:
+                    cache.pop(next(iter(cache)))
+                ent = cache[key] = _capture_joint_graphs(self, obs, noise)
+            for k, v in obs.items():
+                ent.xs[k].copy_(v, non_blocking=True)
+            ent.noise.copy_(noise, non_blocking=True)
+            ent_fn, args = _JointGraphFn, (self, ent)
+        live = tuple(mae.live_param_names(geo, True))
+        vit_names = tuple(Av.names)
+        loss, feats = ent_fn.apply(*args, live, vit_names, *[A.params[k] for k in live], *[Av.params[k] for k in vit_names])
+        self._joint_feats = (_obs_key(obs), feats)
+        return loss
 
     def _forward_graph_grad(self, obs):
         """Training-time call (PPO / SAC evaluate the policy on a minibatch and back-propagate through the extractor:
@@ -716,6 +761,142 @@ class _ExtractorGraphFn(torch.autograd.Function):
         ent.bwd.replay()
         A, Av = ctx.ext.mae_model.arena, ctx.ext.vit_layer.transformer._arena
         gm, gv = ent.gflat.clone(), ent.gflat2.clone()    # .grad must never alias the graph's static buffers
+        return (None, None, None, None, *[A.view(gm, k) for k in ent.live], *[Av.view(gv, k) for k in ent.vit_names])
+
+
+def _obs_key(obs):
+    return tuple((k, v.data_ptr(), tuple(v.shape), v.dtype, v._version) for k, v in sorted(obs.items()))
+
+
+# --------------------------------------------------------------------------------------------
+# joint MAE + feature-extractor pass over one minibatch (ppo_mae.py:255-283)
+# --------------------------------------------------------------------------------------------
+def _joint_forward(ext, xs, noise, geo, B, gflat_m):
+    """-> (loss_acc [1], feats [B, dim], ctx).  gflat_m: gradient buffer of the masked-autoencoder branch."""
+    mae, tr = ext.mae_model, ext.vit_layer.transformer
+    Av = tr._arena
+    emb, c = engine.embeddings_forward(mae, xs, geo, B, training=True)          # embeds ALL tokens once; encoder over them
+    loss_acc, cm = engine.mae_forward(mae, xs, noise, geo, training=True, gflat=gflat_m, tokens_all=c["tokens_all"])
+    spec = engine.StackSpec("t", tr.dim, tr.depth, tr.heads, tr.dim_head, tr.mlp_dim)
+    saved = []
+    xe = engine.stack_fwd(Av, spec, emb, B, geo.n, saved)
+    y, st = ops.layernorm_fwd(xe, Av.f32("t.norm.weight"), Av.f32("t.norm.bias"), want_stats=True)
+    feats = ops.token_mean_fwd(y, B, geo.n)
+    return loss_acc, feats, (c, cm, spec, saved, xe, st, B, geo.n)
+
+
+def _joint_backward(ext, ctx, g_loss, g_feats, gflat, gflat_m, gflat2):
+    """gflat: MAE-arena gradients of the extractor branch and of the shared embedding; gflat_m: of the masked-autoencoder
+    branch (scaled by the loss gradient, then added into gflat); gflat2: extra-block arena gradients."""
+    mae, Av = ext.mae_model, ext.vit_layer.transformer._arena
+    c, cm, spec, saved, xe, st, B, n = ctx
+    Gv = engine.GradView(Av, gflat2)
+    dy = ops.token_mean_bwd(g_feats, B, n)
+    dxe = ops.layernorm_bwd(dy, xe, st, Av.f32("t.norm.weight"), dgamma=Gv("t.norm.weight"), dbeta=Gv("t.norm.bias"),
+                            dx_colsum=Gv(engine.last_ff_bias(spec)))
+    demb = engine.stack_bwd(Av, Gv, spec, dxe, B, n, saved)
+    engine.mae_backward_decoder(mae, cm, gflat_m)
+    dx0 = engine.mae_backward_encoder(mae, cm, gflat_m)
+    dx0.mul_(g_loss.to(dx0.dtype))
+    gflat_m.mul_(g_loss)
+    engine.embeddings_backward(mae, c, demb, gflat, extra_token_grad=(dx0, cm["emb"]["unmasked32"]))
+    gflat.add_(gflat_m)
+
+
+class _JointFn(torch.autograd.Function):
+    """Eager form (owns its activations): used when a graph-replayed joint pass is still outstanding."""
+
+    @staticmethod
+    def forward(ctx, ext, xs, noise, geo, B, live, vit_names, *params):
+        A = ext.mae_model.arena
+        gm = A.new_grad_buffer()
+        loss_acc, feats, c = _joint_forward(ext, xs, noise, geo, B, gm)
+        ctx.c = (ext, c, gm, live, vit_names)
+        ext.mae_model.last_masked_indices = ext.mae_model.last_masked_indices.clone()
+        return loss_acc.reshape(()), feats
+
+    @staticmethod
+    def backward(ctx, g_loss, g_feats):
+        ext, c, gm, live, vit_names = ctx.c
+        A, Av = ext.mae_model.arena, ext.vit_layer.transformer._arena
+        g, gv = A.new_grad_buffer(), Av.new_grad_buffer()
+        B, dim = c[6], ext.vit_layer.transformer.dim
+        gl = g_loss if g_loss is not None else torch.zeros((), device=A.device)
+        gf = g_feats.to(torch.float32).contiguous() if g_feats is not None else torch.zeros((B, dim), device=A.device)
+        _joint_backward(ext, c, gl.reshape(()).to(torch.float32), gf, g, gm, gv)
+        return (None,) * 7 + tuple(A.view(g, k) for k in live) + tuple(Av.view(gv, k) for k in vit_names)
+
+
+def _capture_joint_graphs(ext, obs, noise):
+    mae, tr = ext.mae_model, ext.vit_layer.transformer
+    ent = _GraphEntry()
+    ent.xs = {k: v.clone() for k, v in obs.items()}
+    ent.noise = noise.clone()
+    ent.gen, ent.consumed, ent.node = 0, True, None
+    xs, geo, B, A, Av = ext._prep(dict(ent.xs))
+    ent.live, ent.vit_names = tuple(mae.live_param_names(geo, True)), tuple(Av.names)
+    ent.gflat, ent.gflat2 = A.new_grad_buffer(), Av.new_grad_buffer()
+    gflat_m = A.new_grad_buffer()
+    ent.gout = (torch.ones((), dtype=torch.float32, device=A.device), torch.zeros((B, tr.dim), dtype=torch.float32, device=A.device))
+
+    def fwd():
+        xs, geo, B, _, _ = ext._prep(dict(ent.xs))
+        gflat_m.zero_()
+        loss_acc, feats, ent.ctx = _joint_forward(ext, xs, ent.noise, geo, B, gflat_m)
+        ent.loss = (loss_acc, feats)
+        ent.masked, ent.unmasked = mae.last_masked_indices, mae.last_unmasked_indices
+
+    def bwd():
+        ent.gflat.zero_()
+        ent.gflat2.zero_()
+        _joint_backward(ext, ent.ctx, ent.gout[0], ent.gout[1], ent.gflat, gflat_m, ent.gflat2)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fwd()
+        bwd()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    pool = torch.cuda.graph_pool_handle()
+    ent.fwd, ent.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with engine.capture_guard():
+        with torch.cuda.graph(ent.fwd, pool=pool):
+            fwd()
+        with torch.cuda.graph(ent.bwd, pool=pool):
+            bwd()
+    return ent
+
+
+class _JointGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ext, ent, live, vit_names, *params):
+        ent.gen += 1
+        ent.consumed = False
+        ent.node = _weak(ctx)
+        ent.fwd.replay()
+        mae = ext.mae_model
+        mae.last_masked_indices, mae.last_unmasked_indices = ent.masked.clone(), ent.unmasked.clone()
+        ctx.ext, ctx.ent, ctx.gen = ext, ent, ent.gen
+        return ent.loss[0].reshape(()).clone(), ent.loss[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_feats):
+        ent = ctx.ent
+        if ctx.gen != ent.gen or ent.consumed:
+            raise M3LError("backward through a CUDA-graph replayed joint pass whose saved activations were overwritten")
+        ent.consumed = True
+        if g_loss is not None:
+            ent.gout[0].copy_(g_loss.reshape(()))
+        else:
+            ent.gout[0].zero_()
+        if g_feats is not None:
+            ent.gout[1].copy_(g_feats)
+        else:
+            ent.gout[1].zero_()
+        ent.bwd.replay()
+        A, Av = ctx.ext.mae_model.arena, ctx.ext.vit_layer.transformer._arena
+        gm, gv = ent.gflat.clone(), ent.gflat2.clone()
         return (None, None, None, None, *[A.view(gm, k) for k in ent.live], *[Av.view(gv, k) for k in ent.vit_names])
 
 

@@ -419,3 +419,59 @@ def test_cpu_module_fails_loudly():
     mae = build_product(O.VTMAEConfig(depth=1, decoder_depth=1), device="cpu")
     with pytest.raises(M3LError):
         mae({"image": torch.zeros(1, 12, 64, 64)})
+
+
+@pytest.mark.parametrize("ecm", [False, True])
+def test_joint_mae_and_extractor_pass_matches_separate_passes(ecm):
+    """SURVEY.md 8(f)-2 / ppo_mae.py:255-283: `mae(x).backward()` and the extractor forward / backward of
+    `evaluate_actions` over the same minibatch as ONE pass (shared patch embedding): same loss, same features, and the
+    same accumulated gradients as the two separate passes (which are checked against the oracle above)."""
+    from m3l_b200 import MAEExtractor
+    from m3l_b200.data import vt_load_lazy
+    cfg = O.VTMAEConfig(depth=2, decoder_depth=2, early_conv_masking=ecm)
+    sd = O.init_state_dict(cfg, seed=8)
+    gen = torch.Generator().manual_seed(21)
+    B = 6
+    mae = build_product(cfg, weights=sd)
+    ext = MAEExtractor(None, mae, cfg.dim, False, cfg.frame_stack).to(DEV)
+    obs = {"image": torch.rand(B, cfg.frame_stack, 64, 64, 3, generator=gen).to(DEV),
+           "tactile": (torch.rand(B, cfg.frame_stack, 6, 32, 32, generator=gen) * 2 - 1).to(DEV)}
+    noise = O.tie_free_noise(B, 192, gen, [64] * 3).to(DEV)
+    w = torch.randn(B, cfg.dim, generator=gen).to(DEV)
+
+    def grads():
+        return {k: p.grad.clone() for k, p in ext.named_parameters() if p.grad is not None}
+
+    # separate passes (the reference's sequence)
+    ext.zero_grad(set_to_none=True)
+    l_sep = mae(vt_load_lazy(obs, frame_stack=cfg.frame_stack), noise=noise)
+    l_sep.backward()
+    f_sep = ext(obs)
+    (f_sep * w).sum().backward()
+    g_sep = grads()
+    for rep in range(3):          # graph capture, replay, replay
+        ext.zero_grad(set_to_none=True)
+        l_j = ext.joint_mae_loss(obs, noise=noise)
+        f_j = ext(obs)
+        assert f_j.grad_fn is l_j.grad_fn or type(f_j.grad_fn).__name__ != type(f_sep.grad_fn).__name__
+        assert torch.equal(l_j.detach(), l_sep.detach())
+        assert torch.allclose(f_j.detach(), f_sep.detach(), rtol=0, atol=0)
+        ((f_j * w).sum() + l_j).backward()
+        g_j = grads()
+        assert g_j.keys() == g_sep.keys()
+        for k in g_sep:
+            c = cos(g_j[k], g_sep[k])
+            assert c >= 0.9995, (k, c)
+            assert torch.allclose(g_j[k], g_sep[k], rtol=5e-2, atol=2e-3 * float(g_sep[k].abs().max()) + 1e-7), k
+    # outstanding joint pass -> the next one takes the eager path; both backwards work
+    ext.zero_grad(set_to_none=True)
+    l1 = ext.joint_mae_loss(obs, noise=noise)
+    f1 = ext(obs)
+    l2 = ext.joint_mae_loss(obs, noise=noise)
+    f2 = ext(obs)
+    assert torch.equal(l1.detach(), l2.detach())
+    ((f1 * w).sum() + l1).backward()
+    ((f2 * w).sum() + l2).backward()
+    g2 = grads()
+    for k in g_sep:
+        assert cos(g2[k], g_sep[k]) >= 0.9995, k
