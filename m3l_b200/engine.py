@@ -22,7 +22,16 @@ from .arena import ParamArena
 
 import os
 
-_SM_COUNT = 148
+_SM_COUNT_CACHE = {}
+
+
+def _sm_count() -> int:
+    """SMs of the current device (148 on B200; MIG slices and other SKUs differ): sizes the single-wave wgrad tiling."""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    n = _SM_COUNT_CACHE.get(dev)
+    if n is None:
+        n = _SM_COUNT_CACHE[dev] = torch.cuda.get_device_properties(dev).multi_processor_count if dev >= 0 else 148
+    return n
 # M3L_FUSED_MLP=0: the unfused LayerNorm / FF1+GELU / FF2 kernels instead of csrc/rowblock.cu (A/B measurements)
 _FUSED_MLP = os.environ.get("M3L_FUSED_MLP", "1") != "0"
 
@@ -47,7 +56,7 @@ def _wgrad_tiling(m_out: int, n_out: int, k_tokens: int):
     bn = 256 if n_out % 256 == 0 else (128 if n_out % 128 == 0 else 64)
     tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
     kb = (k_tokens + 63) // 64
-    s = max(1, _SM_COUNT // tiles)
+    s = max(1, _sm_count() // tiles)
     return bn, max(1, min(s, kb))
 
 

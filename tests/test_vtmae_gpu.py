@@ -475,3 +475,71 @@ def test_joint_mae_and_extractor_pass_matches_separate_passes(ecm):
     g2 = grads()
     for k in g_sep:
         assert cos(g2[k], g_sep[k]) >= 0.9995, k
+
+
+def test_ppo_mae_update_sequence_with_shared_adam():
+    """The MAE-related lines of one PPO_MAE minibatch update (/root/reference/models/ppo_mae.py:236-283, non-separate
+    optimizer): policy.optimizer.zero_grad(); mae_loss = mae(vt_load(obs)); mae_loss.backward(); features =
+    extractor(obs) -> policy loss; loss.backward(); clip_grad_norm_; policy.optimizer.step() with ONE torch Adam over
+    all policy parameters (extractor incl. the MAE).  Product modules driven exactly like that for three updates must
+    track the oracle driven the same way: losses within 1e-2, parameters after the updates cosine >= 0.999."""
+    from m3l_b200 import MAEExtractor
+    from m3l_b200.data import vt_load
+    cfg = O.VTMAEConfig(depth=2, decoder_depth=2)
+    sd = O.init_state_dict(cfg, seed=12)
+    gen = torch.Generator().manual_seed(33)
+    B, F = 8, cfg.frame_stack
+    mae = build_product(cfg, weights=sd)
+    ext = MAEExtractor(None, mae, cfg.dim, False, F).to(DEV)
+    head = torch.nn.Linear(cfg.dim, 3).to(DEV)                       # stands in for the actor / critic heads
+    opt = torch.optim.Adam(list(ext.parameters()) + list(head.parameters()), lr=3e-4)
+    # oracle side: same weights as leaf tensors
+    vit_sd = {k[len("vit_layer."):]: v.detach().cpu().clone().requires_grad_(True) for k, v in ext.state_dict().items()
+              if k.startswith("vit_layer.transformer")}
+    osd = {k: v.clone() for k, v in sd.items()}
+    for k in O.param_keys(osd):
+        osd[k].requires_grad_(True)
+    ohead = torch.nn.Linear(cfg.dim, 3)
+    ohead.load_state_dict({k: v.cpu() for k, v in head.state_dict().items()})
+    oparams = [osd[k] for k in O.param_keys(osd)] + list(vit_sd.values()) + list(ohead.parameters())
+    oopt = torch.optim.Adam(oparams, lr=3e-4)
+    for it in range(3):
+        obs = {"image": torch.rand(B, F, 64, 64, 3, generator=gen), "tactile": torch.rand(B, F, 6, 32, 32, generator=gen) * 2 - 1}
+        noise = O.tie_free_noise(B, 192, gen, [64] * 3)
+        tgt = torch.randn(B, 3, generator=gen)
+        # ---- product, the reference's call sequence
+        observations = {k: v.to(DEV) for k, v in obs.items()}
+        observations["image"] = observations["image"].permute(0, 2, 3, 1, 4).reshape(B, 64, 64, -1)
+        observations["tactile"] = observations["tactile"].reshape(B, -1, 32, 32)
+        opt.zero_grad()
+        x = vt_load({k: v.clone() for k, v in observations.items()}, frame_stack=F)
+        mae_loss = mae(x, noise=noise.to(DEV))
+        mae_loss.backward()
+        feats = ext(observations)
+        loss = ((head(feats) - tgt.to(DEV)) ** 2).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(ext.parameters()) + list(head.parameters()), 0.5)
+        opt.step()
+        # ---- oracle, same sequence
+        oopt.zero_grad()
+        o4 = {"image": obs["image"].permute(0, 2, 3, 1, 4).reshape(B, 64, 64, -1), "tactile": obs["tactile"].reshape(B, -1, 32, 32)}
+        ox = O.vt_load({k: v.clone() for k, v in o4.items()}, frame_stack=F)
+        ol = O.vtmae_forward(osd, cfg, ox, noise)
+        ol.backward()
+        of = O.extractor_forward(osd, cfg, vit_sd, {k: v.clone() for k, v in obs.items()}, vision_only_control=False)
+        oloss = ((ohead(of) - tgt) ** 2).mean()
+        oloss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in oparams if p.grad is not None], 0.5)
+        oopt.step()
+        assert abs(float(mae_loss) - float(ol)) <= 1e-2 * abs(float(ol)), (it, float(mae_loss), float(ol))
+        assert abs(float(loss) - float(oloss)) <= 2e-2 * abs(float(oloss)) + 1e-4, (it, float(loss), float(oloss))
+    named = dict(mae.named_parameters(remove_duplicate=False))
+    moved = 0
+    for k in O.param_keys(osd):
+        if k in named and osd[k].grad is not None:
+            d_ref = osd[k].detach() - sd[k]
+            d_got = named[k].detach().cpu() - sd[k]
+            if float(d_ref.norm()) > 0:
+                moved += 1
+                assert cos(d_got, d_ref) >= 0.99, (k, cos(d_got, d_ref))          # the UPDATE directions agree
+    assert moved > 50

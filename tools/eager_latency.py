@@ -39,3 +39,20 @@ for use_graph in (False, True):
         for _ in range(10): it()
         torch.cuda.synchronize()
         print(f"PPO-style minibatch B={B:4d} graphs={use_graph}: extractor fwd+bwd + mae fwd+bwd = {(time.perf_counter() - t0) / 10 * 1e3:.3f} ms")
+
+# joint pass: one embedding of all tokens feeds the masked MAE pass and the extractor
+ext.use_cuda_graph = True
+mae.use_cuda_graph = True
+for B in (64, 512):
+    g = torch.Generator().manual_seed(B)
+    obs = {"image": torch.rand(B, 4, 64, 64, 3, generator=g).to(dev), "tactile": (torch.rand(B, 4, 6, 32, 32, generator=g) * 2 - 1).to(dev)}
+    w = torch.randn(B, 256, device=dev)
+    def jt():
+        ext.zero_grad(set_to_none=True)
+        l = ext.joint_mae_loss(obs)
+        ((ext(obs) * w).sum() + l).backward()
+    for _ in range(3): jt()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10): jt()
+    torch.cuda.synchronize()
+    print(f"PPO-style minibatch B={B:4d} JOINT pass (graphs): {(time.perf_counter() - t0) / 10 * 1e3:.3f} ms")
