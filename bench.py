@@ -509,6 +509,154 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# secondary workloads of BASELINE.json (configs[2], configs[3]) - strong scaling of a fixed global batch
+# ------------------------------------------------------------------------------------------------
+def run_other_config(args):
+    """--config 3: vision_only_control VTMAE (image tokens only), global batch 1024 split over the ranks.
+    --config 4: DINO-tac-MAE variant, global batch 512: tactile-only MAE train step (70x70 maps, patch 14, dim 384)
+                + the frozen DINOv2 ViT-S/14-reg forward on the mid frame of the image stack (feature branch of
+                models/pretrain_models_dino_cat_mae.py:884-889; random weights: torch.hub is unreachable offline).
+    value = device-resident samples/s; e2e = from pinned host rollout batches (raw observations, H2D inside)."""
+    import torch
+    import torch.distributed as dist
+    from m3l_b200 import VTT, VTMAE
+    from m3l_b200.trainer import FusedTrainer
+    from m3l_b200.data import vt_load_lazy
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    dino = None
+    if args.config == 3:
+        gb, flops, size, n_tok = 1024, 1140.5e6, 64, 64
+        name = "vision_only_control VTMAE train step (image tokens only), global batch 1024 (BASELINE.json configs[2])"
+        enc = VTT(image_size=(64, 64), tactile_size=(32, 32), image_patch_size=8, tactile_patch_size=4, dim=256, depth=4,
+                  heads=4, mlp_dim=512, num_tactiles=0, image_channels=12, tactile_channels=12, frame_stack=4)
+        mae = VTMAE(encoder=enc, decoder_dim=256, masking_ratio=0.95, decoder_depth=3, decoder_heads=4, num_tactiles=0,
+                    frame_stack=4).to(dev)
+    else:
+        from m3l_b200.dinov2 import DinoV2, mid_frame_view
+        gb, flops, size, n_tok = 512, 2163.5e6 + 1285.3e6, 70, 50
+        name = ("DINO-tac-MAE: tactile-only VTMAE train step (70x70, patch 14, dim 384, r 0.8) + frozen DINOv2 ViT-S/14-reg "
+                "forward on the mid frame, global batch 512 (BASELINE.json configs[3])")
+        enc = VTT(image_size=(70, 70), tactile_size=(70, 70), image_patch_size=14, tactile_patch_size=14, dim=384, depth=4,
+                  heads=4, mlp_dim=768, num_tactiles=2, image_channels=12, tactile_channels=12, frame_stack=4)
+        mae = VTMAE(encoder=enc, decoder_dim=384, masking_ratio=0.8, decoder_depth=3, decoder_heads=4, num_tactiles=2,
+                    frame_stack=4).to(dev)
+        dino = DinoV2().to(dev).eval()
+    assert gb % world == 0
+    B = gb // world
+    mae._sync()
+    trainer = FusedTrainer(mae, lr=1e-4)
+
+    def synth(seed):
+        g = torch.Generator().manual_seed(seed)
+        obs = {"image": torch.rand(B, 4, size, size, 3, generator=g).pin_memory()}
+        if args.config == 4:
+            obs["tactile"] = (torch.rand(B, 4, 6, size, size, generator=g) * 2 - 1).pin_memory()
+        return obs, torch.rand(B, n_tok, generator=g).pin_memory()
+
+    def step(views, noise):
+        if args.config == 3:
+            return trainer.step({"image": views["image"]}, noise=noise)
+        loss = trainer.step({k: v for k, v in views.items() if k.startswith("tactile")}, noise=noise)
+        dino(mid_frame_view(views["image"], 4))
+        return loss
+
+    nbuf = 3
+    host = [synth(99 + rank * 10 + i) for i in range(nbuf)]
+    devb = [(vt_load_lazy({k: v.to(dev) for k, v in o.items()}, frame_stack=4), n.to(dev)) for o, n in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(*devb[i % nbuf])
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        s.record()
+        for i in range(args.steps):
+            loss = step(*devb[i % nbuf])
+        e.record()
+        barrier()
+    t = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = gb / (ms_per_step * 1e-3)
+    # e2e: host rollout batch -> H2D (prefetched on a copy stream) -> step; loss read back every step
+    copy_stream = torch.cuda.Stream()
+    stage = [({k: torch.empty_like(v, device=dev) for k, v in host[0][0].items()}, torch.empty(B, n_tok, device=dev)) for _ in range(2)]
+    views = [vt_load_lazy(st[0], frame_stack=4) for st in stage]
+    ready, consumed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in consumed:
+        ev.record()
+
+    def prefetch(i):
+        slot = i % 2
+        copy_stream.wait_event(consumed[slot])
+        with torch.cuda.stream(copy_stream):
+            for k, v in host[i % nbuf][0].items():
+                stage[slot][0][k].copy_(v, non_blocking=True)
+            stage[slot][1].copy_(host[i % nbuf][1], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+    barrier()
+    s.record()
+    prefetch(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        l = step(views[i % 2], stage[i % 2][1])
+        consumed[i % 2].record()
+        loss_host[i:i + 1].copy_(l.reshape(1), non_blocking=True)
+    e.record()
+    barrier()
+    assert bool(torch.isfinite(loss_host).all())
+    t = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = gb * args.steps / (float(t.item()) * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + B * n_tok * 4
+    replicas_identical = None
+    if world > 1:
+        flat = mae.arena.flat
+        chk = torch.stack([flat.view(torch.int32).to(torch.int64).sum(), (flat.view(torch.int32).to(torch.int64) ** 2 % 1000003).sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = all(torch.equal(c, allc[0]) for c in allc)
+    if rank == 0:
+        tfl = value / world * flops / 1e12
+        line = {"metric": "VTMAE train samples/sec (fwd+bwd+AdamW)", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": name, "global_batch": gb, "batch_per_gpu": B, "parallelism": f"dp{world}", "cuda_graph": True,
+                           "loss_last_step": float(loss.item())},
+                "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches_per_step": (trainer.kernel_launches_per_step or 0) + (4 + 7 * len(dino.blocks) + 1 if dino is not None else 0),
+                "step_tensor_utilisation": {"achieved": tfl, "unit": "TFLOP/s per GPU", "peak": peaks["tf_sustained"],
+                                            "frac": tfl / peaks["tf_sustained"]}}
+        line["gpu_launches"] = line["gpu_launches_per_step"] * args.steps
+        if replicas_identical is not None:
+            line["replicas_identical"] = replicas_identical
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -517,11 +665,15 @@ def main():
     ap.add_argument("--impl", default="m3l_b200", choices=["m3l_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly (for ncu launch lists)")
     ap.add_argument("--profile", action="store_true", help="device-resident loop only (no e2e / CPU baseline legs)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json workload: 2 = headline (configs[1]); 3 = vision-only, global batch 1024; 4 = DINO-tac-MAE, global batch 512")
     ap.add_argument("--sustain-seconds", type=float, default=3.0,
                     help="also time the device-resident loop for at least this long (0 disables)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config in (3, 4):
+        run_other_config(args)
     else:
         run_gpu_arm(args)
 

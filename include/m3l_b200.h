@@ -302,7 +302,11 @@ int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_s
 typedef struct m3l_matrix_desc {
   int64_t src_offset; /* elements from src_base */
   int64_t dst_offset; /* elements from dst_base */
-  int32_t rows, cols; /* of the source, row-major */
+  int32_t rows, cols; /* Momentum (EMA) teacher update over flat fp32 arenas: teacher = teacher * beta + (1 - beta) * student
+ * (/root/reference/tactile_ssl/utils/ema.py:6-19, called from models/vtdino.py:159-173 after every train batch). */
+int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, void* stream);
+
+/* of the source, row-major */
 } m3l_matrix_desc;
 int m3l_cast_bf16(const float* src, void* dst_bf16, size_t count, void* stream);
 int m3l_transpose_cast_bf16(const float* src_base, void* dst_base_bf16, const m3l_matrix_desc* descs_dev,

@@ -15,6 +15,9 @@ def __getattr__(name):
     if name in ("DinoV2", "DinoCatMAEExtractor"):
         from . import dinov2
         return getattr(dinov2, name)
+    if name in ("VTDINO", "DINOHead", "DINOLoss", "update_moving_average"):
+        from . import vtdino
+        return getattr(vtdino, name)
     if name == "VTTDino":
         from .vtt import VTT as VTTDino
         return VTTDino

@@ -114,5 +114,5 @@ EXPORTED_SYMBOLS = (
     "m3l_mse_loss", "m3l_colsum", "m3l_ln_param_grad", "m3l_attention_fwd", "m3l_attention_bwd",
     "m3l_grad_sumsq", "m3l_optimizer_step_begin", "m3l_clip_adamw", "m3l_cast_bf16",
     "m3l_transpose_cast_bf16", "m3l_token_mean_fwd", "m3l_token_mean_bwd",
-    "m3l_im2col", "m3l_col2im_relu", "m3l_token_finish", "m3l_token_finish_bwd", "m3l_vt_load", "m3l_patchify", "m3l_row_scatter_add",
+    "m3l_im2col", "m3l_col2im_relu", "m3l_token_finish", "m3l_token_finish_bwd", "m3l_vt_load", "m3l_patchify", "m3l_row_scatter_add", "m3l_ema_update",
 )

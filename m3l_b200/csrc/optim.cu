@@ -118,6 +118,27 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
     dst[i] = __float2bfloat16(src[i]);
 }
 
+// teacher[i] = teacher[i] * beta + (1 - beta) * student[i] over a flat fp32 arena (DINO momentum teacher:
+// tactile_ssl/utils/ema.py update_moving_average, called from models/vtdino.py:159-173); same operation order as the
+// reference (old * beta + (1.0 - beta) * new) so the fp32 results are bit-identical
+__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, size_t n, float beta) {
+  pdl_wait();
+  pdl_trigger();
+  const float omb = 1.0f - beta;
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 t = reinterpret_cast<float4*>(teacher)[i];
+    const float4 s = reinterpret_cast<const float4*>(student)[i];
+    t.x = __fadd_rn(__fmul_rn(t.x, beta), __fmul_rn(omb, s.x));
+    t.y = __fadd_rn(__fmul_rn(t.y, beta), __fmul_rn(omb, s.y));
+    t.z = __fadd_rn(__fmul_rn(t.z, beta), __fmul_rn(omb, s.z));
+    t.w = __fadd_rn(__fmul_rn(t.w, beta), __fmul_rn(omb, s.w));
+    reinterpret_cast<float4*>(teacher)[i] = t;
+  }
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    teacher[i] = __fadd_rn(__fmul_rn(teacher[i], beta), __fmul_rn(omb, student[i]));
+}
+
 // transposed bf16 copies of a table of fp32 matrices: dst[c, r] = src[r, c]
 __global__ void transpose_cast_kernel(const float* __restrict__ src_base, bf16* __restrict__ dst_base,
                                       const m3l_matrix_desc* __restrict__ descs) {
@@ -202,6 +223,15 @@ extern "C" int m3l_transpose_cast_bf16(const float* src_base, void* dst_base_bf1
   if (count == 0) return M3L_OK;
   M3L_CUDA(launch_kernel(transpose_cast_kernel, dim3(dim3(64, count)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, src_base, (bf16*)dst_base_bf16,
                                                                                   descs_dev));
+  M3L_CUDA(cudaGetLastError());
+  return M3L_OK;
+}
+
+extern "C" int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, void* stream) {
+  M3L_REQUIRE(teacher && student, "ema_update: null pointer");
+  M3L_REQUIRE((((uintptr_t)teacher | (uintptr_t)student) & 15) == 0, "ema_update: pointers must be 16-byte aligned");
+  if (count == 0) return M3L_OK;
+  M3L_CUDA(launch_kernel(ema_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, teacher, student, count, beta));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -33,6 +33,18 @@ def split_buckets(live_names: Sequence[str]) -> Tuple[List[str], List[str]]:
     return dec, enc
 
 
+ENCODER_STACK_PREFIX = "encoder.transformer."
+
+
+def split_three(live_names: Sequence[str]) -> Tuple[List[str], List[str], List[str]]:
+    """(heads + decoder, encoder transformer, token embeddings) in the order their gradients become final in the
+    backward pass: three all-reduce buckets, each overlapped with the next phase of the backward."""
+    dec, enc = split_buckets(live_names)
+    stack = [k for k in enc if k.startswith(ENCODER_STACK_PREFIX)]
+    emb = [k for k in enc if not k.startswith(ENCODER_STACK_PREFIX)]
+    return dec, stack, emb
+
+
 def allreduce_ranges(flat: torch.Tensor, ranges: Sequence[Tuple[int, int]], group=None, average: bool = True):
     """All-reduces flat[s:e] for every range (in place).  AVG where the backend has it (NCCL), else
     SUM followed by a scale (gloo)."""

@@ -680,10 +680,11 @@ def mae_backward_decoder(model, ctx, gflat: torch.Tensor):
         wgrad(dd, ctx["enc_out"], G("enc_to_dec.weight"))
 
 
-def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
-    cfg, A = model.cfg, model.arena
+def mae_backward_encoder_stack(model, ctx, gflat: torch.Tensor):
+    """Encoder transformer part of the backward; returns the gradient w.r.t. the encoder input rows."""
+    A = model.arena
     G = GradView(A, gflat)
-    geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
+    geo, B = ctx["geo"], ctx["B"]
     dd = ctx["dd"]
     if model.has_enc_to_dec:
         denc = ops.gemm(dd, A.bf_t("enc_to_dec.weight"))
@@ -692,13 +693,25 @@ def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
     dxe = ops.layernorm_bwd(denc, ctx["xe"], ctx["st_enc"], A.f32("encoder.transformer.norm.weight"),
                             dgamma=G("encoder.transformer.norm.weight"), dbeta=G("encoder.transformer.norm.bias"),
                             dx_colsum=G(last_ff_bias(model.enc_spec)))
-    dx0 = stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
-    if ctx["emb"].get("shared"):
-        return dx0                       # joint step: the caller adds it into the full-sequence gradient
+    return stack_bwd(A, G, model.enc_spec, dxe, B, geo.nv, ctx["enc"])
+
+
+def mae_backward_embed(model, ctx, gflat: torch.Tensor, dx0: torch.Tensor):
+    """Token-embedding part of the backward (patch embeddings / conv stems, modality and position tables)."""
+    cfg, A = model.cfg, model.arena
+    G = GradView(A, gflat)
+    geo, B, tabs = ctx["geo"], ctx["B"], ctx["tabs"]
     if cfg.early_conv_masking:
         _embed_bwd_ecm(model, A, G, geo, tabs, dx0, B, True, ctx["emb"], slots=ctx["slots"])
     else:
         _embed_bwd(model, A, G, geo, tabs, dx0, B, True, ctx["emb"])
+
+
+def mae_backward_encoder(model, ctx, gflat: torch.Tensor):
+    dx0 = mae_backward_encoder_stack(model, ctx, gflat)
+    if ctx["emb"].get("shared"):
+        return dx0                       # joint step: the caller adds it into the full-sequence gradient
+    mae_backward_embed(model, ctx, gflat, dx0)
     return None
 
 

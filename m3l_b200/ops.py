@@ -444,6 +444,15 @@ def clip_adamw(params, grads, exp_avg, exp_avg_sq, state, *, lr, betas=(0.9, 0.9
           "m3l_clip_adamw")
 
 
+def ema_update(teacher, student, beta: float):
+    """teacher = teacher * beta + (1 - beta) * student, in place, over flat fp32 tensors."""
+    _req_cuda(teacher, student)
+    assert teacher.dtype == torch.float32 and student.dtype == torch.float32 and teacher.numel() == student.numel()
+    assert teacher.is_contiguous() and student.is_contiguous()
+    check(_lib.load().m3l_ema_update(ptr(teacher), ptr(student), C.c_size_t(teacher.numel()), C.c_float(beta), current_stream()),
+          "m3l_ema_update")
+
+
 def cast_bf16(src, dst):
     check(_lib.load().m3l_cast_bf16(ptr(src), ptr(dst), C.c_size_t(src.numel()), current_stream()), "m3l_cast_bf16")
 

@@ -9,6 +9,7 @@ the encoder backward on a side stream, then encoder+embeddings.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -69,6 +70,9 @@ class FusedTrainer:
         self.opt = FusedAdamW(self, lr, betas, eps, weight_decay)
         self._graphs: Dict = {}
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # M3L_DP_ONE_GRAPH=0: keep the NCCL calls outside the graphs (four graph replays per step, host-launched
+        # all-reduces between them) - the fallback if a NCCL build cannot be stream-captured
+        self.one_graph_dp = os.environ.get("M3L_DP_ONE_GRAPH", "1") != "0"
         self.kernel_launches_per_step = None
 
     def optimizer_facade(self):
@@ -76,10 +80,11 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------------------------
     def _plan(self, geo):
+        """(live names, all live ranges, [bucket ranges]) - three buckets in the order their gradients become final:
+        heads + decoder, encoder transformer, token embeddings (dp.split_three)."""
         model, A = self.model, self.model.arena
         live = model.live_param_names(geo, True)
-        dec_names, enc_names = dp.split_buckets(live)
-        return live, A.ranges(live), A.ranges(dec_names), A.ranges(enc_names)
+        return live, A.ranges(live), [A.ranges(names) for names in dp.split_three(live)]
 
     def _phase_a(self, xs, noise, geo, box):
         self.gflat.zero_()
@@ -89,7 +94,30 @@ class FusedTrainer:
         box["loss"], box["ctx"] = loss_acc, ctx
 
     def _phase_b(self, box):
-        engine.mae_backward_encoder(self.model, box["ctx"], self.gflat)
+        self._phase_b1(box)
+        self._phase_b2(box)
+
+    def _phase_b1(self, box):
+        box["dx0"] = engine.mae_backward_encoder_stack(self.model, box["ctx"], self.gflat)
+
+    def _phase_b2(self, box):
+        engine.mae_backward_embed(self.model, box["ctx"], self.gflat, box["dx0"])
+
+    def _dp_sequence(self, xs, noise, geo, box, ranges, buckets):
+        """The data-parallel step as one stream program: each bucket's all-reduce runs on the communication stream
+        beside the next phase of the backward (event fork / join, so the whole sequence - NCCL included - can be
+        captured into ONE CUDA graph): decoder bucket || encoder-stack backward, encoder-stack bucket || embedding
+        backward, embedding bucket, then clip + AdamW on the averaged gradients."""
+        main = torch.cuda.current_stream()
+        phases = (lambda: self._phase_a(xs, noise, geo, box), lambda: self._phase_b1(box), lambda: self._phase_b2(box))
+        for phase, rng in zip(phases, buckets):
+            phase()
+            if rng:
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    dp.allreduce_ranges(self.gflat, rng, group=self.pg)
+        main.wait_stream(self.comm_stream)
+        self._phase_c(ranges)
 
     def _push_hyper(self):
         """Optimizer hyper-parameters -> device buffer (only when they changed): the kernels read them at run time,
@@ -113,11 +141,6 @@ class FusedTrainer:
                            hyper=self.hyper)
         A.refresh_shadows()
 
-    def _allreduce(self, ranges, after_event):
-        self.comm_stream.wait_event(after_event)
-        with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_ranges(self.gflat, ranges, group=self.pg)
-
     # ------------------------------------------------------------------------------------
     def step(self, x, noise=None, use_vision=True, use_tactile=True):
         model = self.model
@@ -126,7 +149,7 @@ class FusedTrainer:
         if noise is None:
             noise = torch.rand(B, geo.n, device=A.device)
         noise = noise.to(device=A.device, dtype=torch.float32).contiguous()
-        live, ranges, dec_ranges, enc_ranges = self._plan(geo)
+        live, ranges, buckets = self._plan(geo)
         for k in live:
             p = A.params[k]
             if p.grad is None or p.grad.data_ptr() != A.view(self.gflat, k).data_ptr():
@@ -134,16 +157,12 @@ class FusedTrainer:
         self._push_hyper()
         if not self.use_graph:
             box = {}
-            self._phase_a(xs, noise, geo, box)
             if self.world > 1:
-                ev = torch.cuda.Event(); ev.record()
-                self._allreduce(dec_ranges, ev)
-            self._phase_b(box)
-            if self.world > 1:
-                ev2 = torch.cuda.Event(); ev2.record()
-                self._allreduce(enc_ranges, ev2)
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
-            self._phase_c(ranges)
+                self._dp_sequence(xs, noise, geo, box, ranges, buckets)
+            else:
+                self._phase_a(xs, noise, geo, box)
+                self._phase_b(box)
+                self._phase_c(ranges)
             A._version_seen = A.version()
             return box["loss"].reshape(())
         key = (geo.use_vision, geo.nt, B, input_signature(xs))
@@ -151,25 +170,26 @@ class FusedTrainer:
         if g is None:
             while len(self._graphs) >= self._MAX_GRAPHS:       # each capture owns a full activation pool
                 self._graphs.pop(next(iter(self._graphs)))
-            g = self._capture(xs, noise, geo, ranges)
+            g = self._capture(xs, noise, geo, ranges, buckets)
             self._graphs[key] = g
         copy_inputs(g["xs"], xs)
         g["noise"].copy_(noise, non_blocking=True)
-        if self.world == 1:
-            g["all"].replay()
+        if "all" in g:
+            g["all"].replay()             # single GPU, or the data-parallel step with its all-reduces captured
         else:
-            g["a"].replay()
-            ev = torch.cuda.Event(); ev.record()
-            self._allreduce(dec_ranges, ev)
-            g["b"].replay()
-            ev2 = torch.cuda.Event(); ev2.record()
-            self._allreduce(enc_ranges, ev2)
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            main = torch.cuda.current_stream()
+            for name, rng in zip(("a", "b1", "b2"), buckets):
+                g[name].replay()
+                if rng:
+                    self.comm_stream.wait_stream(main)
+                    with torch.cuda.stream(self.comm_stream):
+                        dp.allreduce_ranges(self.gflat, rng, group=self.pg)
+            main.wait_stream(self.comm_stream)
             g["c"].replay()
         A._version_seen = A.version()
         return g["box"]["loss"].reshape(())
 
-    def _capture(self, xs, noise, geo, ranges):
+    def _capture(self, xs, noise, geo, ranges, buckets):
         """Warm-up once eagerly (lazy kernel attributes, allocator), then capture."""
         sx = clone_inputs(xs)
         sn = noise.clone()
@@ -196,16 +216,24 @@ class FusedTrainer:
                     self._phase_b(out["box"])
                     self._phase_c(ranges)
                 out["all"] = g
+            elif self.one_graph_dp:
+                # NCCL all-reduces captured with the kernels: one graph launch per step, no host in the loop
+                g = torch.cuda.CUDAGraph()
+                with counter, torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._dp_sequence(sx, sn, geo, out["box"], ranges, buckets)
+                out["all"] = g
             else:
-                ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                gs = [torch.cuda.CUDAGraph() for _ in range(4)]
                 pool = torch.cuda.graph_pool_handle()
                 with counter:
-                    with torch.cuda.graph(ga, pool=pool):
+                    with torch.cuda.graph(gs[0], pool=pool):
                         self._phase_a(sx, sn, geo, out["box"])
-                    with torch.cuda.graph(gb, pool=pool):
-                        self._phase_b(out["box"])
-                    with torch.cuda.graph(gc, pool=pool):
+                    with torch.cuda.graph(gs[1], pool=pool):
+                        self._phase_b1(out["box"])
+                    with torch.cuda.graph(gs[2], pool=pool):
+                        self._phase_b2(out["box"])
+                    with torch.cuda.graph(gs[3], pool=pool):
                         self._phase_c(ranges)
-                out.update(a=ga, b=gb, c=gc)
+                out.update(a=gs[0], b1=gs[1], b2=gs[2], c=gs[3])
         self.kernel_launches_per_step = counter.count
         return out

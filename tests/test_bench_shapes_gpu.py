@@ -107,3 +107,19 @@ def test_rollout_extractor_at_512_observations_vs_oracle():
     assert cos(feats, ref) >= 0.9995
     per_row = torch.nn.functional.cosine_similarity(feats.cpu().double(), ref.double(), dim=1)
     assert per_row.min().item() >= 0.999, per_row.min().item()
+
+
+def test_data_parallel_replicas_stay_identical_two_ranks():
+    """Two-rank NCCL run of the fused trainer (tests/dp_worker.py): bit-identical replicas after three steps with the
+    all-reduces captured in the step graph and with host-launched all-reduces, canonical dims and decoder_dim != dim;
+    loss of the sharded step against the oracle on the global batch.  Needs two GPUs (skipped on a one-GPU box)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(root / "tests" / "dp_worker.py")],
+                       capture_output=True, text=True, timeout=900, cwd=str(root))
+    assert r.returncode == 0 and "DP_WORKER_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

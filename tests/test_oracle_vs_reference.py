@@ -192,3 +192,44 @@ def test_vtt_dino_product_module_mirrors_reference_state_dict():
     w = b["transformer.layers.0.1.net.1.weight"]
     assert abs(float(w.std()) - 0.02) < 2e-3 and float(b["transformer.layers.0.1.net.1.bias"].abs().max()) == 0.0
     mine.load_state_dict(a)
+
+
+def _load_ref_file(rel, name):
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location(name, str(Path("/root/reference") / rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_dino_head_loss_and_ema_match_reference_files():
+    """oracle/vtdino_oracle.py against the UNMODIFIED tactile_ssl/model/layers/dino_head.py, tactile_ssl/loss/dino_loss.py
+    and tactile_ssl/utils/ema.py (loaded by path: they only need torch)."""
+    from oracle import vtdino_oracle as DO
+    head_mod = _load_ref_file("tactile_ssl/model/layers/dino_head.py", "ref_dino_head")
+    loss_mod = _load_ref_file("tactile_ssl/loss/dino_loss.py", "ref_dino_loss")
+    ema_mod = _load_ref_file("tactile_ssl/utils/ema.py", "ref_ema")
+    torch.manual_seed(0)
+    head = head_mod.DINOHead(in_dim=64, out_dim=96, hidden_dim=128, bottleneck_dim=32)
+    with torch.no_grad():
+        head.last_layer.weight_g.mul_(1 + 0.1 * torch.randn_like(head.last_layer.weight_g))
+    x = torch.randn(5, 3, 64)
+    assert torch.equal(DO.dino_head_forward(head.state_dict(), x), head(x))
+    ref_loss = loss_mod.DINOLoss(out_dim=96)
+    t_out = torch.randn(10, 1, 96)
+    s_list = [torch.randn(5, 1, 96, requires_grad=True) for _ in range(3)]
+    for it in range(2):
+        t_soft_ref = ref_loss.softmax_center_teacher(t_out, teacher_temp=0.05)
+        center_before = ref_loss.center.clone()
+        assert torch.equal(DO.softmax_center_teacher(t_out, center_before, 0.05), t_soft_ref)
+        ref_loss.update_center(t_out)
+        ref_loss.apply_center_update()
+        assert torch.equal(DO.center_update(center_before, t_out), ref_loss.center)
+        tl = list(t_soft_ref.view(2, -1, 1, 96))
+        assert torch.equal(DO.dino_loss(s_list, tl), ref_loss(s_list, tl))
+    a, b = torch.nn.Linear(7, 5), torch.nn.Linear(7, 5)
+    want = [DO.ema(pa.data.clone(), pb.data.clone(), 0.97) for pb, pa in zip(b.parameters(), a.parameters())]
+    ema_mod.update_moving_average(a, b, 0.97)
+    for w, pa in zip(want, a.parameters()):
+        assert torch.equal(w, pa.data)

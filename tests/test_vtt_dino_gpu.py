@@ -114,3 +114,66 @@ def test_forward_features_vs_reference_golden(name):
             assert abs(float(named[k].grad.double().norm()) - n) <= 3e-2 * n, (k, float(named[k].grad.double().norm()), n)
     for k, gr in g.full_grads().items():
         assert cos(named[k].grad, gr) >= 0.999, (k, cos(named[k].grad, gr))
+
+
+def test_vtdino_step_vs_oracle():
+    """models/vtdino.py:332-397 on the kernel path (m3l_b200.vtdino.VTDINO): DINO loss, student gradients, the centre
+    update and the momentum (EMA) teacher update against the oracle (oracle/vtdino_oracle.py; heads / loss / EMA
+    pinned bit-for-bit against the reference files, the backbone against models/VTT.py)."""
+    from functools import partial
+    from oracle import vtdino_oracle as DO
+    from m3l_b200.vtdino import VTDINO, DINOHead
+    cfg = VD.VTTDinoConfig(depth=2, num_register_tokens=1, heads=4)
+    enc = build(cfg, seed=41)
+    torch.manual_seed(5)
+    model = VTDINO(enc, partial(DINOHead, out_dim=256, hidden_dim=128, bottleneck_dim=64), num_global_masks=2, num_local_masks=3,
+                   moving_average_decay=0.9, teacher_temp=0.05)
+    with torch.no_grad():     # make the teacher differ from the student and the centre non-trivial
+        for p in model.teacher_encoder.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+        model.dino_loss.center.normal_(0, 0.1)
+    sds = {k: v.detach().clone() for k, v in model.student_encoder["backbone"].state_dict().items()}
+    sdt = {k: v.detach().clone() for k, v in model.teacher_encoder["backbone"].state_dict().items()}
+    hs = {k: v.detach().clone() for k, v in model.student_encoder["dino_head"].state_dict().items()}
+    ht = {k: v.detach().clone() for k, v in model.teacher_encoder["dino_head"].state_dict().items()}
+    center = model.dino_loss.center.detach().clone()
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(77)
+    B = 4
+    x = {"image": torch.rand(B, 12, 64, 64, generator=g), "tactile1": torch.rand(B, 12, 32, 32, generator=g),
+         "tactile2": torch.rand(B, 12, 32, 32, generator=g)}
+    gm = [torch.stack([torch.randperm(64, generator=g)[:30] for _ in range(B)]) for _ in range(2)]
+    lm = [torch.stack([torch.randperm(64, generator=g)[:12] for _ in range(B)]) for _ in range(3)]
+    loss = model({k: v.to(DEV) for k, v in x.items()}, [m.to(DEV) for m in gm], [m.to(DEV) for m in lm])
+    loss.backward()
+    for d in (sds, hs):
+        for k in d:
+            if d[k].dtype.is_floating_point and k != "pos_embed.frequency_bands":
+                d[k].requires_grad_(True)
+    lref, t_cls = DO.vtdino_forward(sds, hs, sdt, ht, cfg, x, gm, lm, center, 0.05)
+    lref.backward()
+    assert abs(float(loss) - float(lref)) <= 1e-2 * abs(float(lref)), (float(loss), float(lref))
+    checked = 0
+    for prefix, mod, d in (("backbone", model.student_encoder["backbone"], sds), ("head", model.student_encoder["dino_head"], hs)):
+        for k, p in mod.named_parameters():
+            gr = d[k].grad
+            if gr is None or float(gr.abs().max()) == 0.0:
+                continue
+            assert p.grad is not None and cos(p.grad, gr) >= 0.995, (prefix, k, cos(p.grad, gr) if p.grad is not None else None)
+            checked += 1
+    assert checked > 30
+    for p in model.teacher_encoder.parameters():
+        assert p.grad is None
+    # centre update (applied lazily at the next softmax_center_teacher) and the EMA teacher update
+    model.dino_loss.apply_center_update()
+    want_c = DO.center_update(center, t_cls)
+    assert cos(model.dino_loss.center, want_c) >= 0.9999
+    model.on_train_batch_end()
+    for (k, pt), ps in zip(model.teacher_encoder["backbone"].named_parameters(), model.student_encoder["backbone"].parameters()):
+        want = DO.ema(sdt[k], ps.detach().cpu(), 0.9)
+        assert torch.equal(pt.detach().cpu(), want), k                  # fp32, same operation order: bit-exact
+    for (k, pt), ps in zip(model.teacher_encoder["dino_head"].named_parameters(), model.student_encoder["dino_head"].parameters()):
+        assert torch.equal(pt.detach().cpu(), DO.ema(ht[k], ps.detach().cpu(), 0.9)), k
+    # the updated teacher is what the next forward uses (bf16 shadows refreshed), and training_step runs end to end
+    out = model.training_step({k: v.to(DEV) for k, v in x.items()})
+    assert out["loss"].requires_grad and out["ssl_loss"] == out["ssl_loss"]

@@ -17,7 +17,7 @@ x_host, noise_host = bench.synth_batch(B, 1234)
 xs = {k: v.to(dev) for k, v in x_host.items()}
 noise = noise_host.to(dev)
 xs, geo, _ = model._prep_inputs(xs, True, True)
-live, ranges, _, _ = tr._plan(geo)
+live, ranges, _ = tr._plan(geo)
 G = engine.GradView(A, tr.gflat)
 
 
