@@ -297,6 +297,27 @@ def per_kernel_roofline(peaks, ms_per_step):
     return rows
 
 
+def _teardown(world, trainer=None):
+    """Multi-rank exit: the step graphs hold captured NCCL kernels, and tearing the communicator down while they are
+    alive (or letting the interpreter do it in arbitrary order at exit) can block for minutes.  Order: all ranks
+    finished (barrier) -> drop the graphs -> flush -> leave the process without running the NCCL destructor path."""
+    if world <= 1:
+        return
+    import gc
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if trainer is not None:
+        trainer._graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -353,8 +374,7 @@ def run_gpu_arm(args):
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "value": value, "loss": loss_val}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        _teardown(world, trainer)
         return
 
     # ---- sustained: the same loop for >= args.sustain_seconds (the 20-step figure above is a burst of ~50 ms)
@@ -504,9 +524,7 @@ def run_gpu_arm(args):
                                     "sample": f"batch 32 slice of the workload, fp32 torch CPU oracle, 30 timed steps, "
                                               f"{cpu_ms:.1f} ms/step"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _teardown(world, trainer)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -652,9 +670,7 @@ def run_other_config(args):
         if replicas_identical is not None:
             line["replicas_identical"] = replicas_identical
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _teardown(world, trainer)
 
 
 def main():

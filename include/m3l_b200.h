@@ -302,9 +302,11 @@ int m3l_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_s
 typedef struct m3l_matrix_desc {
   int64_t src_offset; /* elements from src_base */
   int64_t dst_offset; /* elements from dst_base */
-  int32_t rows, cols; /* Momentum (EMA) teacher update over flat fp32 arenas: teacher = teacher * beta + (1 - beta) * student
- * (/root/reference/tactile_ssl/utils/ema.py:6-19, called from models/vtdino.py:159-173 after every train batch). */
-int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, void* stream);
+  int32_t rows, cols; /* Momentum (EMA) teacher update over flat fp32 arenas: teacher = teacher * beta + one_minus_beta * student
+ * (/root/reference/tactile_ssl/utils/ema.py:6-19, called from models/vtdino.py:159-173 after every train batch).
+ * one_minus_beta is passed separately: the reference forms (1.0 - beta) in double precision before it meets the fp32
+ * tensor, which is not the fp32 difference 1.0f - beta. */
+int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, float one_minus_beta, void* stream);
 
 /* of the source, row-major */
 } m3l_matrix_desc;

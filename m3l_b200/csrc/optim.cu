@@ -121,10 +121,9 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 // teacher[i] = teacher[i] * beta + (1 - beta) * student[i] over a flat fp32 arena (DINO momentum teacher:
 // tactile_ssl/utils/ema.py update_moving_average, called from models/vtdino.py:159-173); same operation order as the
 // reference (old * beta + (1.0 - beta) * new) so the fp32 results are bit-identical
-__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, size_t n, float beta) {
+__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, size_t n, float beta, float omb) {
   pdl_wait();
   pdl_trigger();
-  const float omb = 1.0f - beta;
   const size_t n4 = n >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 t = reinterpret_cast<float4*>(teacher)[i];
@@ -227,11 +226,12 @@ extern "C" int m3l_transpose_cast_bf16(const float* src_base, void* dst_base_bf1
   return M3L_OK;
 }
 
-extern "C" int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, void* stream) {
+extern "C" int m3l_ema_update(float* teacher, const float* student, size_t count, float beta, float one_minus_beta,
+                              void* stream) {
   M3L_REQUIRE(teacher && student, "ema_update: null pointer");
   M3L_REQUIRE((((uintptr_t)teacher | (uintptr_t)student) & 15) == 0, "ema_update: pointers must be 16-byte aligned");
   if (count == 0) return M3L_OK;
-  M3L_CUDA(launch_kernel(ema_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, teacher, student, count, beta));
+  M3L_CUDA(launch_kernel(ema_kernel, dim3(stream_grid(count, 4)), dim3(256), 0, (cudaStream_t)stream, teacher, student, count, beta, one_minus_beta));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

@@ -449,8 +449,8 @@ def ema_update(teacher, student, beta: float):
     _req_cuda(teacher, student)
     assert teacher.dtype == torch.float32 and student.dtype == torch.float32 and teacher.numel() == student.numel()
     assert teacher.is_contiguous() and student.is_contiguous()
-    check(_lib.load().m3l_ema_update(ptr(teacher), ptr(student), C.c_size_t(teacher.numel()), C.c_float(beta), current_stream()),
-          "m3l_ema_update")
+    check(_lib.load().m3l_ema_update(ptr(teacher), ptr(student), C.c_size_t(teacher.numel()), C.c_float(beta),
+                                     C.c_float(1.0 - beta), current_stream()), "m3l_ema_update")
 
 
 def cast_bf16(src, dst):

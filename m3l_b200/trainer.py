@@ -199,10 +199,18 @@ class FusedTrainer:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             box = {}
-            self._phase_a(sx, sn, geo, box)
-            self._phase_b(box)
-            self._phase_c(ranges)
+            if self.world > 1:
+                # the warm-up runs the real data-parallel sequence: NCCL sets up its channels / buffers on the first
+                # collective of a communicator (host-side allocation and peer exchange), which must not happen for
+                # the first time inside a stream capture
+                self._dp_sequence(sx, sn, geo, box, ranges, buckets)
+            else:
+                self._phase_a(sx, sn, geo, box)
+                self._phase_b(box)
+                self._phase_c(ranges)
         torch.cuda.current_stream().wait_stream(s)
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
         torch.cuda.synchronize()
         self.model.arena.flat.copy_(snap[0]); self.m.copy_(snap[1]); self.v.copy_(snap[2]); self.state.copy_(snap[3])
         self.model.arena.refresh_shadows()

@@ -169,8 +169,7 @@ def update_moving_average(ma_model: nn.Module, current_model: nn.Module, beta: f
             ops.ema_update(at.flat, as_.flat, float(beta))
             for n in at.names:
                 done.add(id(at.params[n]))
-                at.params[n]._version            # noqa: B018 - (documentation) in-place on .data: bump below
-            at._version_seen = None              # the bf16 shadows are stale
+            at._version_seen = None              # the bf16 shadows are stale: refreshed at the next forward
     for ps, pt in zip(current_model.parameters(), ma_model.parameters()):
         if id(pt) in done:
             continue

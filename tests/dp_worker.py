@@ -54,10 +54,13 @@ def main():
                 print(f"[dp_worker] {case} one_graph={one_graph}: world {world} replicas identical after 3 steps; "
                       f"step-0 loss {float(l0):.5f} vs oracle (global batch) {float(lref):.5f}", flush=True)
             del mae, tr
+    torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
         print("DP_WORKER_OK", flush=True)
-    dist.destroy_process_group()
+    # captured NCCL kernels were alive in this process: leave without the communicator teardown (see bench._teardown)
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -233,3 +233,61 @@ def test_dino_head_loss_and_ema_match_reference_files():
     ema_mod.update_moving_average(a, b, 0.97)
     for w, pa in zip(want, a.parameters()):
         assert torch.equal(w, pa.data)
+
+
+def test_sb3_checkpoint_round_trip_with_the_reference_extractor(tmp_path):
+    """SB3's CheckpointCallback (utils/callbacks.py:126-133 -> BaseAlgorithm.save) writes a zip whose `policy.pth`
+    member is torch.save(policy.state_dict()); the MAE part of a policy lives under `features_extractor.`.  A
+    checkpoint written from the UNMODIFIED reference MAEExtractor loads strictly into the product extractor, and one
+    written from the product loads strictly back into the reference: saved policies stay interchangeable."""
+    import io
+    import zipfile
+    from m3l_b200 import VTT, VTMAE, MAEExtractor
+    ref = R.load_reference_module()
+    cfg = O.VTMAEConfig(depth=2, decoder_depth=1)
+    ref_mae = R.build_reference_model(cfg, seed=1)
+    torch.manual_seed(2)
+    ref_ext = ref.MAEExtractor(None, ref_mae, cfg.dim, False, cfg.frame_stack)
+
+    class Policy(torch.nn.Module):             # the slice of an SB3 ActorCriticPolicy that matters here
+        def __init__(self, ext):
+            super().__init__()
+            self.features_extractor = ext
+            self.action_net = torch.nn.Linear(cfg.dim, 4)
+
+    def save_sb3_zip(policy, path):
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data", "{}")
+            for member, obj in (("policy.pth", policy.state_dict()), ("policy.optimizer.pth", {}), ("pytorch_variables.pth", {})):
+                buf = io.BytesIO()
+                torch.save(obj, buf)
+                z.writestr(member, buf.getvalue())
+            z.writestr("_stable_baselines3_version", "2.1.0")
+
+    def load_policy_pth(path):
+        with zipfile.ZipFile(path) as z:
+            return torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
+
+    enc = VTT(image_size=cfg.image_size, tactile_size=cfg.tactile_size, image_patch_size=cfg.image_patch_size,
+              tactile_patch_size=cfg.tactile_patch_size, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_dim=cfg.mlp_dim,
+              num_tactiles=cfg.num_tactiles, image_channels=cfg.image_channels, tactile_channels=cfg.tactile_channels,
+              frame_stack=cfg.frame_stack)
+    mae = VTMAE(encoder=enc, decoder_dim=cfg.decoder_dim, masking_ratio=cfg.masking_ratio, decoder_depth=cfg.decoder_depth,
+                decoder_heads=cfg.decoder_heads, num_tactiles=cfg.num_tactiles, frame_stack=cfg.frame_stack)
+    mine = Policy(MAEExtractor(None, mae, cfg.dim, False, cfg.frame_stack))
+    theirs = Policy(ref_ext)
+    # reference -> zip -> product
+    save_sb3_zip(theirs, tmp_path / "ref.zip")
+    sd = load_policy_pth(tmp_path / "ref.zip")
+    assert set(sd) == set(mine.state_dict())
+    mine.load_state_dict(sd, strict=True)
+    for k, v in theirs.state_dict().items():
+        assert torch.equal(mine.state_dict()[k], v), k
+    # product -> zip -> reference
+    with torch.no_grad():
+        for p in mine.parameters():
+            p.mul_(1.01)
+    save_sb3_zip(mine, tmp_path / "mine.zip")
+    theirs.load_state_dict(load_policy_pth(tmp_path / "mine.zip"), strict=True)
+    for k, v in mine.state_dict().items():
+        assert torch.equal(theirs.state_dict()[k], v), k
