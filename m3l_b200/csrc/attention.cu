@@ -476,6 +476,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA loader -----------------------------------------
+    // Row statistics of ALL items of this CTA -> L2, by the 31 otherwise idle lanes of this warp.  The producers read
+    // LSE / delta into runtime-indexed (local-memory) arrays, which blocks until the loads land: 1.3 k clk per step in
+    // the r02 timeline, because LSE was written a whole forward pass earlier and came from HBM.  (Prefetching from the
+    // producer warps themselves cost registers they do not have: 168 / 168 used, the address math spilled.)
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int h = item % p.heads, b = item / p.heads;
+      const char* l0 = reinterpret_cast<const char*>(p.lse + ((size_t)b * p.heads + h) * n);
+      for (int off = lane * 128; off < n * 4; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l0 + off));
+      if (p.delta != nullptr) {                 // delta rows of a sample hold all heads (the block is shared by its 4 items)
+        const char* d0 = reinterpret_cast<const char*>(p.delta + (size_t)b * n * p.heads);
+        for (int off = lane * 128; off < n * p.heads * 4; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d0 + off));
+      }
+    }
     if (elect_one()) {      // single issuing thread; elect (not lane == 0) keeps TMA / MMA operands in uniform registers
       for (int it = 0; it < my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
@@ -719,8 +733,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const bool valid = grow < n;
           const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
           const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
-          const bool cols_any = key0 < n;
-          // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
+          const bool cols_any = key0 < n;          // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
           // wait: behind it the LDL latency sat on the producers' critical path (r01_ncu_attention_hot_lines_v5.txt)
           const float dl = delta[i], lg = l2[i] * kLog2e;
           mbar_wait(&bars->sdp_full, g & 1);
