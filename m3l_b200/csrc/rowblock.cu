@@ -55,7 +55,7 @@ struct Cfg {
 struct alignas(8) Bars {
   uint64_t full[kMaxSlots], empty[kMaxSlots];
   uint64_t a_loaded, a_ready, a_free, a_stored;
-  uint64_t acc1_full[2], h_full[2];
+  uint64_t acc1_full[2], h_full[2], h_read[2];
   uint64_t acc2_full, acc2_empty;
   uint64_t side_full[kRowWarps][2];
   uint32_t tmem_base;
@@ -242,6 +242,7 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars->acc1_full[b], 1);
       mbar_init(&bars->h_full[b], kGeluWarps);
+      mbar_init(&bars->h_read[b], kRowWarps);
     }
     mbar_init(&bars->acc2_full, 1);
     mbar_init(&bars->acc2_empty, kRowWarps);
@@ -333,6 +334,12 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const int k = gc + c, buf = k & 1;
           if (!is_g2) {
             // ---- acc1[buf] = LN(x) . W1[c]^T
+            // (training: the row warps copy the hidden chunk that lived in this buffer, h(k - 2), out of tensor memory;
+            // the product that consumed it was issued earlier, only their read has to be waited for)
+            if (SAVE && k >= 2) {
+              mbar_wait(&bars->h_read[buf], ((k - 2) >> 1) & 1);
+              tc_fence_after_sync();
+            }
             const uint32_t d = tmem_base + buf * 128;
             RB_EV(1, (i * 2 * nc + it) * 2);
 #pragma unroll
@@ -393,11 +400,54 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       mbar_arrive_expect_tx(&bars->side_full[rw][b], kStgUnit);
       tma_load_2d_u32(stg + b * kStgUnit, &map_x32, &bars->side_full[rw][b], r * 32, m0 + quad * 32);
     };
+    int gc_r = 0;                                     // chunks before this tile (same counter as the MMA / GELU roles)
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
       const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * kBM;
       const int row0 = m0 + quad * 32;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 256;
+      if (SAVE) {
+        // ---- training: these warps are idle during the chunk loop, so THEY write GELU(pre) to HBM.  The bf16 hidden
+        // chunk already sits in tensor memory (packed, the A operand of the second product): read it back (4 x 16
+        // columns = this row's 128 values), release the buffer, then stage + TMA-store two [32 x 64] tiles.  The GELU
+        // warps are left with ONE store per chunk (GELU'): with both on them the kernel was store-wait bound
+        // (102 us vs 67 us without the training outputs, r02 ncu).
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+          const int k = gc_r + c, buf = k & 1;
+          const int pc = (c + rot) % nc;
+          mbar_wait(&bars->h_full[buf], (k >> 1) & 1);
+          tc_fence_after_sync();
+          uint32_t hw[64];
+          const uint32_t th = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * 128;
+#pragma unroll
+          for (int part = 0; part < 4; ++part)
+            tmem_ld_32x16(th + part * 32, *reinterpret_cast<uint32_t(*)[16]>(&hw[part * 16]));
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->h_read[buf]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {               // hidden columns pc*128 + u*64 .. +64 of rows row0 .. +32
+            tma_wait_group_read<0>();                 // (issuing lane) the previous tile has left the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {             // 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+              const uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hw[u * 32 + 4 * j]),
+                           "r"(hw[u * 32 + 4 * j + 1]), "r"(hw[u * 32 + 4 * j + 2]), "r"(hw[u * 32 + 4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_2d(&map_h, stg, pc * kCH + u * 64, row0);
+              tma_commit_group();
+            }
+          }
+        }
+        gc_r += nc;
+      }
       if (p.out_has_x) {
         // ---- out += acc2 + b2 with bf16 vector reductions: no residual fetch on the path that frees acc2
         mbar_wait(&bars->acc2_full, i & 1);
@@ -644,10 +694,7 @@ ln_mlp_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->h_full[buf]);
         if (gw == 0 && lane == 0) RB_EV(3, k * 4 + 3);
-        if (SAVE) {
-          rb_store_unit(&map_gp, stg, lane, gp, pc * kCH + part * 32, row0);
-          rb_store_unit(&map_h, stg, lane, hp, pc * kCH + part * 32, row0);
-        }
+        if (SAVE) rb_store_unit(&map_gp, stg, lane, gp, pc * kCH + part * 32, row0);      // GELU(pre): row warps
       }
       gc += nc;
       if (i + 1 < n_tiles) layer_norm_tile(i + 1);
@@ -679,7 +726,7 @@ int launch(const m3l_ln_mlp_args* a, cudaStream_t stream) {
   map_gp = map_out;
   if (a->xn_out != nullptr && (s = make_tmap_2d_bf16(&map_xn, a->xn_out, a->rows, kD, kD, 128))) return s;
   if (SAVE) {
-    if ((s = make_tmap_2d_bf16_sw64(&map_h, a->h_out, a->rows, a->hidden, a->hidden, 32))) return s;
+    if ((s = make_tmap_2d_bf16(&map_h, a->h_out, a->rows, a->hidden, a->hidden, 32))) return s;
     if ((s = make_tmap_2d_bf16_sw64(&map_gp, a->gp_out, a->rows, a->hidden, a->hidden, 32))) return s;
   }
   Args p;
@@ -731,6 +778,8 @@ extern "C" int m3l_ln_mlp_fwd(const m3l_ln_mlp_args* a, void* stream) {
               "ln_mlp_fwd: bad shape rows=%d hidden=%d (hidden must be a multiple of 128 up to 1024)", a->rows, a->hidden);
   M3L_REQUIRE(a->x && a->gamma && a->beta && a->w1 && a->b1 && a->w2 && a->b2 && a->out, "ln_mlp_fwd: null pointer");
   M3L_REQUIRE((a->h_out == nullptr) == (a->gp_out == nullptr), "ln_mlp_fwd: h_out and gp_out go together");
+  M3L_REQUIRE(a->h_out == nullptr || a->out == a->x || a->out_has_x,
+              "ln_mlp_fwd: the training outputs need the accumulate-into-out mode (out == x or out_has_x)");
   if (a->h_out != nullptr) return launch<true>(a, (cudaStream_t)stream);
   return launch<false>(a, (cudaStream_t)stream);
 }

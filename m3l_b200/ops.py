@@ -114,7 +114,10 @@ def ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, *, save: bool = False, eps: float
     assert w1.shape == (hidden, D) and w2.shape == (D, hidden) and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
     if out is None:
         assert not out_has_x
-        out = torch.empty_like(x)
+        if save:                      # the training outputs go with the accumulate-into-out mode of the kernel
+            out, out_has_x = x.clone(), True
+        else:
+            out = torch.empty_like(x)
     assert out.shape == x.shape and out.dtype == torch.bfloat16 and out.is_contiguous()
     a = _lib.LnMlpArgs()
     a.x, a.rows, a.dim, a.hidden = ptr(x), M, D, hidden
