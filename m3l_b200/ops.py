@@ -197,11 +197,13 @@ def make_patch_source(maps, patch_h: int, patch_w: int, token_base: int):
     return ps
 
 
-def vt_load_map(raw) -> torch.Tensor:
+def vt_load_map(raw, out=None) -> torch.Tensor:
     """data.RawMap -> fp32 [B, C, H, W] contiguous (utils/pretrain_utils.py:7-57 as one kernel)."""
     ps = make_patch_source([raw], 1, 1, 0)
     B = raw.shape[0]
-    out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    assert out.shape == tuple(raw.shape) and out.dtype == torch.float32 and out.is_contiguous()
     check(_lib.load().m3l_vt_load(C.byref(ps), B, 0, ptr(out), current_stream()), "m3l_vt_load")
     return out
 
