@@ -112,48 +112,51 @@ class DINOHead(nn.Module):
 
 
 class DINOLoss(nn.Module):
-    """tactile_ssl/loss/dino_loss.py:10-101 (softmax-centre teacher; the Sinkhorn-Knopp variant is not used by VTDINO)."""
+    """Centred-softmax cross-entropy of tactile_ssl/loss/dino_loss.py:10-101 (same constructor, `center` buffer and
+    method names; the Sinkhorn-Knopp teacher is not used by VTDINO and not provided).  The centre update is lazy, as in
+    the reference: `update_center` only starts the (all-reduced) batch sum, the EMA is applied at the next
+    `softmax_center_teacher`."""
 
     def __init__(self, out_dim, student_temp=0.1, center_momentum=0.9):
         super().__init__()
-        self.student_temp = student_temp
-        self.center_momentum = center_momentum
+        self.student_temp, self.center_momentum = student_temp, center_momentum
         self.register_buffer("center", torch.zeros(1, out_dim))
-        self.updated = True
-        self.reduce_handle = None
-        self.len_teacher_output = None
-        self.async_batch_center = None
+        self._pending = None              # (batch sum of teacher outputs, rows summed, async all-reduce handle)
+
+    @staticmethod
+    def _world():
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    @torch.no_grad()
+    def apply_center_update(self):
+        if self._pending is None:
+            return
+        total, rows, handle = self._pending
+        if handle is not None:
+            handle.wait()
+        batch_center = total / (rows * self._world())
+        self.center = self.center * self.center_momentum + batch_center * (1 - self.center_momentum)
+        self._pending = None
 
     @torch.no_grad()
     def softmax_center_teacher(self, teacher_output, teacher_temp):
         self.apply_center_update()
         return F.softmax((teacher_output - self.center) / teacher_temp, dim=-1)
 
-    def forward(self, student_output_list, teacher_out_softmaxed_centered_list):
-        total_loss = 0
-        for s in student_output_list:
-            lsm = F.log_softmax(s / self.student_temp, dim=-1)
-            for t in teacher_out_softmaxed_centered_list:
-                total_loss -= torch.sum(t * lsm, dim=-1).mean()
-        return total_loss
-
     @torch.no_grad()
     def update_center(self, teacher_output):
-        self.updated = False
-        self.len_teacher_output = len(teacher_output)
-        self.async_batch_center = torch.sum(teacher_output, dim=0, keepdim=True)
-        if dist.is_available() and dist.is_initialized():
-            self.reduce_handle = dist.all_reduce(self.async_batch_center, async_op=True)
+        total = torch.sum(teacher_output, dim=0, keepdim=True)
+        handle = dist.all_reduce(total, async_op=True) if self._world() > 1 else None
+        self._pending = (total, len(teacher_output), handle)
 
-    @torch.no_grad()
-    def apply_center_update(self):
-        if self.updated is False:
-            world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-            if self.reduce_handle is not None:
-                self.reduce_handle.wait()
-            _t = self.async_batch_center / (self.len_teacher_output * world_size)
-            self.center = self.center * self.center_momentum + _t * (1 - self.center_momentum)
-            self.updated = True
+    def forward(self, student_output_list, teacher_out_softmaxed_centered_list):
+        """-sum over (student view, teacher view) pairs of mean_b sum_k t_k log softmax(s / student_temp)_k."""
+        loss = 0
+        for s_out in student_output_list:
+            log_p = F.log_softmax(s_out / self.student_temp, dim=-1)
+            for t_prob in teacher_out_softmaxed_centered_list:
+                loss = loss - torch.sum(t_prob * log_p, dim=-1).mean()
+        return loss
 
 
 def update_moving_average(ma_model: nn.Module, current_model: nn.Module, beta: float) -> None:
