@@ -39,6 +39,15 @@ namespace m3l {
 namespace {
 
 constexpr int kDh = 64;
+// backward probes (profile build): the producer warps whose counters / events are recorded.  Producer warps are 2..9,
+// group = (warp - 2) / 4, TMEM lane quadrant = warp % 4: warp 4 = group 0 / rows 0-31 (has work in EVERY step: the
+// critical path), warp 8 = group 1 / rows 0-31.  (The first profiles recorded warps 2 and 7 - quadrants 2 and 3, idle in
+// every step of the second query tile of n = 192 - and showed mostly waiting.)
+#ifndef M3L_ATTN_PROBE_W0
+#define M3L_ATTN_PROBE_W0 4
+#define M3L_ATTN_PROBE_W1 8
+#endif
+constexpr int kProbeW0 = M3L_ATTN_PROBE_W0, kProbeW1 = M3L_ATTN_PROBE_W1;
 constexpr float kLog2e = 1.4426950408889634f;
 
 M3L_DEVINL uint32_t round_up_pow2_cols(int c) {
@@ -419,7 +428,7 @@ M3L_DEVINL void store_row64(bf16* dst, const uint32_t (&a0)[32], const uint32_t 
 
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap map_dqkv, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -443,14 +452,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_dqkv);
+    // the operand regions are released by the MMA thread (its last product on them) AND by the two producer groups,
+    // which stage dQ / dK / dV in the dead regions and TMA-store them from there: 1 + 2 arrivals
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->qdo_full[i], 1);
-      mbar_init(&bars->qdo_empty[i], 1);
+      mbar_init(&bars->qdo_empty[i], 3);
       mbar_init(&bars->kvl_full[i], 1);
-      mbar_init(&bars->kvl_empty[i], 1);
+      mbar_init(&bars->kvl_empty[i], 3);
     }
     mbar_init(&bars->kva_full, 1);
-    mbar_init(&bars->kva_empty, 1);
+    mbar_init(&bars->kva_empty, 3);
     mbar_init(&bars->sdp_full, 1);
     mbar_init(&bars->sdp_free, 256);
     mbar_init(&bars->pds_full, 256);
@@ -661,7 +673,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pc = pf_t0;
 #define PF(k) { const long long c_ = M3L_CLK(); pf[k] += c_ - pc; pc = c_; \
-                if (lane == 0 && (warp == 2 || warp == 6)) M3L_EVT(warp == 2 ? 1 : 2, g, k); }
+                if (lane == 0 && (warp == kProbeW0 || warp == kProbeW1)) M3L_EVT(warp == kProbeW0 ? 1 : 2, g, k); }
     // delta_i = rowsum(dO * O) and LSE (log2 domain) of this thread's row in each query tile; with a
     // precomputed delta the next item's values are fetched one item ahead
     float delta[2] = {0.f, 0.f}, l2[2] = {0.f, 0.f}, delta_n[2] = {0.f, 0.f}, l2_n[2] = {0.f, 0.f};
@@ -693,39 +705,97 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         }
       }
     };
-    // dV_j (group 0) / dK_j (group 1) epilogue of a finished key tile.  It is deferred until this thread
-    // has issued the next step's TMEM reads and math: waiting for the tile's last products right after
-    // handing over P / dS left the producers idle for a whole MMA batch every second step.
-    int pend_j = -1, pend_b = 0, pend_h = 0;
-    auto drain_dkv = [&]() {
-      if (pend_j < 0) return;
-      mbar_wait(&bars->dkv_full, dk & 1);
-      tc_fence_after_sync();
-      const int key = pend_j * 128 + row;
-      if (pend_j * 128 + quad * 32 < n) {
+    // ---- dQ / dK / dV epilogues.  A finished accumulator tile is read from tensor memory (which frees it for the tensor
+    // core at once), staged as bf16 in the shared-memory region of the INPUT tile it is the gradient of (dQ_i over Q_i,
+    // dK_j over K_j, dV_j over V_j: same shape, and dead once the accumulator is complete) and written with TMA.  The
+    // r02 timeline showed why: the thread-per-row global stores (16 bytes per lane at a 1536-byte stride, 32 sectors per
+    // instruction) cost the producer warps 2 - 3 k clk per tile, three tiles per item, on the critical path of the
+    // kernel; eight conflict-free shared-memory stores per thread cost a few hundred.  All epilogues are deferred until
+    // after the NEXT step's P / dS hand-over - across item boundaries as well, where math, hand-over, drains and the
+    // statistics fetch used to run back to back while the tensor core waited (11.7 k of 29 k clk per item).
+    const bool issuer = quad == 0 && lane == 0;              // the thread of this group that issues its TMA stores
+    const bool cross_p = p.qdo_bufs == 2 && p.kvl_bufs == 2;   // operands of the next item have their own buffers
+    uint64_t* rel[4];                                        // (issuer) regions to release once the stores have read them
+    int n_rel = 0;
+    auto flush_releases = [&]() {
+      if (issuer && n_rel > 0) {
+        tma_wait_group_read<0>();
+        for (int k = 0; k < n_rel; ++k) mbar_arrive(rel[k]);
+        n_rel = 0;
+      }
+    };
+    // accumulator columns [col, col + 64) of this thread's row -> region (rows_loaded x 128 B, SWIZZLE_128B) -> global
+    auto drain_tile = [&](uint32_t col, uint64_t* free_bar, uint32_t region, int rows_loaded, int gcol, int grow0, int gb,
+                          uint64_t* release) {
+      const bool have = quad * 32 < rows_loaded;
+      if (have) {
         uint32_t a0[32], a1[32];
-        const uint32_t col = wg == 0 ? kColDV : kColDK;
         tmem_ld_32x32(t_row + col, a0);
         tmem_ld_32x32(t_row + col + 32, a1);
         tmem_ld_wait();
         tc_fence_before_sync();
-        mbar_arrive(&bars->dkv_free);
-        if (key < n)
-          store_row64(p.dqkv + ((size_t)pend_b * n + key) * (3 * p.inner) + (wg == 0 ? 2 : 1) * p.inner + pend_h * kDh,
-                      a0, a1);
+        mbar_arrive(free_bar);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          st_swz_chunk(region, row, c4, make_uint4(pack_bf16x2(__uint_as_float(a0[8 * c4 + 0]), __uint_as_float(a0[8 * c4 + 1])),
+                                                   pack_bf16x2(__uint_as_float(a0[8 * c4 + 2]), __uint_as_float(a0[8 * c4 + 3])),
+                                                   pack_bf16x2(__uint_as_float(a0[8 * c4 + 4]), __uint_as_float(a0[8 * c4 + 5])),
+                                                   pack_bf16x2(__uint_as_float(a0[8 * c4 + 6]), __uint_as_float(a0[8 * c4 + 7]))));
+          st_swz_chunk(region, row, 4 + c4, make_uint4(pack_bf16x2(__uint_as_float(a1[8 * c4 + 0]), __uint_as_float(a1[8 * c4 + 1])),
+                                                       pack_bf16x2(__uint_as_float(a1[8 * c4 + 2]), __uint_as_float(a1[8 * c4 + 3])),
+                                                       pack_bf16x2(__uint_as_float(a1[8 * c4 + 4]), __uint_as_float(a1[8 * c4 + 5])),
+                                                       pack_bf16x2(__uint_as_float(a1[8 * c4 + 6]), __uint_as_float(a1[8 * c4 + 7]))));
+        }
       } else {
         tc_fence_before_sync();
-        mbar_arrive(&bars->dkv_free);
+        mbar_arrive(free_bar);
       }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);                             // every row of this group's tile is staged
+      if (issuer) {
+        for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
+        tma_commit_group();
+        rel[n_rel++] = release;
+      }
+    };
+    int pend_j = -1, pend_b = 0, pend_h = 0, pend_it = 0;     // key tile whose dV (group 0) / dK (group 1) is complete
+    bool pend_dq = false;                                     // dQ tiles of the previous item
+    int dq_b = 0, dq_h = 0, dq_it = 0;
+    auto drain_dkv = [&]() {
+      if (pend_j < 0) return;
+      mbar_wait(&bars->dkv_full, dk & 1);
+      tc_fence_after_sync();
+      const bool last = pend_j == jl;
+      const uint32_t base = last ? smem_u32(sKL + kvl_buf(pend_it) * 2 * p.kvl_region) : smem_u32(sKA + pend_j * 16384);
+      const uint32_t region = base + (wg == 0 ? (last ? p.kvl_region : p.kva_region) : 0);     // V region : K region
+      drain_tile(wg == 0 ? kColDV : kColDK, &bars->dkv_free, region, last ? p.k_rows[jl] : 128,
+                 (wg == 0 ? 2 : 1) * p.inner + pend_h * kDh, pend_j * 128, pend_b,
+                 last ? &bars->kvl_empty[kvl_buf(pend_it)] : &bars->kva_empty);
       ++dk;
       pend_j = -1;
+    };
+    auto drain_dq = [&]() {           // group w drains query tile w (the last dkv_full wait covered every product)
+      if (!pend_dq) return;
+      pend_dq = false;
+      uint64_t* release = &bars->qdo_empty[qdo_buf(dq_it)];
+      if (wg < p.q_tiles) {
+        drain_tile(kColDQ + wg * 64, &bars->item_done, smem_u32(sQ + qdo_buf(dq_it) * p.q_region + p.q_off[wg]), p.q_rows[wg],
+                   dq_h * kDh, wg * 128, dq_b, release);
+      } else {                        // no tile for this group: only the hand-shakes
+        tc_fence_before_sync();
+        mbar_arrive(&bars->item_done);
+        if (issuer) rel[n_rel++] = release;
+      }
     };
     if (my_items > 0) fetch_stats(0, delta_n, l2_n);
     for (int it = 0; it < my_items; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int h = item % p.heads, b = item / p.heads;
       delta[0] = delta_n[0]; delta[1] = delta_n[1]; l2[0] = l2_n[0]; l2[1] = l2_n[1];
-      if (it + 1 < my_items) fetch_stats(it + 1, delta_n, l2_n);
+      bool stats_due = it + 1 < my_items;          // next item's statistics: fetched after this item's first hand-over
+      // With ONE step per item the regions released at this item's hand-over would be the ones the item after it is
+      // waiting to load into (two buffers, the stores of item it-1 were issued during item it): release them now.
+      if (steps_per_item == 1) flush_releases();
       PF(0)
       for (int j = 0; j < p.key_tiles; ++j) {
         for (int i = 0; i < p.q_tiles; ++i, ++g) {
@@ -733,7 +803,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const bool valid = grow < n;
           const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
           const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
-          const bool cols_any = key0 < n;          // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
+          const bool cols_any = key0 < n;
+          // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
           // wait: behind it the LDL latency sat on the producers' critical path (r01_ncu_attention_hot_lines_v5.txt)
           const float dl = delta[i], lg = l2[i] * kLog2e;
           mbar_wait(&bars->sdp_full, g & 1);
@@ -772,8 +843,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             for (int e = 0; e < 32; ++e) pw[e] = dw[e] = 0u;
           }
           PF(2)
-          drain_dkv();
-          PF(5)
           // the slabs are still being read by the previous step's dV / dK / dQ products
           if (g > 0) mbar_wait(&bars->pds_free, (g - 1) & 1);
           PF(3)
@@ -786,30 +855,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           tc_fence_before_sync();
           mbar_arrive(&bars->pds_full);
           PF(4)
-          if (i == p.q_tiles - 1) { pend_j = j; pend_b = b; pend_h = h; }   // dV_j / dK_j drained during the next step
+          // ---- epilogues of accumulators completed by EARLIER steps, behind this step's hand-over
+          flush_releases();                 // (stores issued a step or more ago have long read their staging regions)
+          drain_dkv();
+          PF(5)
+          drain_dq();
+          PF(6)
+          if (stats_due) { fetch_stats(it + 1, delta_n, l2_n); stats_due = false; }
+          PF(7)
+          if (i == p.q_tiles - 1) { pend_j = j; pend_b = b; pend_h = h; pend_it = it; }   // dV_j / dK_j: after the next hand-over
         }
       }
-      // ---- dQ epilogue: group w drains query tile w (the last dkv_full commit covered every MMA)
-      drain_dkv();
-      PF(6)
-      if (wg < p.q_tiles && (wg * 128 + quad * 32) < n) {
-        uint32_t a0[32], a1[32];
-        tmem_ld_32x32(t_row + kColDQ + wg * 64, a0);
-        tmem_ld_32x32(t_row + kColDQ + wg * 64 + 32, a1);
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&bars->item_done);
-        const int grow = wg * 128 + row;
-        if (grow < n) store_row64(p.dqkv + ((size_t)b * n + grow) * (3 * p.inner) + h * kDh, a0, a1);
-      } else {
-        tc_fence_before_sync();
-        mbar_arrive(&bars->item_done);
+      pend_dq = true; dq_b = b; dq_h = h; dq_it = it;
+      if (!cross_p || it + 1 == my_items) {
+        // the next item's operands reuse this item's regions (single buffers), or there is no next item: finish now
+        drain_dkv();
+        drain_dq();
+        if (issuer && n_rel > 0) flush_releases();
       }
-      PF(7)
     }
 #undef PF
-    if (p.prof && blockIdx.x == 0 && (warp == 2 || warp == 7) && lane == 0) {
-      const int o = warp == 2 ? 0 : 16;
+    if (p.prof && blockIdx.x == 0 && (warp == kProbeW0 || warp == kProbeW1) && lane == 0) {
+      const int o = warp == kProbeW0 ? 0 : 16;
       for (int k = 0; k < 8; ++k) p.prof[o + k] = pf[k];
       p.prof[o + 8] = g;
       p.prof[o + 9] = M3L_CLK() - pf_t0;
@@ -1165,6 +1232,9 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
   if (s) return s;
   s = make_tmap_3d_bf16(&map_do, dout_bf16, inner, n, batch, inner, (uint64_t)n * inner, 64);
   if (s) return s;
+  CUtensorMap map_dqkv;      // same geometry as map_qkv: gradient tiles leave through 64-row TMA stores
+  s = make_tmap_3d_bf16(&map_dqkv, dqkv_bf16, 3 * inner, n, batch, 3 * inner, (uint64_t)n * 3 * inner, 64);
+  if (s) return s;
   AttnBwdParams p;
   p.o = (const bf16*)out_bf16; p.dout = (const bf16*)dout_bf16; p.lse = lse; p.delta = delta; p.dqkv = (bf16*)dqkv_bf16;
   p.n = n; p.heads = heads; p.inner = inner; p.scale = scale;
@@ -1199,7 +1269,7 @@ extern "C" int m3l_attention_bwd(const void* qkv_bf16, const void* out_bf16, con
     configured = true;
   }
   const int grid = std::min(p.num_items, device_sm_count());
-  M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_qkv, map_do, p));
+  M3L_CUDA(launch_kernel(attn_bwd_kernel, dim3(grid), dim3(320), smem, (cudaStream_t)stream, map_qkv, map_do, map_dqkv, p));
   M3L_CUDA(cudaGetLastError());
   return M3L_OK;
 }

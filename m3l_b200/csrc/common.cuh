@@ -304,6 +304,16 @@ M3L_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t smem_src_u32, int 
                : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src_u32), "r"(c0), "r"(c1)
                : "memory");
 }
+M3L_DEVINL void tma_store_3d(const CUtensorMap* map, uint32_t smem_src_u32, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src_u32), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+M3L_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // global[tile] += smem tile (element type taken from the tensor map; fp32 here)
 M3L_DEVINL void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src_u32, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"

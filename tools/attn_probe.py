@@ -20,7 +20,7 @@ buf = (C.c_longlong * 32)()
 for _ in range(2):
     ops.attention_bwd(qkv, o, do, lse, B, n, H, 64, 0.125, dqkv=dq, delta=delta); lib.m3l_debug_attn_prof(buf, 32)
 names = ["stats", "wait S,dP", "LDTM+math", "wait slabs", "STS+arrive", "wait dKV", "dKV epi", "dQ epi"]
-for o_, w_ in ((0, "warp2 (wg0,quad2)"), (16, "warp7 (wg1,quad3)")):
+for o_, w_ in ((0, "warp4 (group 0, rows 0-31)"), (16, "warp8 (group 1, rows 0-31)")):
     t_ = max(buf[o_ + 8], 1)
     print(f"bwd {w_} per step [clk]: " + " | ".join(f"{nm} {buf[o_ + k] / t_:.0f}" for k, nm in enumerate(names)) + f" | total {buf[o_ + 9] / t_:.0f}")
 t_ = max(buf[8], 1)
