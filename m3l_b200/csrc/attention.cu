@@ -713,7 +713,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     // kernel; eight conflict-free shared-memory stores per thread cost a few hundred.  All epilogues are deferred until
     // after the NEXT step's P / dS hand-over - across item boundaries as well, where math, hand-over, drains and the
     // statistics fetch used to run back to back while the tensor core waited (11.7 k of 29 k clk per item).
-    const bool issuer = quad == 0 && lane == 0;              // the thread of this group that issues its TMA stores
+    // the thread of each group that issues its TMA stores: in the LAST lane quadrant, which has no rows in the steps of
+    // a partial second query tile and can afford to wait for a store's shared-memory read when a region is needed back
+    // at once (quadrant 0 is the critical path of every step)
+    const bool issuer = quad == 3 && lane == 0;
     const bool cross_p = p.qdo_bufs == 2 && p.kvl_bufs == 2;   // operands of the next item have their own buffers
     uint64_t* rel[4];                                        // (issuer) regions to release once the stores have read them
     int n_rel = 0;
@@ -756,6 +759,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
         tma_commit_group();
         rel[n_rel++] = release;
+        // the early-key-tile region is single-buffered and the next item's K / V load is waiting for it (r02 timeline:
+        // released one step later, the load landed 4 k clk after the tensor core wanted it)
+        if (release == &bars->kva_empty) flush_releases();
       }
     };
     int pend_j = -1, pend_b = 0, pend_h = 0, pend_it = 0;     // key tile whose dV (group 0) / dK (group 1) is complete
