@@ -727,11 +727,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         n_rel = 0;
       }
     };
-    // accumulator columns [col, col + 64) of this thread's row -> region (rows_loaded x 128 B, SWIZZLE_128B) -> global
-    auto drain_tile = [&](uint32_t col, uint64_t* free_bar, uint32_t region, int rows_loaded, int gcol, int grow0, int gb,
-                          uint64_t* release) {
-      const bool have = quad * 32 < rows_loaded;
-      if (have) {
+    // accumulator columns [col, col + 64) of this thread's row -> tensor core may reuse them (free_bar) -> bf16 rows in
+    // `region` (rows_loaded x 128 B, SWIZZLE_128B).  Reading + staging one tile at a time keeps 64 registers live, not
+    // 128; the group barrier and the TMA stores come once, after BOTH tiles of an item boundary are staged (with a
+    // barrier per tile the second accumulator was handed back 1.5 k clk after the first; r02 timeline).
+    auto read_and_stage = [&](uint32_t col, uint64_t* free_bar, uint32_t region, int rows_loaded) {
+      if (quad * 32 < rows_loaded) {
         uint32_t a0[32], a1[32];
         tmem_ld_32x32(t_row + col, a0);
         tmem_ld_32x32(t_row + col + 32, a1);
@@ -753,45 +754,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         tc_fence_before_sync();
         mbar_arrive(free_bar);
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + wg, 128);                             // every row of this group's tile is staged
-      if (issuer) {
-        for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
-        tma_commit_group();
-        rel[n_rel++] = release;
-        // the early-key-tile region is single-buffered and the next item's K / V load is waiting for it (r02 timeline:
-        // released one step later, the load landed 4 k clk after the tensor core wanted it)
-        if (release == &bars->kva_empty) flush_releases();
-      }
+    };
+    auto issue_store = [&](uint32_t region, int rows_loaded, int gcol, int grow0, int gb, uint64_t* release) {
+      // (issuer, after the group barrier that follows the staging)
+      for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
+      tma_commit_group();
+      rel[n_rel++] = release;
+      // the early-key-tile region is single-buffered and the next item's K / V load is waiting for it (r02 timeline:
+      // released one step later, the load landed 4 k clk after the tensor core wanted it)
+      if (release == &bars->kva_empty) flush_releases();
     };
     int pend_j = -1, pend_b = 0, pend_h = 0, pend_it = 0;     // key tile whose dV (group 0) / dK (group 1) is complete
     bool pend_dq = false;                                     // dQ tiles of the previous item
     int dq_b = 0, dq_h = 0, dq_it = 0;
-    auto drain_dkv = [&]() {
-      if (pend_j < 0) return;
-      mbar_wait(&bars->dkv_full, dk & 1);
-      tc_fence_after_sync();
-      const bool last = pend_j == jl;
-      const uint32_t base = last ? smem_u32(sKL + kvl_buf(pend_it) * 2 * p.kvl_region) : smem_u32(sKA + pend_j * 16384);
-      const uint32_t region = base + (wg == 0 ? (last ? p.kvl_region : p.kva_region) : 0);     // V region : K region
-      drain_tile(wg == 0 ? kColDV : kColDK, &bars->dkv_free, region, last ? p.k_rows[jl] : 128,
-                 (wg == 0 ? 2 : 1) * p.inner + pend_h * kDh, pend_j * 128, pend_b,
-                 last ? &bars->kvl_empty[kvl_buf(pend_it)] : &bars->kva_empty);
-      ++dk;
-      pend_j = -1;
-    };
-    auto drain_dq = [&]() {           // group w drains query tile w (the last dkv_full wait covered every product)
-      if (!pend_dq) return;
-      pend_dq = false;
-      uint64_t* release = &bars->qdo_empty[qdo_buf(dq_it)];
-      if (wg < p.q_tiles) {
-        drain_tile(kColDQ + wg * 64, &bars->item_done, smem_u32(sQ + qdo_buf(dq_it) * p.q_region + p.q_off[wg]), p.q_rows[wg],
-                   dq_h * kDh, wg * 128, dq_b, release);
-      } else {                        // no tile for this group: only the hand-shakes
-        tc_fence_before_sync();
-        mbar_arrive(&bars->item_done);
-        if (issuer) rel[n_rel++] = release;
+    // epilogues that are due: dV / dK of a finished key tile and, at an item boundary, the dQ tiles of the finished item
+    auto drain_pending = [&]() {
+      const bool do_kv = pend_j >= 0, do_q = pend_dq;
+      if (!do_kv && !do_q) return;
+      uint32_t reg_kv = 0, reg_q = 0;
+      int rows_kv = 0, rows_q = 0;
+      uint64_t *rel_kv = nullptr, *rel_q = nullptr;
+      if (do_kv) {
+        mbar_wait(&bars->dkv_full, dk & 1);
+        tc_fence_after_sync();
+        const bool last = pend_j == jl;
+        const uint32_t base = last ? smem_u32(sKL + kvl_buf(pend_it) * 2 * p.kvl_region) : smem_u32(sKA + pend_j * 16384);
+        reg_kv = base + (wg == 0 ? (last ? p.kvl_region : p.kva_region) : 0);     // V region : K region
+        rows_kv = last ? p.k_rows[jl] : 128;
+        rel_kv = last ? &bars->kvl_empty[kvl_buf(pend_it)] : &bars->kva_empty;
+        read_and_stage(wg == 0 ? kColDV : kColDK, &bars->dkv_free, reg_kv, rows_kv);
+        ++dk;
       }
+      if (do_q) {                       // group w drains query tile w (the dkv_full wait above covered every product)
+        rel_q = &bars->qdo_empty[qdo_buf(dq_it)];
+        if (wg < p.q_tiles) {
+          reg_q = smem_u32(sQ + qdo_buf(dq_it) * p.q_region + p.q_off[wg]);
+          rows_q = p.q_rows[wg];
+        }
+        read_and_stage(kColDQ + wg * 64, &bars->item_done, reg_q, rows_q);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);                             // every row of this group's tiles is staged
+      if (issuer) {
+        if (do_q) {
+          if (rows_q > 0) issue_store(reg_q, rows_q, dq_h * kDh, wg * 128, dq_b, rel_q);
+          else rel[n_rel++] = rel_q;                           // no tile for this group: only the hand-shake
+        }
+        if (do_kv) issue_store(reg_kv, rows_kv, (wg == 0 ? 2 : 1) * p.inner + pend_h * kDh, pend_j * 128, pend_b, rel_kv);
+      }
+      pend_j = -1;
+      pend_dq = false;
     };
     if (my_items > 0) fetch_stats(0, delta_n, l2_n);
     for (int it = 0; it < my_items; ++it) {
@@ -863,9 +875,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           PF(4)
           // ---- epilogues of accumulators completed by EARLIER steps, behind this step's hand-over
           flush_releases();                 // (stores issued a step or more ago have long read their staging regions)
-          drain_dkv();
+          drain_pending();
           PF(5)
-          drain_dq();
           PF(6)
           if (stats_due) { fetch_stats(it + 1, delta_n, l2_n); stats_due = false; }
           PF(7)
@@ -875,9 +886,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       pend_dq = true; dq_b = b; dq_h = h; dq_it = it;
       if (!cross_p || it + 1 == my_items) {
         // the next item's operands reuse this item's regions (single buffers), or there is no next item: finish now
-        drain_dkv();
-        drain_dq();
-        if (issuer && n_rel > 0) flush_releases();
+        drain_pending();
+        flush_releases();
       }
     }
 #undef PF
