@@ -822,6 +822,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const bool warp_rows = (i * 128 + quad * 32) < n;            // any valid row in this warp
           const int key0 = j * 128 + wg * 64;                          // first key of this thread's half
           const bool cols_any = key0 < n;
+          const bool interior = (i * 128 + quad * 32 + 32 <= n) && (key0 + 64 <= n);      // warp-uniform
           // this step's row statistics are read from their (runtime-indexed, hence local-memory) arrays BEFORE the
           // wait: behind it the LDL latency sat on the producers' critical path (r01_ncu_attention_hot_lines_v5.txt)
           const float dl = delta[i], lg = l2[i] * kLog2e;
@@ -842,16 +843,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
                 tc_fence_before_sync();
                 mbar_arrive(&bars->sdp_free);
               }
+              if (interior) {
+                // every (row, key) of this warp's 32 x 64 block is inside the sequence (all blocks of n = 192 are either
+                // this or skipped): no per-element masks, packed fp32 arithmetic (two elements per FFMA2 / FMUL2 / FADD2)
+                const f32x2 sl2_2 = f2_splat(sl2), nlg2 = f2_splat(-lg), ndl2 = f2_splat(-dl), sc2 = f2_splat(p.scale);
 #pragma unroll
-              for (int e = 0; e < 32; e += 2) {
-                const int key = key0 + c * 32 + e;
-                const float p0 = exp2f(fmaf(__uint_as_float(sv[e]), sl2, -lg));
-                const float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lg));
-                const bool ok0 = valid && key < n, ok1 = valid && key + 1 < n;
-                const float q0 = ok0 ? p0 : 0.f, q1 = ok1 ? p1 : 0.f;
-                pw[c * 16 + (e >> 1)] = pack_bf16x2(q0, q1);
-                dw[c * 16 + (e >> 1)] = pack_bf16x2(q0 * (__uint_as_float(dv[e]) - dl) * p.scale,
-                                                    q1 * (__uint_as_float(dv[e + 1]) - dl) * p.scale);
+                for (int e = 0; e < 32; e += 2) {
+                  const f32x2 t = f2_fma(f2_packu(sv[e], sv[e + 1]), sl2_2, nlg2);
+                  float t0, t1;
+                  f2_unpack(t, t0, t1);
+                  const float p0 = exp2f(t0), p1 = exp2f(t1);
+                  const f32x2 pp = f2_pack(p0, p1);
+                  const f32x2 ds = f2_mul(f2_mul(pp, f2_add(f2_packu(dv[e], dv[e + 1]), ndl2)), sc2);
+                  float d0, d1;
+                  f2_unpack(ds, d0, d1);
+                  pw[c * 16 + (e >> 1)] = pack_bf16x2(p0, p1);
+                  dw[c * 16 + (e >> 1)] = pack_bf16x2(d0, d1);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  const int key = key0 + c * 32 + e;
+                  const float p0 = exp2f(fmaf(__uint_as_float(sv[e]), sl2, -lg));
+                  const float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lg));
+                  const bool ok0 = valid && key < n, ok1 = valid && key + 1 < n;
+                  const float q0 = ok0 ? p0 : 0.f, q1 = ok1 ? p1 : 0.f;
+                  pw[c * 16 + (e >> 1)] = pack_bf16x2(q0, q1);
+                  dw[c * 16 + (e >> 1)] = pack_bf16x2(q0 * (__uint_as_float(dv[e]) - dl) * p.scale,
+                                                      q1 * (__uint_as_float(dv[e + 1]) - dl) * p.scale);
+                }
               }
             }
           } else {
