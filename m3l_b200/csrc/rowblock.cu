@@ -135,16 +135,19 @@ M3L_DEVINL void gelu2(uint32_t x0u, uint32_t x1u, f32x2& gelu, f32x2& dgelu) {
   const f32x2 eh = f2_pack(exp2f(p0), exp2f(p1));                    // erfc(|x| / sqrt 2) / 2 = Phi(-|x|), MUFU.EX2 x 2
   gelu = f2_fma(na, eh, relu);
   if (WANT_GRAD) {
-    // Phi(x) = x >= 0 ? 1 - eh : eh = c0 + sg * eh
-    const uint32_t c0a = (uint32_t)((int32_t)(~x0u) >> 31) & 0x3f800000u, c0b = (uint32_t)((int32_t)(~x1u) >> 31) & 0x3f800000u;
-    const f32x2 sg = f2_packu((x0u & 0x80000000u) ^ 0xbf800000u, (x1u & 0x80000000u) ^ 0xbf800000u);
-    const f32x2 cdf = f2_fma(sg, eh, f2_packu(c0a, c0b));
-    const f32x2 x = f2_packu(x0u, x1u);
-    const f32x2 xx = f2_mul(f2_mul(x, x), f2_splat(-0.5f * 1.4426950408889634f));
+    // GELU'(x) = Phi(x) + x phi(x) is "odd about 1/2": GELU'(-a) = 1 - GELU'(a).  With q = GELU'(-|x|) = Phi(-|x|) -
+    // |x| phi(x) = eh + na * phi (everything already in the -|x| variable, na^2 = x^2 up to the clamp, where phi = 0):
+    //   GELU'(x) = 1/2 + sign(x) * (1/2 - q)
+    // 3 packed FMA-pipe instructions + 2 sign-bit LOP3 after the second exponential, instead of building Phi(x) and
+    // x phi(x) separately (the GELU warps are instruction-issue bound in the training form: r02 ncu, issue 49 %)
+    const f32x2 xx = f2_mul(f2_mul(na, na), f2_splat(-0.5f * 1.4426950408889634f));
     float q0, q1;
     f2_unpack(xx, q0, q1);
     const f32x2 pdf = f2_pack(exp2f(q0), exp2f(q1));                 // exp(-x^2 / 2)
-    dgelu = f2_fma(f2_mul(x, pdf), f2_splat(0.39894228040143268f), cdf);
+    const f32x2 q = f2_fma(f2_mul(na, f2_splat(0.39894228040143268f)), pdf, eh);
+    uint32_t h0, h1;
+    f2_unpacku(f2_fma(q, f2_splat(-1.0f), f2_splat(0.5f)), h0, h1);              // 1/2 - q
+    dgelu = f2_add(f2_splat(0.5f), f2_packu(h0 ^ (x0u & 0x80000000u), h1 ^ (x1u & 0x80000000u)));
   }
 }
 
