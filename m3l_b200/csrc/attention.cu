@@ -680,6 +680,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     auto fetch_stats = [&](int it, float (&d)[2], float (&l)[2]) {
       const int item = blockIdx.x + it * gridDim.x;
       const int h = item % p.heads, b = item / p.heads;
+      if (p.delta != nullptr) {
+        // all (up to four) loads are issued before any result is stored to the local-memory arrays: in the loop form
+        // below every store waited for its own load, four L2 round trips back to back (3 k clk per item in the r02
+        // timeline, on the producers' critical path)
+        const int g0 = row, g1 = 128 + row;
+        const bool v0 = g0 < n, v1 = p.q_tiles > 1 && g1 < n;
+        const float* pl = p.lse + ((size_t)b * p.heads + h) * n;
+        const float* pdl = p.delta + (size_t)b * n * p.heads + h;
+        const float la = v0 ? __ldg(pl + g0) : 0.f, lb = v1 ? __ldg(pl + g1) : 0.f;
+        const float da = v0 ? __ldg(pdl + (size_t)g0 * p.heads) : 0.f, db = v1 ? __ldg(pdl + (size_t)g1 * p.heads) : 0.f;
+        l[0] = la; l[1] = lb; d[0] = da; d[1] = db;
+        return;
+      }
       for (int i = 0; i < p.q_tiles; ++i) {
         const int grow = i * 128 + row;
         d[i] = 0.f; l[i] = 0.f;
