@@ -57,6 +57,20 @@ typedef struct m3l_gemm_args {
   const void* dot_side; /* bf16 [m, ld_dot] or NULL (bf16 output, no residual / act; n % 64 == 0): */
   int32_t ld_dot;       /*   dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]        */
   float* dot_out;       /* fp32 [m, n/64]: with out = dO and dot_side = O this is FlashAttention's delta */
+  /* Fused LayerNorm backward (ln_x != NULL; n == 256 = the normalised dimension, bf16 output, no other epilogue
+   * option): the product is the gradient w.r.t. LayerNorm(x)'s OUTPUT, dy = A B^T, and the kernel writes
+   *     out = dLN(dy; x, stats, gamma) (+ ln_skip)           [m, 256] bf16
+   * and accumulates ln_dgamma += sum_rows dy * xhat, ln_dbeta += sum_rows dy, ln_dxcol += sum_rows out (the bias
+   * gradient of the Linear whose output gradient `out` is).  dy itself never reaches HBM.  This is the backward of
+   * vit_pytorch's pre-norm blocks (`x = attn(norm(x)) + x`, `x = ff(norm(x)) + x`, pretrain_models.py:113,784):
+   * the dgrad GEMM through to_qkv / FeedForward's first Linear, nn.LayerNorm's backward and the residual add. */
+  const void* ln_x;       /* bf16 [m, 256]: the LayerNorm input */
+  const float* ln_stats;  /* fp32 [m, 2]: (mean, rstd) per row, as m3l_layernorm_fwd / m3l_ln_mlp_fwd store them */
+  const float* ln_gamma;  /* fp32 [256] */
+  const void* ln_skip;    /* bf16 [m, 256] or NULL: gradient arriving through the residual connection */
+  float* ln_dgamma;       /* fp32 [256], accumulated */
+  float* ln_dbeta;        /* fp32 [256], accumulated */
+  float* ln_dxcol;        /* fp32 [256] or NULL, accumulated */
 } m3l_gemm_args;
 
 int m3l_gemm_bf16(const m3l_gemm_args* args, void* stream);

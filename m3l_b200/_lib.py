@@ -29,6 +29,8 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("aux_out", C.c_void_p), ("aux_in", C.c_void_p),
         ("ld_aux", C.c_int32), ("alpha", C.c_float), ("colsum_out", C.c_void_p),
         ("out2", C.c_void_p), ("dot_side", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
+        ("ln_x", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_skip", C.c_void_p),
+        ("ln_dgamma", C.c_void_p), ("ln_dbeta", C.c_void_p), ("ln_dxcol", C.c_void_p),
     ]
 
 

@@ -58,8 +58,9 @@ struct GemmCfg {
   static constexpr int kResidentBytes = WS ? kWsMaxKb * kBBytes : 0;
   static constexpr int kStagingBytes = kNumEpiWarps * kStgBufs * kStgTileBytes;
   static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kScratchBytes = WS ? 0 : 4096;             // EPI_LN_BWD: row-sum exchange between column halves
   static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + kResidentBytes + kStagingBytes + 512;
+      1024 /*align slack*/ + kStages * kStageBytes + kResidentBytes + kStagingBytes + 512 + kScratchBytes;
 };
 
 struct alignas(8) GemmBarriers {
@@ -80,7 +81,24 @@ enum : int {
   EPI_GELU_BWD = 2,  // out bf16 = acc * aux_in   (aux_in = the stored GELU')
   EPI_F32 = 3,       // out fp32 = acc (+ bias)
   EPI_F32_RED = 4,   // out fp32 += acc  (TMA reduce-add, split-K)
+  EPI_LN_BWD = 5,    // out bf16 = LayerNorm backward of acc (+ skip); dgamma / dbeta / dx column sums (N == BN == 256)
 };
+
+// column sums over the 32 lanes of a warp: v[c] of lane l is element (row l, column c); returns, in lane l, the sum over
+// the rows of column l (reduce-scatter butterfly, 31 shuffles; destroys v)
+M3L_DEVINL float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 // ---- staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) == SWIZZLE_128B ------
 // thread `lane` owns row `lane` (this is how tcgen05.ld hands out the accumulator); bank-conflict free.
@@ -170,7 +188,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
     if (EPI == EPI_GELU_FWD || (EPI == EPI_BF16 && p.out2 != nullptr)) tma_prefetch_desc(&map_aux);
-    if (EPI == EPI_GELU_BWD || EPI == EPI_BF16) tma_prefetch_desc(&map_side);
+    if (EPI == EPI_GELU_BWD || EPI == EPI_BF16 || EPI == EPI_LN_BWD) tma_prefetch_desc(&map_side);
+    if (EPI == EPI_LN_BWD) tma_prefetch_desc(&map_aux);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -270,6 +289,173 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         umma_commit(&bars->tmem_full[buf]);
       }
     }
+  } else if constexpr (EPI == EPI_LN_BWD) {
+    // ------------------------------- epilogue: fused LayerNorm backward ------------------
+    // The accumulator tile holds dy = grad w.r.t. LayerNorm's output for 128 FULL rows (BN == N == 256).  Per row
+    //   g = dy * gamma,  xhat = (x - mean) * rstd,  dx = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat)) + skip
+    // thread = row; a warp owns 32 rows x one 128-column half, in two rounds of 64 columns.  Pass 1 forms the two row
+    // sums (the halves meet through 8 bytes of shared memory per row), pass 2 re-reads the accumulator from tensor memory
+    // and x through TMA, writes dx in place over the skip tile and stores it with TMA; dgamma / dbeta / column sums of dx
+    // come from register butterflies (no staging).  With K = 768 / 1024 the products of a tile take 6 - 8 k clk, the
+    // epilogue is hidden behind them: the separate LayerNorm-backward kernel (29 us, six per step) and the dy round
+    // trip through HBM disappear.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int col_half = ew >> 2;
+    const int span0 = col_half * 128;
+    const uint32_t stg = smem_u32(staging + ew * 2 * kStgTileBytes);
+    float2* scratch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);     // [2][4 quads][2 halves][32]
+    const bool has_skip = p.ln_skip != nullptr;
+    uint32_t uses0 = 0, uses1 = 0;                       // completed phases of side_full[ew][0 / 1]
+    auto load_side = [&](int b, const CUtensorMap* map, int col, int row) {      // elected lane
+      mbar_arrive_expect_tx(&bars->side_full[ew][b], kStgTileBytes);
+      tma_load_2d_u32(stg + b * kStgTileBytes, map, &bars->side_full[ew][b], col, row);
+    };
+    float acc_g[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f}, acc_c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = 0; it < sched.count; ++it) {
+      int m0, n0, split;
+      sched.get(it, BN, &m0, &n0, &split);
+      const int row0 = m0 + quad * 32;
+      const int my_row = row0 + lane;
+      const bool in = my_row < p.M;
+      float mean = 0.f, rstd = 0.f;
+      if (in) {
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + my_row);
+        mean = ms.x; rstd = ms.y;
+      }
+      // x tiles of both rounds (buffer 1 may still be read by the previous tile's last dx store)
+      if (elect_one()) {
+        load_side(0, &map_side, span0, row0);
+        tma_wait_group_read<0>();
+        fence_proxy_async_smem();
+        load_side(1, &map_side, span0 + 64, row0);
+      }
+      __syncwarp();
+      const int buf = it & 1;
+      mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + span0;
+      // ---------------- pass 1: row sums
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int r = 0; r < 2; ++r) {
+        uint32_t v[64], w[32];
+        tmem_ld_32x32(t_acc + r * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(t_acc + r * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        if (r == 0) { mbar_wait(&bars->side_full[ew][0], uses0 & 1); ++uses0; }
+        else { mbar_wait(&bars->side_full[ew][1], uses1 & 1); ++uses1; }
+        stg_load_row(stg + r * kStgTileBytes, lane, w);
+        __syncwarp();                                  // every lane has its x row of this buffer in registers
+        if (elect_one()) {                             // pass 2, round 0: x again into buffer 0, skip into buffer 1
+          fence_proxy_async_smem();
+          if (r == 0) load_side(0, &map_side, span0, row0);
+          else if (has_skip) load_side(1, &map_aux, span0, row0);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + span0 + r * 64 + j));
+          const float2 x01 = unpack_bf16x2(w[j >> 1]), x23 = unpack_bf16x2(w[(j >> 1) + 1]);
+          const float g0 = __uint_as_float(v[j]) * gm.x, g1 = __uint_as_float(v[j + 1]) * gm.y;
+          const float g2 = __uint_as_float(v[j + 2]) * gm.z, g3 = __uint_as_float(v[j + 3]) * gm.w;
+          s1 += (g0 + g1) + (g2 + g3);
+          s2 = fmaf(g0, (x01.x - mean) * rstd, s2);
+          s2 = fmaf(g1, (x01.y - mean) * rstd, s2);
+          s2 = fmaf(g2, (x23.x - mean) * rstd, s2);
+          s2 = fmaf(g3, (x23.y - mean) * rstd, s2);
+        }
+      }
+      // the two column halves of a row meet (parity-double-buffered scratch: one barrier per tile suffices)
+      float2* my_slot = scratch + (((it & 1) * 4 + quad) * 2 + col_half) * 32 + lane;
+      *my_slot = make_float2(s1, s2);
+      named_bar_sync(1 + quad, 64);
+      const float2 other = scratch[(((it & 1) * 4 + quad) * 2 + (col_half ^ 1)) * 32 + lane];
+      const float c1 = (s1 + other.x) * (1.0f / 256.0f), c2 = (s2 + other.y) * (1.0f / 256.0f);
+      // ---------------- pass 2: dx, parameter-gradient column sums (32 columns at a time: register budget)
+#pragma unroll 1
+      for (int r = 0; r < 2; ++r) {
+        mbar_wait(&bars->side_full[ew][0], uses0 & 1); ++uses0;
+        if (has_skip) { mbar_wait(&bars->side_full[ew][1], uses1 & 1); ++uses1; }
+        else if (r == 1) tma_wait_group_read<0>();       // round 0's store has left buffer 1
+#pragma unroll 1
+        for (int grp = 0; grp < 2; ++grp) {
+          uint32_t v[32], wx[16], ws[16];
+          tmem_ld_32x32(t_acc + r * 64 + grp * 32, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                  // chunks grp*4 .. grp*4+3 of this thread's 128-byte rows
+            const uint32_t off = lane * 128 + (((grp * 4 + k) ^ (lane & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(wx[4 * k]), "=r"(wx[4 * k + 1]), "=r"(wx[4 * k + 2]), "=r"(wx[4 * k + 3]) : "r"(stg + off) : "memory");
+            if (has_skip) {
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(ws[4 * k]), "=r"(ws[4 * k + 1]), "=r"(ws[4 * k + 2]), "=r"(ws[4 * k + 3])
+                           : "r"(stg + kStgTileBytes + off) : "memory");
+            } else {
+              ws[4 * k] = ws[4 * k + 1] = ws[4 * k + 2] = ws[4 * k + 3] = 0u;
+            }
+          }
+          tmem_ld_wait();
+          if (r == 1 && grp == 1) {                      // last read of this accumulator
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+          }
+          float a_g[32], a_c[32];
+          uint32_t outw[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 gm = __ldg(reinterpret_cast<const float2*>(p.ln_gamma + span0 + r * 64 + grp * 32 + j));
+            const float2 xv = unpack_bf16x2(wx[j >> 1]), kv = unpack_bf16x2(ws[j >> 1]);
+            const float dy0 = in ? __uint_as_float(v[j]) : 0.f, dy1 = in ? __uint_as_float(v[j + 1]) : 0.f;
+            const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd;
+            const float dx0 = in ? fmaf(rstd, dy0 * gm.x - c1 - xh0 * c2, kv.x) : 0.f;
+            const float dx1 = in ? fmaf(rstd, dy1 * gm.y - c1 - xh1 * c2, kv.y) : 0.f;
+            a_g[j] = dy0 * xh0; a_g[j + 1] = dy1 * xh1;
+            a_c[j] = dx0; a_c[j + 1] = dx1;
+            v[j] = __float_as_uint(dy0); v[j + 1] = __float_as_uint(dy1);
+            outw[j >> 1] = pack_bf16x2(dx0, dx1);
+          }
+          // dx in place over the skip tile (buffer 1)
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t off = lane * 128 + (((grp * 4 + k) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + kStgTileBytes + off), "r"(outw[4 * k]),
+                         "r"(outw[4 * k + 1]), "r"(outw[4 * k + 2]), "r"(outw[4 * k + 3]) : "memory");
+          }
+          float a_b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a_b[j] = __uint_as_float(v[j]);
+          const float tg = warp_colsum32(a_g, lane), tb = warp_colsum32(a_b, lane), tc = warp_colsum32(a_c, lane);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)            // static register indexing
+            if (q == r * 2 + grp) { acc_g[q] += tg; acc_b[q] += tb; acc_c[q] += tc; }
+        }
+        __syncwarp();                                   // every lane is done with the x tile of buffer 0
+        fence_proxy_async_smem();
+        if (r == 0 && elect_one()) load_side(0, &map_side, span0 + 64, row0);       // x of round 1
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&map_out, stg + kStgTileBytes, span0 + r * 64, row0);
+          tma_commit_group();
+          if (r == 0 && has_skip) {                    // skip of round 1 into the same buffer, once the store has read it
+            tma_wait_group_read<0>();
+            fence_proxy_async_smem();
+            load_side(1, &map_aux, span0 + 64, row0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // parameter gradients: lane l holds columns span0 + q * 32 + l of this warp's rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = span0 + q * 32 + lane;
+      atomicAdd(p.ln_dgamma + c, acc_g[q]);
+      atomicAdd(p.ln_dbeta + c, acc_b[q]);
+      if (p.ln_dxcol != nullptr) atomicAdd(p.ln_dxcol + c, acc_c[q]);
+    }
+    tma_wait_group_read<0>();
   } else {
     // ------------------------------- epilogue -------------------------------------------
     const int ew = warp - 2;
@@ -553,6 +739,9 @@ int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
       return launch_variant<BN, false, false, EPI_BF16, true>(plan, stream);
     }
   }
+  if constexpr (BN == 256) {
+    if (p.ln_x != nullptr) return launch_variant<BN, false, false, EPI_LN_BWD>(plan, stream);
+  }
   if (p.out_mode == 1) return launch_variant<BN, false, false, EPI_F32>(plan, stream);
   if (p.act == 1) return launch_variant<BN, false, false, EPI_GELU_FWD>(plan, stream);
   if (p.act == 2) return launch_variant<BN, false, false, EPI_GELU_BWD>(plan, stream);
@@ -604,6 +793,15 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   M3L_REQUIRE(p.dot_out == nullptr || (p.out_mode == 0 && p.act == 0 && p.residual == nullptr && p.N % 64 == 0 &&
                                        p.ld_dot % 8 == 0 && !p.a_mn_major),
               "gemm: the fused row-dot needs a plain bf16 output with N %% 64 == 0");
+  if (p.ln_x != nullptr) {
+    M3L_REQUIRE(p.N == 256 && p.out_mode == 0 && !p.a_mn_major && p.splits == 1, "gemm: the LayerNorm-backward epilogue needs n == 256, bf16 output, K-major operands");
+    M3L_REQUIRE(p.bias == nullptr && p.residual == nullptr && p.act == 0 && p.colsum_out == nullptr && p.dot_out == nullptr &&
+                    p.out2 == nullptr && p.aux_out == nullptr,
+                "gemm: the LayerNorm-backward epilogue excludes the other epilogue options");
+    M3L_REQUIRE(p.ln_stats && p.ln_gamma && p.ln_dgamma && p.ln_dbeta, "gemm: LayerNorm-backward epilogue: null pointer");
+    M3L_REQUIRE(p.ldo == 256, "gemm: LayerNorm-backward epilogue writes a contiguous [m, 256] output");
+    bn = 256;
+  }
   if (bn == 0) bn = gemm_pick_bn(p.M, p.N);
   M3L_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
   plan->bn = bn;
@@ -625,6 +823,10 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   }
   plan->map_aux = plan->map_out;
   plan->map_side = plan->map_out;
+  if (p.ln_x != nullptr) {
+    if ((s = make_tmap_2d_bf16(&plan->map_side, p.ln_x, p.M, p.N, p.N, 32))) return s;
+    if (p.ln_skip != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.ln_skip, p.M, p.N, p.N, 32))) return s;
+  }
   if (p.aux_out != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.aux_out, p.M, p.N, p.ld_aux, 32))) return s;
   if (p.out2 != nullptr && (s = make_tmap_2d_bf16(&plan->map_aux, p.out2, p.M, p.N, p.ldo, 32))) return s;
   if (p.act == 2) {
@@ -642,8 +844,8 @@ int gemm_make_plan(GemmPlan* plan, const GemmArgs& args, int bn) {
   // (M3L_GEMM_WS=0 disables it, for A/B measurements)
   static const bool ws_allowed = [] { const char* e = getenv("M3L_GEMM_WS"); return !(e && e[0] == '0'); }();
   plan->ws = ws_allowed && !p.a_mn_major && kb_total <= kWsMaxKb && p.splits == 1 && bn >= 128 &&
-             p.residual == nullptr && p.dot_out == nullptr && p.act != 2 && tiles >= 2 * device_sm_count() &&
-             tiles_n <= plan->grid;
+             p.residual == nullptr && p.dot_out == nullptr && p.act != 2 && p.ln_x == nullptr &&
+             tiles >= 2 * device_sm_count() && tiles_n <= plan->grid;
   // decoder feed-forward forward shape (GELU + GELU' outputs, K <= 256, N % 256 == 0): dedicated kernel
   // with 16 epilogue warps (M3L_GELU16=0 falls back to the generic epilogue, for A/B measurements)
   static const bool g16_allowed = [] { const char* e = getenv("M3L_GELU16"); return !(e && e[0] == '0'); }();
@@ -690,6 +892,8 @@ extern "C" int m3l_gemm_bf16(const m3l_gemm_args* a, void* stream) {
   g.act = a->act; g.aux_out = (m3l::bf16*)a->aux_out; g.aux_in = (const m3l::bf16*)a->aux_in;
   g.ld_aux = a->ld_aux; g.alpha = a->alpha; g.colsum_out = a->colsum_out; g.out2 = (m3l::bf16*)a->out2;
   g.dot_side = (const m3l::bf16*)a->dot_side; g.ld_dot = a->ld_dot; g.dot_out = a->dot_out;
+  g.ln_x = (const m3l::bf16*)a->ln_x; g.ln_stats = a->ln_stats; g.ln_gamma = a->ln_gamma;
+  g.ln_skip = (const m3l::bf16*)a->ln_skip; g.ln_dgamma = a->ln_dgamma; g.ln_dbeta = a->ln_dbeta; g.ln_dxcol = a->ln_dxcol;
   m3l::GemmPlan plan;
   int s = m3l::gemm_make_plan(&plan, g, a->bn);
   if (s) return s;

@@ -30,6 +30,14 @@ struct GemmArgs {
   const bf16* dot_side = nullptr;   // [M, ld_dot] bf16: dot_out[row, c] = sum_{j<64} out[row, 64c+j] * dot_side[row, 64c+j]
   int ld_dot = 0;
   float* dot_out = nullptr;         // [M, N/64] fp32
+  // fused LayerNorm backward epilogue (EPI_LN_BWD; see m3l_gemm_args in include/m3l_b200.h)
+  const bf16* ln_x = nullptr;
+  const float* ln_stats = nullptr;
+  const float* ln_gamma = nullptr;
+  const bf16* ln_skip = nullptr;
+  float* ln_dgamma = nullptr;
+  float* ln_dbeta = nullptr;
+  float* ln_dxcol = nullptr;
 };
 
 struct GemmPlan {

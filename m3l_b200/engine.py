@@ -34,6 +34,22 @@ def _sm_count() -> int:
     return n
 # M3L_FUSED_MLP=0: the unfused LayerNorm / FF1+GELU / FF2 kernels instead of csrc/rowblock.cu (A/B measurements)
 _FUSED_MLP = os.environ.get("M3L_FUSED_MLP", "1") != "0"
+# M3L_FUSED_LN_BWD=0: separate dgrad GEMM + LayerNorm-backward kernels instead of the GEMM's fused epilogue (A/B measurements)
+_FUSED_LN_BWD = os.environ.get("M3L_FUSED_LN_BWD", "1") != "0"
+# the fused epilogue needs BN = 256 tiles of 128 full rows: below this many rows the tiles no longer cover the SMs (the
+# encoder's 2560 rows are 20 tiles: measured 207 -> 247 us for the encoder backward) and the two separate kernels win
+_FUSED_LN_BWD_MIN_ROWS = int(os.environ.get("M3L_FUSED_LN_BWD_MIN_ROWS", "16384"))
+
+
+def _dgrad_ln_bwd(dy_in, w_t, x, stats, gamma, dgamma, dbeta, skip, dx_colsum):
+    """dx = dLN(dy_in @ w_t.T; x, stats, gamma) + skip, with the LayerNorm parameter gradients and the column sums of
+    dx accumulated: one GEMM with the LayerNorm backward in its epilogue when the normalised dimension is 256 (the
+    gradient w.r.t. the LayerNorm output never reaches HBM), else the dgrad GEMM followed by the LayerNorm-backward kernel."""
+    if _FUSED_LN_BWD and x.shape[1] == 256 and x.shape[0] >= _FUSED_LN_BWD_MIN_ROWS:
+        return ops.gemm(dy_in, w_t, ln_bwd=dict(x=x, stats=stats, gamma=gamma, skip=skip, dgamma=dgamma, dbeta=dbeta,
+                                               dx_colsum=dx_colsum))
+    dxn = ops.gemm(dy_in, w_t)
+    return ops.layernorm_bwd(dxn, x, stats, gamma, dgamma=dgamma, dbeta=dbeta, skip=skip, dx_colsum=dx_colsum)
 
 
 @dataclass
@@ -230,9 +246,8 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
         dpre = ops.gemm(dx, A.bf_t(pf + ".net.4.weight"), act=ops.GELU_BWD, aux_in=pre,
                         colsum_out=G(pf + ".net.1.bias"))
         fork.wgrad(dpre, xn2, G(pf + ".net.1.weight"))
-        dxn2 = ops.gemm(dpre, A.bf_t(pf + ".net.1.weight"))
-        dx_mid = ops.layernorm_bwd(dxn2, x_mid, st2, A.f32(pf + ".net.0.weight"), dgamma=G(pf + ".net.0.weight"),
-                                   dbeta=G(pf + ".net.0.bias"), skip=dx, dx_colsum=G(pa + ".to_out.0.bias"))
+        dx_mid = _dgrad_ln_bwd(dpre, A.bf_t(pf + ".net.1.weight"), x_mid, st2, A.f32(pf + ".net.0.weight"),
+                               G(pf + ".net.0.weight"), G(pf + ".net.0.bias"), dx, G(pa + ".to_out.0.bias"))
         # ---- attention branch: x_mid = x + Wo attn(Wqkv LN1(x)) + bo
         fork.wgrad(dx_mid, o, G(pa + ".to_out.0.weight"))
         # dO, and in the same epilogue delta = rowsum(dO * O) per head (dim_head == 64 == one epilogue round)
@@ -240,10 +255,9 @@ def stack_bwd(A: ParamArena, G: GradView, spec: StackSpec, dx: torch.Tensor, B: 
         do = ops.gemm(dx_mid, A.bf_t(pa + ".to_out.0.weight"), dot_side=o if delta is not None else None, dot_out=delta)
         dqkv = ops.attention_bwd(qkv, o, do, lse, B, n, spec.heads, spec.dim_head, scale, delta=delta)
         fork.wgrad(dqkv, xn1, G(pa + ".to_qkv.weight"))
-        dxn1 = ops.gemm(dqkv, A.bf_t(pa + ".to_qkv.weight"))
         prev_bias = G(f"{spec.prefix}.layers.{l - 1}.1.net.4.bias") if l > 0 else None
-        dx_in = ops.layernorm_bwd(dxn1, x, st1, A.f32(pa + ".norm.weight"), dgamma=G(pa + ".norm.weight"),
-                                  dbeta=G(pa + ".norm.bias"), skip=dx_mid, dx_colsum=prev_bias)
+        dx_in = _dgrad_ln_bwd(dqkv, A.bf_t(pa + ".to_qkv.weight"), x, st1, A.f32(pa + ".norm.weight"),
+                              G(pa + ".norm.weight"), G(pa + ".norm.bias"), dx_mid, prev_bias)
         fork.join()          # this layer's wgrad operands (dx, dpre, dx_mid, dqkv) die below
         dx = dx_in
     return dx

@@ -45,7 +45,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None,
          alpha: float = 1.0, colsum_out: Optional[torch.Tensor] = None,
          dot_side: Optional[torch.Tensor] = None, dot_out: Optional[torch.Tensor] = None,
-         out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out2: Optional[torch.Tensor] = None, ln_bwd: Optional[dict] = None) -> torch.Tensor:
     """out[m, n] = epilogue(alpha * sum_k A[m, k] B[n, k]).
 
     mn_major=False: a is [M, K], b is [N, K] (nn.Linear forward: x @ W.T).
@@ -92,6 +92,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, mn_major: bool = False, out: Optio
         assert dot_side.dtype == torch.bfloat16 and dot_side.stride(1) == 1 and dot_side.shape == (M, N)
         assert dot_out is not None and dot_out.dtype == torch.float32 and dot_out.is_contiguous() and dot_out.shape == (M, N // 64)
         args.dot_side, args.ld_dot, args.dot_out = ptr(dot_side), dot_side.stride(0), ptr(dot_out)
+    if ln_bwd is not None:
+        # fused LayerNorm backward epilogue: out = dLN(a @ b.T; x, stats, gamma) (+ skip); dgamma / dbeta / dxcol accumulated
+        x, st, gm = ln_bwd["x"], ln_bwd["stats"], ln_bwd["gamma"]
+        assert N == 256 and out.dtype == torch.bfloat16 and x.shape == (M, N) and x.dtype == torch.bfloat16 and x.is_contiguous()
+        assert st.shape == (M, 2) and st.dtype == torch.float32 and gm.dtype == torch.float32 and gm.numel() == N
+        sk = ln_bwd.get("skip")
+        assert sk is None or (sk.shape == (M, N) and sk.dtype == torch.bfloat16 and sk.is_contiguous())
+        args.ln_x, args.ln_stats, args.ln_gamma, args.ln_skip = ptr(x), ptr(st), ptr(gm), ptr(sk)
+        args.ln_dgamma, args.ln_dbeta, args.ln_dxcol = ptr(ln_bwd["dgamma"]), ptr(ln_bwd["dbeta"]), ptr(ln_bwd.get("dx_colsum"))
     check(_lib.load().m3l_gemm_bf16(C.byref(args), current_stream()), "m3l_gemm_bf16")
     return out
 

@@ -585,3 +585,39 @@ def test_errors_are_loud(ops):
     qkv = torch.randn(2 * 300, 3 * 64, device=DEV).bfloat16()  # n = 300 > 256
     with pytest.raises(M3LError):
         ops.attention_fwd(qkv, 2, 300, 1, 64, 0.125)
+
+
+@pytest.mark.parametrize("M,K,with_skip", [(49152, 1024, True), (2560, 512, True), (1000, 768, False), (128, 64, True)])
+def test_gemm_layernorm_backward_epilogue(ops, M, K, with_skip):
+    """dgrad GEMM with the fused LayerNorm-backward epilogue (EPI_LN_BWD) against the two separate kernels it replaces
+    (gemm -> m3l_layernorm_bwd) and against torch autograd of LayerNorm in fp32."""
+    torch.manual_seed(3)
+    D = 256
+    a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(D, K, device=DEV) * (K ** -0.5)).bfloat16()
+    x = torch.randn(M, D, device=DEV).bfloat16()
+    gamma = torch.rand(D, device=DEV) + 0.5
+    skip = torch.randn(M, D, device=DEV).bfloat16() if with_skip else None
+    _, stats = ops.layernorm_fwd(x, gamma, torch.zeros(D, device=DEV), want_stats=True)
+    # separate kernels
+    dy = ops.gemm(a, w)
+    dg0, db0, dc0 = (torch.zeros(D, device=DEV) for _ in range(3))
+    dx0 = ops.layernorm_bwd(dy, x, stats, gamma, dgamma=dg0, dbeta=db0, skip=skip, dx_colsum=dc0)
+    # fused
+    dg1, db1, dc1 = (torch.zeros(D, device=DEV) for _ in range(3))
+    dx1 = ops.gemm(a, w, ln_bwd=dict(x=x, stats=stats, gamma=gamma, skip=skip, dgamma=dg1, dbeta=db1, dx_colsum=dc1))
+    assert dx1.shape == (M, D) and dx1.dtype == torch.bfloat16
+    assert cos(dx1, dx0) > 0.9999 and rel_err(dx1, dx0) < 2e-2
+    for name, u, v in (("dgamma", dg1, dg0), ("dbeta", db1, db0), ("dx_colsum", dc1, dc0)):
+        assert cos(u, v) > 0.9999 and rel_err(u, v) < 2e-2, name
+    # fp32 autograd statement
+    xr = x.float().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = torch.zeros(D, device=DEV, requires_grad=True)
+    y = F.layer_norm(xr, (D,), gr, br)
+    dyr = a.float() @ w.float().T
+    y.backward(dyr)
+    ref = xr.grad + (skip.float() if with_skip else 0)
+    assert cos(dx1, ref) > 0.9995
+    assert cos(dg1, gr.grad) > 0.9995 and cos(db1, br.grad) > 0.9995
+    assert cos(dc1, ref.sum(0)) > 0.999
