@@ -729,14 +729,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     // the thread of each group that issues its TMA stores: in the LAST lane quadrant, which has no rows in the steps of
     // a partial second query tile and can afford to wait for a store's shared-memory read when a region is needed back
     // at once (quadrant 0 is the critical path of every step)
-    const bool issuer = quad == 3 && lane == 0;
+    // The whole warp runs the bookkeeping (warp-uniform) and the stores are issued behind `elect.sync`, which keeps the
+    // TMA operands in uniform registers (`lane == 0` made every UTMASTG a 20-instruction waterfall loop; elect.sync on a
+    // full warp always names the same lane, so commit / wait groups stay with one thread).
+    const bool issuer = quad == 3;
     const bool cross_p = p.qdo_bufs == 2 && p.kvl_bufs == 2;   // operands of the next item have their own buffers
     uint64_t* rel[4];                                        // (issuer) regions to release once the stores have read them
     int n_rel = 0;
     auto flush_releases = [&]() {
       if (issuer && n_rel > 0) {
-        tma_wait_group_read<0>();
-        for (int k = 0; k < n_rel; ++k) mbar_arrive(rel[k]);
+        if (elect_one()) {
+          tma_wait_group_read<0>();
+          for (int k = 0; k < n_rel; ++k) mbar_arrive(rel[k]);
+        }
         n_rel = 0;
       }
     };
@@ -769,9 +774,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       }
     };
     auto issue_store = [&](uint32_t region, int rows_loaded, int gcol, int grow0, int gb, uint64_t* release) {
-      // (issuer, after the group barrier that follows the staging)
-      for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
-      tma_commit_group();
+      // (issuer warp, after the group barrier that follows the staging)
+      if (elect_one()) {
+        for (int r = 0; r < rows_loaded; r += 64) tma_store_3d(&map_dqkv, region + r * 128, gcol, grow0 + r, gb);
+        tma_commit_group();
+      }
       rel[n_rel++] = release;
       // the early-key-tile region is single-buffered and the next item's K / V load is waiting for it (r02 timeline:
       // released one step later, the load landed 4 k clk after the tensor core wanted it)
