@@ -157,7 +157,8 @@ def _ln_mlp_reference(x, gamma, beta, w1, b1, w2, b2):
     return out, torch.cat([mean, rstd], 1), xn, h, pre.grad
 
 
-@pytest.mark.parametrize("M,hidden", [(128, 128), (128, 1024), (777, 512), (2560, 512), (49152, 1024), (148 * 128 * 2 + 5, 256)])
+@pytest.mark.parametrize("M,hidden", [(128, 128), (128, 1024), (777, 512), (2560, 512), (2560, 1024), (49152, 1024),
+                                      (148 * 128 * 2 + 5, 256)])
 def test_ln_mlp_fused_block(ops, M, hidden):
     torch.manual_seed(5)
     D = 256
@@ -188,6 +189,11 @@ def test_ln_mlp_fused_block(ops, M, hidden):
     o4, stats4, xn4, h4, gp4 = ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, save=True, out=buf, out_has_x=True)
     assert rel_err(o4, ref_out) < 1e-2 and torch.equal(stats4, stats) and torch.equal(xn4, xn)
     assert torch.equal(h4, h) and torch.equal(gp4, gp)
+    # inference form accumulating into a copy of x
+    buf5 = x.clone()
+    o5 = ops.ln_mlp_fwd(x, gamma, beta, w1, b1, w2, b2, out=buf5, out_has_x=True)
+    assert rel_err(o5, ref_out) < 1e-2
+    assert (o5.float() - ref_out).abs().amax(1).max().item() < 6e-2 * ref_out.abs().max().item()
 
 
 def test_ln_mlp_rejects_unsupported_shapes(ops):
