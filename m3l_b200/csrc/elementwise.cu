@@ -8,6 +8,8 @@
 //   LN(D) + modality + pos    models/pretrain_models.py:771,778,202-219
 //   decoder assembly          models/pretrain_models.py:270-307
 //   masked MSE                models/pretrain_models.py:327-340 (and :311-322 for early_conv_masking)
+#include <type_traits>
+
 #include "common.cuh"
 #include "m3l_internal.h"
 
@@ -82,13 +84,19 @@ struct PatchSrc {
   float lo, span;
 };
 
+// source pointer of sensor s WITHOUT indexing the kernel parameter dynamically (a runtime index makes the compiler copy
+// the whole struct to local memory: 120-byte stack frame and an LDL on every row's critical path)
+M3L_DEVINL const float* src_of(const PatchSrc& ps, int s) {
+  return s == 0 ? ps.src[0] : (s == 1 ? ps.src[1] : (s == 2 ? ps.src[2] : ps.src[3]));
+}
+
 M3L_DEVINL const float* patch_origin(const PatchSrc& ps, int b, int tok, int* sensor) {
   const int t = tok - ps.tok_base;
   const int s = t / ps.n_per_src;
   const int tl = t - s * ps.n_per_src;
   const int hh = tl / ps.gw, ww = tl - hh * ps.gw;
   *sensor = s;
-  return ps.src[s] + ((size_t)b * ps.C * ps.H + (size_t)hh * ps.ph) * ps.W + (size_t)ww * ps.pw;
+  return src_of(ps, s) + ((size_t)b * ps.C * ps.H + (size_t)hh * ps.ph) * ps.W + (size_t)ww * ps.pw;
 }
 
 // element e of the flattened patch, order (p1, p2, c) with c fastest
@@ -225,8 +233,8 @@ M3L_DEVINL void gather_patch_raw(const PatchSrc& ps, const T* base, float* dst, 
 M3L_DEVINL void gather_patch(const PatchSrc& ps, int b, int tok, float* dst, int pitch, int t, int nthr) {
   int sensor;
   const long long off = raw_origin(ps, b, tok, &sensor);
-  if (ps.u8) gather_patch_raw(ps, reinterpret_cast<const unsigned char*>(ps.src[sensor]) + off, dst, pitch, t, nthr);
-  else gather_patch_raw(ps, ps.src[sensor] + off, dst, pitch, t, nthr);
+  if (ps.u8) gather_patch_raw(ps, reinterpret_cast<const unsigned char*>(src_of(ps, sensor)) + off, dst, pitch, t, nthr);
+  else gather_patch_raw(ps, src_of(ps, sensor) + off, dst, pitch, t, nthr);
 }
 
 // Two-stage column reduction without contended atomics (same-sector fp32 atomics serialise at
@@ -1026,9 +1034,19 @@ __global__ void rowclass_sum_kernel(const bf16* __restrict__ dx, int B, int nv, 
 //    conflict free (the first version put all 8 p1 rows of a lane group on one bank).  The final
 //    loss reduction over the block partials is done by ALL threads of the last block in a fixed
 //    order (deterministic, and not a 1184-long chain of L2 round trips on one thread).
+//    GATHER selects how the target patch reaches shared memory.  The generic loops (0) issue one wide load, scatter
+//    its values, then issue the next: with run lengths only known at run time nothing is hoisted, and a row costs up to
+//    six DEPENDENT DRAM round trips (r02 ncu source page: 34 % of all stall samples on the first scatter store, long
+//    scoreboard; 50 us for 118 MB).  The specialised forms load every run of the lane into registers first and
+//    scatter afterwards (compile-time run count SEGS and length V4):
+//      1  channel planes, fp32, x contiguous (layout 0 maps, or raw tactile [B, F, 6, h, w]): SEGS runs of 4*V4 floats
+//      2  interleaved fp32 frames (raw images [B, F, H, W, 3]): one run of 4*V4 floats per lane
+//      3  interleaved uint8 frames: one run of 4*V4 bytes per lane
+//    The token index of the warp's NEXT row is fetched one iteration ahead (it heads the chain of every row).
 // ------------------------------------------------------------------------------------------
 constexpr int kMseMaxT = 8;   // column sums kept in registers: P <= 128 * 4 * ... = 1024
-__global__ void __launch_bounds__(256)
+template <int GATHER, int SEGS, int V4, int T, int MINB>      // T: float4 per lane and row (P <= 128 T); MINB: blocks per SM
+__global__ void __launch_bounds__(256, MINB)
 mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, int col0, int ncols, int rows,
                 const float* __restrict__ pred, float weight, bf16* __restrict__ dpred,
                 float* __restrict__ loss_acc, float* __restrict__ dcolsum, int pitch, void* ws) {
@@ -1045,28 +1063,116 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
   const int src_rows = ps.C * ps.ph;
   const float w2 = 2.f * weight;
   float acc = 0.f;
-  float cs[kMseMaxT][4];
+  float cs[T][4];
 #pragma unroll
-  for (int t = 0; t < kMseMaxT; ++t) cs[t][0] = cs[t][1] = cs[t][2] = cs[t][3] = 0.f;
+  for (int t = 0; t < T; ++t) cs[t][0] = cs[t][1] = cs[t][2] = cs[t][3] = 0.f;
   if (dcolsum) {
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_cs[i] = 0.f;
   }
-  for (int r = blockIdx.x * nwarps + warp; r < rows; r += gridDim.x * nwarps) {
+  auto token_of = [&](int r) -> int {
     const int b = r / ncols, jj = r - b * ncols;
-    const int tok = tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+    return tok_idx ? (int)tok_idx[(size_t)b * idx_ld + col0 + jj] : ps.tok_base + jj;
+  };
+  const int stride = gridDim.x * nwarps;
+  int r = blockIdx.x * nwarps + warp;
+  int tok_next = r < rows ? token_of(r) : 0;
+  for (; r < rows; r += stride) {
+    const int b = r / ncols;
+    const int tok = tok_next;
+    if (r + stride < rows) tok_next = token_of(r + stride);      // consumed one iteration later
     int sensor = 0;
-    const float* origin = ps.layout == 0 ? patch_origin(ps, b, tok, &sensor) : nullptr;
+    const float* origin = (GATHER == 0 && ps.layout == 0) ? patch_origin(ps, b, tok, &sensor) : nullptr;
     // the predictions of this row are requested BEFORE the target gather so that both global round trips
     // overlap (they used to be exposed back to back, one row at a time per warp)
     const float* prow = pred + (size_t)r * P;
-    float4 pvr[kMseMaxT];
+    float4 pvr[T];
 #pragma unroll
-    for (int t = 0; t < kMseMaxT; ++t) {
+    for (int t = 0; t < T; ++t) {
       const int e = t * 128 + lane * 4;
       if (e < P) pvr[t] = __ldcs(reinterpret_cast<const float4*>(prow + e));
     }
-    if (ps.layout != 0) gather_patch(ps, b, tok, patch, pitch, lane, 32);     // raw observations (vt_load fused)
-    for (int i = lane; i < (ps.layout == 0 ? src_rows : 0); i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
+    if constexpr (GATHER == 1) {
+      // channel planes: run i = (p1, c), c fastest, 4 * V4 floats along x.  All loads first, then the scatter.
+      const float* base;
+      if (ps.layout == 0) {
+        base = patch_origin(ps, b, tok, &sensor);
+      } else {
+        const long long off = raw_origin(ps, b, tok, &sensor);
+        base = src_of(ps, sensor) + off;
+      }
+      float4 tg[SEGS][V4];
+#pragma unroll
+      for (int k = 0; k < SEGS; ++k) {
+        const int i = lane + 32 * k;
+        if (i < src_rows) {
+          const int p1 = i / ps.C, c = i - p1 * ps.C;
+          const float* src;
+          if (ps.layout == 0) {
+            src = base + ((size_t)c * ps.H + p1) * ps.W;
+          } else {
+            const int f = c / ps.cg, ch = c - f * ps.cg;
+            src = base + (long long)f * ps.sf + (long long)ch * ps.sch + (long long)p1 * ps.sy;
+          }
+#pragma unroll
+          for (int v = 0; v < V4; ++v) tg[k][v] = __ldg(reinterpret_cast<const float4*>(src) + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SEGS; ++k) {
+        const int i = lane + 32 * k;
+        if (i < src_rows) {
+          const int p1 = i / ps.C, c = i - p1 * ps.C;
+          float* d = patch + p1 * pitch + c;
+#pragma unroll
+          for (int v = 0; v < V4; ++v) {
+            const float4 t4 = tg[k][v];
+            if (ps.layout == 0) {
+              d[(4 * v + 0) * ps.C] = t4.x; d[(4 * v + 1) * ps.C] = t4.y;
+              d[(4 * v + 2) * ps.C] = t4.z; d[(4 * v + 3) * ps.C] = t4.w;
+            } else {
+              d[(4 * v + 0) * ps.C] = raw_norm(ps, t4.x); d[(4 * v + 1) * ps.C] = raw_norm(ps, t4.y);
+              d[(4 * v + 2) * ps.C] = raw_norm(ps, t4.z); d[(4 * v + 3) * ps.C] = raw_norm(ps, t4.w);
+            }
+          }
+        }
+      }
+    } else if constexpr (GATHER == 2 || GATHER == 3) {
+      // interleaved frames: run i = (p1, f), f fastest; run element q = p2 * cg + ch goes to (p1, p2, f * cg + ch)
+      using RawT = typename std::conditional<GATHER == 2, float, unsigned char>::type;
+      using VecT = typename std::conditional<GATHER == 2, float4, unsigned int>::type;
+      const int F = ps.C / ps.cg;
+      const long long off = raw_origin(ps, b, tok, &sensor);
+      const RawT* base = reinterpret_cast<const RawT*>(src_of(ps, sensor)) + off;
+      const int p1 = lane / F, f = lane - p1 * F;
+      VecT tg[V4];
+      if (lane < F * ps.ph) {
+        const RawT* src = base + (long long)f * ps.sf + (long long)p1 * ps.sy;
+#pragma unroll
+        for (int v = 0; v < V4; ++v) tg[v] = __ldg(reinterpret_cast<const VecT*>(src) + v);
+        float* d = patch + p1 * pitch + f * ps.cg;
+        int p2 = 0, ch = 0;
+#pragma unroll
+        for (int v = 0; v < V4; ++v) {
+          float vv[4];
+          if constexpr (GATHER == 2) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&tg[v]);
+            vv[0] = raw_norm(ps, t4.x); vv[1] = raw_norm(ps, t4.y); vv[2] = raw_norm(ps, t4.z); vv[3] = raw_norm(ps, t4.w);
+          } else {
+            const unsigned int w = *reinterpret_cast<const unsigned int*>(&tg[v]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vv[e] = raw_norm_u8(ps, (w >> (8 * e)) & 0xffu);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            d[p2 * ps.C + ch] = vv[e];
+            if (++ch == ps.cg) { ch = 0; ++p2; }
+          }
+        }
+      }
+    } else if (ps.layout != 0) {
+      gather_patch(ps, b, tok, patch, pitch, lane, 32);     // raw observations (vt_load fused)
+    }
+    for (int i = lane; i < (origin != nullptr ? src_rows : 0); i += 32) {      // one (patch row, channel) per lane: pw contiguous floats
       const int p1 = i / ps.C, c = i - p1 * ps.C;
       const float* src = origin + ((size_t)c * ps.H + p1) * ps.W;
       float* dst = patch + p1 * pitch + c;
@@ -1083,7 +1189,7 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
     __syncwarp();
     bf16* drow = dpred + (size_t)r * P;
 #pragma unroll
-    for (int t = 0; t < kMseMaxT; ++t) {
+    for (int t = 0; t < T; ++t) {
       const int e = t * 128 + lane * 4;
       if (e < P) {
         const int p1 = e / rowlen;
@@ -1096,7 +1202,7 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
         cs[t][0] += g0; cs[t][1] += g1; cs[t][2] += g2; cs[t][3] += g3;
       }
     }
-    for (int e = kMseMaxT * 128 + lane * 4; e < P; e += 128) {      // P > 1024: no column sums
+    for (int e = T * 128 + lane * 4; e < P; e += 128) {      // P > 1024: no column sums
       const int p1 = e / rowlen;
       const float4 tv = *reinterpret_cast<const float4*>(patch + p1 * pitch + (e - p1 * rowlen));
       const float4 pv = *reinterpret_cast<const float4*>(prow + e);
@@ -1109,7 +1215,7 @@ mse_loss_kernel(PatchSrc ps, const int64_t* __restrict__ tok_idx, int idx_ld, in
   if (dcolsum) {
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < kMseMaxT; ++t) {
+    for (int t = 0; t < T; ++t) {
       const int e = t * 128 + lane * 4;
       if (e < P) {
         atomicAdd(&s_cs[e], cs[t][0]); atomicAdd(&s_cs[e + 1], cs[t][1]);
@@ -1480,8 +1586,8 @@ vt_load_kernel(PatchSrc ps, int sensor, long long total, float* __restrict__ out
     const int f = c / ps.cg, ch = c - f * ps.cg;
     const long long off = (long long)b * ps.sb + (long long)f * ps.sf + (long long)ch * ps.sch + (long long)y * ps.sy +
                           (long long)x * ps.sx;
-    out[i] = ps.u8 ? raw_norm_u8(ps, reinterpret_cast<const unsigned char*>(ps.src[sensor])[off])
-                   : raw_norm(ps, ps.src[sensor][off]);
+    out[i] = ps.u8 ? raw_norm_u8(ps, reinterpret_cast<const unsigned char*>(src_of(ps, sensor))[off])
+                   : raw_norm(ps, src_of(ps, sensor)[off]);
   }
 }
 
@@ -1717,11 +1823,6 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
   const int pitch = rowlen + pad;
   const size_t smem = ((size_t)8 * ps.ph * pitch + ps.P) * sizeof(float);
   M3L_REQUIRE(smem <= 160 * 1024, "mse_loss: patch dim %d unsupported", ps.P);
-  static bool configured = false;
-  if (!configured) {
-    M3L_CUDA(cudaFuncSetAttribute(mse_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
   const int rows = batch * ncols;
   int grid = (rows + 15) / 16;                       // two rows per warp: the per-row gather chain is latency bound
   // one resident wave (126 registers: two blocks of 256 threads per SM): measured 53.8 -> 43.0 us against 4-8 blocks
@@ -1730,10 +1831,49 @@ extern "C" int m3l_mse_loss(const m3l_patch_source* src, int batch, const int64_
   if (grid > cap) grid = cap;
   M3L_REQUIRE(workspace != nullptr && workspace_bytes >= 256 + (size_t)grid * sizeof(float),
               "mse_loss: workspace too small (%zu bytes)", workspace_bytes);
-  M3L_CUDA(launch_kernel(mse_loss_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, ps, tok_idx, idx_ld, col0,
-                         ncols, rows, pred, weight, (bf16*)dpred_bf16, loss_acc, dpred_colsum, pitch, workspace));
-  M3L_CUDA(cudaGetLastError());
-  return M3L_OK;
+  // which gather (see the kernel): the specialised forms need every run 16-byte (fp32) / 4-byte (uint8) aligned
+  static const bool fast_on = [] { const char* e = getenv("M3L_MSE_FAST"); return !(e && e[0] == '0'); }();
+  auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+  bool ptrs16 = true, ptrs4 = true;
+  for (int i = 0; i < 4; ++i)
+    if (ps.src[i] != nullptr) { ptrs16 = ptrs16 && al(ps.src[i], 16); ptrs4 = ptrs4 && al(ps.src[i], 4); }
+  int mode = 0;
+  const int segs = (ps.C * ps.ph + 31) / 32;
+  if (fast_on && !ps.u8 && ps.pw % 4 == 0 && ptrs16 && segs <= 3 && (ps.pw == 8 || ps.pw == 4)) {
+    if (ps.layout == 0 && ps.W % 4 == 0 && ((long long)ps.H * ps.W) % 4 == 0) mode = ps.pw == 8 ? 18 : 14;
+    if (ps.layout == 1 && ps.sx == 1 && ps.sb % 4 == 0 && ps.sf % 4 == 0 && ps.sch % 4 == 0 && ps.sy % 4 == 0)
+      mode = ps.pw == 8 ? 18 : 14;
+  }
+  if (fast_on && ps.layout == 1 && ps.sch == 1 && ps.sx == ps.cg && ps.pw * ps.cg == 24 && (ps.C / ps.cg) * ps.ph <= 32 &&
+      ps.sb % 4 == 0 && ps.sf % 4 == 0 && ps.sy % 4 == 0)
+    mode = ps.u8 ? (ptrs4 ? 3 : 0) : (ptrs16 ? 2 : 0);
+  if (mode == 14 && ps.P <= 256 && segs <= 2) mode = 15;
+  if (mode == 15) {
+    // 64 registers: four blocks per SM, still ONE resident wave
+    grid = (rows + 15) / 16;
+    if (grid > device_sm_count() * 4) grid = device_sm_count() * 4;
+    M3L_REQUIRE(workspace_bytes >= 256 + (size_t)grid * sizeof(float), "mse_loss: workspace too small (%zu bytes)",
+                workspace_bytes);
+  }
+  static bool configured[6] = {false, false, false, false, false, false};     // per kernel variant
+  auto go = [&](auto kern, int slot) -> int {
+    if (!configured[slot]) {
+      M3L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured[slot] = true;
+    }
+    M3L_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, (cudaStream_t)stream, ps, tok_idx, idx_ld, col0, ncols, rows,
+                           pred, weight, (bf16*)dpred_bf16, loss_acc, dpred_colsum, pitch, workspace));
+    M3L_CUDA(cudaGetLastError());
+    return M3L_OK;
+  };
+  switch (mode) {
+    case 18: return go(mse_loss_kernel<1, 3, 2, 8, 2>, 1);    // planes, runs of 8 floats (64 x 64 x 12 frames, patch 8)
+    case 14: return go(mse_loss_kernel<1, 3, 1, 8, 2>, 2);    // planes, runs of 4 floats, any patch dim
+    case 15: return go(mse_loss_kernel<1, 2, 1, 2, 4>, 5);    // ... patch dim <= 256 (32 x 32 x 12 tactile maps, patch 4)
+    case 2: return go(mse_loss_kernel<2, 1, 6, 8, 2>, 3);     // raw fp32 frames [B, F, H, W, 3], patch 8
+    case 3: return go(mse_loss_kernel<3, 1, 6, 8, 2>, 4);     // raw uint8 frames
+    default: return go(mse_loss_kernel<0, 1, 1, 8, 2>, 0);
+  }
 }
 
 extern "C" int m3l_colsum(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream) {
