@@ -251,7 +251,11 @@ def per_kernel_roofline(peaks, ms_per_step):
     tf, hb = peaks["tf_burst"], peaks["hbm_gbs"]
     rows = []
 
+    only = [k for k in os.environ.get("M3L_PER_KERNEL_ONLY", "").split(",") if k]     # (ncu captures of single entries)
+
     def add(name, fn, launches, flops=None, nbytes=None, key=None):
+        if only and key not in only:
+            return
         sec = time_kernel_cold(fn)
         ent = {"kernel": name, "us_per_launch": sec * 1e6, "launches_per_step": launches,
                "us_per_step": sec * 1e6 * launches, "share_of_step": sec * 1e3 * launches / ms_per_step}
@@ -282,17 +286,26 @@ def per_kernel_roofline(peaks, ms_per_step):
     gp = h.clone()
     add("gemm_bf16_kernel<256,0,0,2,0> dgrad dpre = (dx W2) * GELU' [49152 x 1024, K=256]",
         lambda: ops.gemm(dy, w2.t().contiguous(), act=ops.GELU_BWD, aux_in=gp), 3, flops=2.0 * M * H * D, key="dgrad_ff2")
-    w1t = w1.t().contiguous()
-    add("gemm_bf16_kernel<256,0,0,0,0> dgrad dxn = dpre W1 [49152 x 256, K=1024]", lambda: ops.gemm(dh, w1t), 3,
-        flops=2.0 * M * H * D, key="dgrad_ff1")
+    # dgrad through FF1 / to_qkv with the LayerNorm backward (dx, dgamma, dbeta, column sums, + residual gradient) in the
+    # GEMM epilogue: what used to be a dgrad GEMM + ln_bwd_pipe_kernel, six per step
+    w1t, wqkvt = w1.t().contiguous(), wqkv.t().contiguous()
+    dg, db, dc = (torch.zeros(D, device=dev) for _ in range(3))
+    lnb = dict(x=x, stats=st, gamma=gamma, skip=dy, dgamma=dg, dbeta=db, dx_colsum=dc)
+    add("gemm_bf16_kernel<256,0,0,5,0> dgrad dpre W1 + LayerNorm backward + residual gradient [49152 x 256, K=1024]",
+        lambda: ops.gemm(dh, w1t, ln_bwd=lnb), 3, flops=2.0 * M * H * D, key="dgrad_ff1_ln")
     add("gemm_bf16_kernel<256,0,0,0,1> QKV projection [49152 x 768, K=256]", lambda: ops.gemm(x, wqkv), 3,
         flops=2.0 * M * 3 * D * D, key="qkv_fwd")
     add("gemm_bf16_kernel<256,0,0,0,0> attention out-projection + residual [49152 x 256, K=256]",
         lambda: ops.gemm(x, wo, bias=b2, residual=dy), 3, flops=2.0 * M * D * D, key="out_proj")
-    add("ln_bwd_pipe_kernel LayerNorm backward + residual-gradient add [49152 x 256]",
-        lambda: ops.layernorm_bwd(dy, x, st, gamma, skip=dy), 6, nbytes=4.0 * M * D * 2 + M * 8, key="ln_bwd")
-    add("ln_fwd_pipe_kernel LayerNorm forward [49152 x 256]", lambda: ops.layernorm_fwd(x, gamma, beta), 3,
+    add("ln_bwd_pipe_kernel LayerNorm backward (final decoder norm; the six per-layer ones run in GEMM epilogues) [49152 x 256]",
+        lambda: ops.layernorm_bwd(dy, x, st, gamma, skip=dy), 1, nbytes=4.0 * M * D * 2 + M * 8, key="ln_bwd")
+    add("ln_fwd_pipe_kernel LayerNorm forward [49152 x 256]", lambda: ops.layernorm_fwd(x, gamma, beta), 4,
         nbytes=2.0 * M * D * 2 + M * 8, key="ln_fwd")
+    add("gemm_bf16_kernel<256,0,0,5,0> dgrad dqkv Wqkv + LayerNorm backward + residual gradient [49152 x 256, K=768]",
+        lambda: ops.gemm(qkv, wqkvt, ln_bwd=lnb), 3, flops=2.0 * M * 3 * D * D, key="dgrad_qkv_ln")
+    wot = wo.t().contiguous()
+    add("gemm_bf16_kernel<256,0,0,0,0> dgrad dO = dx Wo + delta = rowsum(dO * O) per head [49152 x 256, K=256]",
+        lambda: ops.gemm(dy, wot, dot_side=o, dot_out=delta), 3, flops=2.0 * M * D * D, key="out_proj_dgrad")
     rows.sort(key=lambda r: -r["share_of_step"])
     return rows
 

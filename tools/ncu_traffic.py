@@ -30,8 +30,14 @@ for r in rows[2:]:
     lines.append(f"{nm[:60]:60s} time={t:>12s} dram_rd={rd / 1e6:9.2f}MB dram_wr={wr / 1e6:9.2f}MB grid={r[col['launch__grid_size']]} {extra}")
     seq.append((nm, rd + wr))
 open("profiles/r02_ncu_top_kernels.txt", "w").write("\n".join(lines) + "\n")
-# the driver launches the table's kernels in this order (bench.per_kernel_roofline), 1 warm-up... launches each
-order = ["wgrad_ff", "wgrad_ff2", "wgrad_qkv", "ln_mlp_fwd_save", "attn_bwd", "attn_fwd", "dgrad_ff2", "dgrad_ff1", "qkv_fwd",
-         "out_proj", "ln_bwd", "ln_fwd"]
+# the driver (tools/ncu_top_kernels.py) launches the table's kernels in this order, 2 warm-up launches + 1 each: the
+# DRAM bytes of the LAST launch of every group of three is what bench.py reports as `traffic`
+order = ["wgrad_ff", "wgrad_ff2", "wgrad_qkv", "ln_mlp_fwd_save", "attn_bwd", "attn_fwd", "dgrad_ff2", "dgrad_ff1_ln", "qkv_fwd",
+         "out_proj", "ln_bwd", "ln_fwd", "dgrad_qkv_ln", "out_proj_dgrad"]
+if len(seq) == 3 * len(order) + 1 and "attn_fwd" in seq[0][0]:      # the set-up launch that produces O / LSE for the backward
+    seq = seq[1:]
+assert len(seq) == 3 * len(order), (len(seq), len(order))
+traffic = {k: seq[3 * i + 2][1] for i, k in enumerate(order)}
+json.dump(traffic, open("profiles/r02_ncu_traffic.json", "w"), indent=1)
 json.dump({"_launch_sequence": [[n, b] for n, b in seq], "_order": order}, open("profiles/r02_ncu_traffic_raw.json", "w"), indent=1)
 print("\n".join(lines))
